@@ -1,0 +1,190 @@
+/*
+ * ws3d_ops.h -- C ABI of libws3d_ops.so: the B200 (sm_100a) implementation of the
+ * WS3D PointNet++ set-abstraction / feature-propagation ops, roipool3d and iou3d.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one launcher that the
+ * reference's pybind wrappers call (file:line under the reference tree is cited on
+ * each declaration); arguments keep the reference's order and meaning, with two
+ * systematic differences:
+ *   - a trailing stream argument everywhere (the reference's iou3d/roipool3d
+ *     launchers use the legacy default stream; pass NULL for that behaviour);
+ *   - an int return value: 0 on success, otherwise a cudaError_t code (the
+ *     reference prints and calls exit(); see ws3d_last_error()).
+ *
+ * All pointers are DEVICE pointers to contiguous row-major arrays unless a
+ * parameter is explicitly named *_host.  float = IEEE binary32, int = int32.
+ * The caller owns and pre-initialises every output exactly as the reference's
+ * Python wrappers do (zero-filled idx for ball_query, 1e10-filled temp for FPS,
+ * zero-filled grads / pooled features / flags).  No entry point allocates device
+ * memory except the *_host convenience wrappers and ws3d_roipool3d / ws3d_nms*
+ * when called with workspace == NULL (they then use a cached per-device scratch
+ * buffer that is grown on demand and never shrunk).
+ *
+ * No torch types, no C++ types: bindable from ctypes / cgo / JNI / pybind alike.
+ */
+#ifndef WS3D_OPS_H_
+#define WS3D_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same object as cudaStream_t (struct CUstream_st *) */
+typedef struct CUstream_st *ws3d_stream_t;
+
+#define WS3D_ABI_VERSION 1
+
+/* Library identity / diagnostics ------------------------------------------- */
+int ws3d_abi_version(void);
+/* Human-readable text of the last failure on the calling thread ("" if none). */
+const char *ws3d_last_error(void);
+/* Number of kernels this library has launched since load (all threads). */
+uint64_t ws3d_launch_count(void);
+
+/* ---- pointnet2_cuda -------------------------------------------------------- */
+
+/* Replaces furthest_point_sampling_kernel_launcher
+ * (pointnet2_lib/pointnet2/src/sampling_gpu.h:26-27, sampling_gpu.cu:211-253).
+ * xyz (B,N,3), temp (B,N) running min-distance scratch (read at entry, final
+ * values written back; may be NULL = start from 1e10, nothing written),
+ * idx (B,M) int32.  Bit-exact index parity with the reference, including its
+ * block-size dependent tie-break. */
+int ws3d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                 ws3d_stream_t stream);
+
+/* Extension (fusion of sampling_gpu.cu:211 + :26): FPS that also emits the
+ * sampled coordinates new_xyz (B,M,3) from its epilogue, replacing the
+ * transpose + gather_points + transpose sequence of pointnet2_modules.py:30-35.
+ * new_xyz may be NULL. */
+int ws3d_furthest_point_sampling_gather(int b, int n, int m, const float *xyz, float *temp,
+                                        int *idx, float *new_xyz, ws3d_stream_t stream);
+
+/* Replaces gather_points_kernel_launcher_fast (sampling_gpu.h:12-13, sampling_gpu.cu:26-44).
+ * points (B,C,N), idx (B,M) -> out (B,C,M). */
+int ws3d_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                       float *out, ws3d_stream_t stream);
+
+/* Replaces gather_points_grad_kernel_launcher_fast (sampling_gpu.h:19-20, sampling_gpu.cu:65-84).
+ * grad_out (B,C,M), idx (B,M) -> grad_points (B,C,N) += (caller zero-fills). */
+int ws3d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                            const int *idx, float *grad_points, ws3d_stream_t stream);
+
+/* Replaces ball_query_kernel_launcher_fast (ball_query_gpu.h:12-13, ball_query_gpu.cu:48-67).
+ * NOTE the argument order: new_xyz (B,M,3) comes BEFORE xyz (B,N,3), as in the
+ * reference wrapper (ball_query.cpp:14-25).  idx (B,M,nsample) must be zero-filled
+ * by the caller; rows with no neighbour are left untouched. */
+int ws3d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                    const float *xyz, int *idx, ws3d_stream_t stream);
+
+/* Extension: ball_query for TWO radii over the same centres in one scan (the multi-scale
+ * grouping of PointnetSAModuleMSG, pointnet2_modules.py:37-38, queries the same new_xyz/xyz once
+ * per scale).  idx0 (B,M,nsample0), idx1 (B,M,nsample1), both zero-filled by the caller; each is
+ * identical to what ws3d_ball_query returns for its radius. */
+int ws3d_ball_query2(int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
+                     const float *new_xyz, const float *xyz, int *idx0, int *idx1, ws3d_stream_t stream);
+
+/* Replaces group_points_kernel_launcher_fast (group_points_gpu.h:13-14, group_points_gpu.cu:69-86).
+ * points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample). */
+int ws3d_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                      const int *idx, float *out, ws3d_stream_t stream);
+
+/* Replaces group_points_grad_kernel_launcher_fast (group_points_gpu.h:19-20, group_points_gpu.cu:27-45). */
+int ws3d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                           const int *idx, float *grad_points, ws3d_stream_t stream);
+
+/* Extension: QueryAndGroup.forward (pointnet2_utils.py:241-264) as one pass per
+ * scale: ball_query -> gather xyz -> subtract centre -> gather features -> concat,
+ * written once.  xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or NULL,
+ * out (B, 3*use_xyz + C, M, nsample), idx_out (B,M,nsample) zero-filled or NULL.
+ * Results are identical to the unfused sequence. */
+int ws3d_query_and_group(int b, int n, int m, int c, float radius, int nsample, int use_xyz,
+                         const float *xyz, const float *new_xyz, const float *features,
+                         float *out, int *idx_out, ws3d_stream_t stream);
+
+/* The grouping half of the above for a precomputed idx (B,M,nsample): gathers xyz (minus the
+ * centre) and every feature channel into out (B, 3*use_xyz + C, M, nsample) in one pass
+ * (pointnet2_utils.py:250-257). */
+int ws3d_group_concat(int b, int n, int m, int c, int nsample, int use_xyz, const float *xyz,
+                      const float *new_xyz, const float *features, const int *idx, float *out,
+                      ws3d_stream_t stream);
+
+/* Replaces three_nn_kernel_launcher_fast (interpolate_gpu.h:13-14, interpolate_gpu.cu:55-74).
+ * unknown (B,N,3), known (B,M,3) -> dist2 (B,N,3) SQUARED distances, idx (B,N,3). */
+int ws3d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                  int *idx, ws3d_stream_t stream);
+
+/* Replaces three_interpolate_kernel_launcher_fast (interpolate_gpu.h:20-21, interpolate_gpu.cu:99-117).
+ * points (B,C,M), idx (B,N,3), weight (B,N,3) -> out (B,C,N). */
+int ws3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                           const float *weight, float *out, ws3d_stream_t stream);
+
+/* Replaces three_interpolate_grad_kernel_launcher_fast (interpolate_gpu.h:27-28, interpolate_gpu.cu:144-160).
+ * grad_out (B,C,N) -> grad_points (B,C,M) += (caller zero-fills). */
+int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                const float *weight, float *grad_points, ws3d_stream_t stream);
+
+/* ---- iou3d_cuda ------------------------------------------------------------ */
+
+/* Replaces boxesoverlapLauncher (lib/utils/iou3d/src/iou3d.cpp:26, iou3d_kernel.cu:354-363).
+ * boxes_a (Na,5), boxes_b (Nb,5) [x1,y1,x2,y2,ry] -> ans (Na,Nb) overlap area. */
+int ws3d_boxes_overlap_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b,
+                           float *ans, ws3d_stream_t stream);
+
+/* Replaces boxesioubevLauncher (iou3d.cpp:27, iou3d_kernel.cu:365-372). */
+int ws3d_boxes_iou_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b,
+                       float *ans, ws3d_stream_t stream);
+
+/* Bytes of device scratch ws3d_nms / ws3d_nms_normal need for boxes_num boxes. */
+size_t ws3d_nms_workspace_bytes(int boxes_num);
+
+/* Replaces nmsLauncher + the host greedy scan (iou3d.cpp:73-121, iou3d_kernel.cu:374-380)
+ * with an all-device pipeline.  boxes (N,5) sorted by descending score.
+ * keep (N) int64 DEVICE buffer receives the kept indices in ascending order,
+ * num_keep (1) int32 DEVICE receives their count.  workspace: device scratch of
+ * ws3d_nms_workspace_bytes(N) bytes, or NULL to use the library's cached scratch. */
+int ws3d_nms(const float *boxes, int boxes_num, float nms_overlap_thresh, int64_t *keep,
+             int *num_keep, void *workspace, ws3d_stream_t stream);
+
+/* Same for nmsNormalLauncher (iou3d.cpp:123-171, iou3d_kernel.cu:382-388): axis-aligned IoU. */
+int ws3d_nms_normal(const float *boxes, int boxes_num, float nms_overlap_thresh, int64_t *keep,
+                    int *num_keep, void *workspace, ws3d_stream_t stream);
+
+/* Reference-signature convenience: nms_gpu(boxes, keep_cpu_int64, thresh) -> num kept
+ * (iou3d.cpp:73).  keep_host is HOST memory (N int64).  Synchronises the stream.
+ * Returns the number kept (>= 0) or -(cudaError_t). */
+int ws3d_nms_host(const float *boxes, int boxes_num, float nms_overlap_thresh,
+                  int64_t *keep_host, ws3d_stream_t stream);
+int ws3d_nms_normal_host(const float *boxes, int boxes_num, float nms_overlap_thresh,
+                         int64_t *keep_host, ws3d_stream_t stream);
+
+/* ---- roipool3d_cuda -------------------------------------------------------- */
+
+/* Replaces roipool3dLauncher (lib/utils/roipool3d/src/roipool3d.cpp:12-13,
+ * roipool3d_kernel.cu:209-237) -- and roipool3dLauncher_slow (:197-207), whose
+ * results are identical.  xyz (B,N,3), boxes3d (B,M,7) [x,y,z,h,w,l,ry],
+ * pts_feature (B,N,C) -> pooled_features (B,M,S,3+C) and pooled_empty_flag (B,M),
+ * both zero-filled by the caller.  No (B,N,M) flag tensor is materialised. */
+int ws3d_roipool3d(int batch_size, int pts_num, int boxes_num, int feature_in_len,
+                   int sampled_pts_num, const float *xyz, const float *boxes3d,
+                   const float *pts_feature, float *pooled_features, int *pooled_empty_flag,
+                   ws3d_stream_t stream);
+
+/* Host (CPU) entry points of the reference module, HOST pointers throughout.
+ * Replaces pts_in_boxes3d_cpu (roipool3d.cpp:97-125): pts_flag (M,N) int64 <- 0/1. */
+int ws3d_pts_in_boxes3d_cpu(int64_t *pts_flag_host, const float *pts_host, const float *boxes3d_host,
+                            int boxes_num, int pts_num);
+
+/* Replaces roipool3d_cpu (roipool3d.cpp:127-197): pooled_pts (M,S,3), pooled_features (M,S,C),
+ * pooled_empty_flag (M) int64 (cleared here, like the reference's memset). */
+int ws3d_roipool3d_cpu(const float *pts_host, const float *boxes3d_host, const float *pts_feature_host,
+                       float *pooled_pts_host, float *pooled_features_host,
+                       int64_t *pooled_empty_flag_host, int boxes_num, int pts_num, int feature_len,
+                       int sampled_pts_num);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WS3D_OPS_H_ */

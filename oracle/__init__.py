@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE ONLY: numpy front-end of the CPU oracle (oracle/ws3d_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package.  The product package (ws3d_b200/) never does.
+
+Each function mirrors one reference entry point (file:line cited in ws3d_oracle.c),
+allocates its outputs exactly as the reference's Python wrappers do (zero-filled
+idx for ball_query, 1e10-filled temp for FPS, ...) and returns numpy arrays.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libws3d_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile libws3d_oracle.so in place (gcc, seconds)."""
+    src = os.path.join(_HERE, "ws3d_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libws3d_oracle.so"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.oracle_nms.restype = ctypes.c_int
+        _lib.oracle_nms_normal.restype = ctypes.c_int
+        _lib.oracle_opt_n_threads.restype = ctypes.c_int
+        _lib.oracle_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def num_threads() -> int:
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().oracle_set_num_threads(int(n))
+
+
+def opt_n_threads(n: int) -> int:
+    return lib().oracle_opt_n_threads(int(n))
+
+
+def furthest_point_sample(xyz, npoint, return_temp=False):
+    xyz = _f(xyz)
+    b, n, _ = xyz.shape
+    temp = np.full((b, n), 1e10, dtype=np.float32)
+    idx = np.zeros((b, npoint), dtype=np.int32)
+    lib().oracle_furthest_point_sampling(b, n, int(npoint), _p(xyz), _p(temp), _p(idx))
+    return (idx, temp) if return_temp else idx
+
+
+def gather_operation(features, idx):
+    features, idx = _f(features), _i(idx)
+    b, c, n = features.shape
+    m = idx.shape[1]
+    out = np.empty((b, c, m), dtype=np.float32)
+    lib().oracle_gather_points(b, c, n, m, _p(features), _p(idx), _p(out))
+    return out
+
+
+def gather_operation_grad(grad_out, idx, n):
+    grad_out, idx = _f(grad_out), _i(idx)
+    b, c, m = grad_out.shape
+    g = np.zeros((b, c, n), dtype=np.float32)
+    lib().oracle_gather_points_grad(b, c, int(n), m, _p(grad_out), _p(idx), _p(g))
+    return g
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    xyz, new_xyz = _f(xyz), _f(new_xyz)
+    b, n, _ = xyz.shape
+    m = new_xyz.shape[1]
+    idx = np.zeros((b, m, nsample), dtype=np.int32)
+    lib().oracle_ball_query(b, n, m, ctypes.c_float(radius), int(nsample), _p(new_xyz), _p(xyz), _p(idx))
+    return idx
+
+
+def grouping_operation(features, idx):
+    features, idx = _f(features), _i(idx)
+    b, c, n = features.shape
+    _, m, k = idx.shape
+    out = np.empty((b, c, m, k), dtype=np.float32)
+    lib().oracle_group_points(b, c, n, m, k, _p(features), _p(idx), _p(out))
+    return out
+
+
+def grouping_operation_grad(grad_out, idx, n):
+    grad_out, idx = _f(grad_out), _i(idx)
+    b, c, m, k = grad_out.shape
+    g = np.zeros((b, c, n), dtype=np.float32)
+    lib().oracle_group_points_grad(b, c, int(n), m, k, _p(grad_out), _p(idx), _p(g))
+    return g
+
+
+def three_nn(unknown, known):
+    """Returns (dist2, idx): SQUARED distances like the native entry point
+    (the reference's Python wrapper applies sqrt afterwards)."""
+    unknown, known = _f(unknown), _f(known)
+    b, n, _ = unknown.shape
+    m = known.shape[1]
+    dist2 = np.empty((b, n, 3), dtype=np.float32)
+    idx = np.empty((b, n, 3), dtype=np.int32)
+    lib().oracle_three_nn(b, n, m, _p(unknown), _p(known), _p(dist2), _p(idx))
+    return dist2, idx
+
+
+def three_interpolate(features, idx, weight):
+    features, idx, weight = _f(features), _i(idx), _f(weight)
+    b, c, m = features.shape
+    n = idx.shape[1]
+    out = np.empty((b, c, n), dtype=np.float32)
+    lib().oracle_three_interpolate(b, c, m, n, _p(features), _p(idx), _p(weight), _p(out))
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    grad_out, idx, weight = _f(grad_out), _i(idx), _f(weight)
+    b, c, n = grad_out.shape
+    g = np.zeros((b, c, m), dtype=np.float32)
+    lib().oracle_three_interpolate_grad(b, c, n, int(m), _p(grad_out), _p(idx), _p(weight), _p(g))
+    return g
+
+
+def query_and_group(radius, nsample, xyz, new_xyz, features=None, use_xyz=True):
+    """pointnet2_utils.py:241-264 (QueryAndGroup.forward) composed from the oracle ops."""
+    idx = ball_query(radius, nsample, xyz, new_xyz)
+    xyz_t = np.ascontiguousarray(np.transpose(_f(xyz), (0, 2, 1)))
+    grouped_xyz = grouping_operation(xyz_t, idx)
+    grouped_xyz = grouped_xyz - np.transpose(_f(new_xyz), (0, 2, 1))[..., None]
+    if features is None:
+        return grouped_xyz
+    g = grouping_operation(features, idx)
+    return np.concatenate([grouped_xyz, g], axis=1) if use_xyz else g
+
+
+def boxes_overlap_bev(boxes_a, boxes_b):
+    a, b = _f(boxes_a), _f(boxes_b)
+    out = np.zeros((a.shape[0], b.shape[0]), dtype=np.float32)
+    lib().oracle_boxes_overlap_bev(a.shape[0], _p(a), b.shape[0], _p(b), _p(out))
+    return out
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    a, b = _f(boxes_a), _f(boxes_b)
+    out = np.zeros((a.shape[0], b.shape[0]), dtype=np.float32)
+    lib().oracle_boxes_iou_bev(a.shape[0], _p(a), b.shape[0], _p(b), _p(out))
+    return out
+
+
+def nms(boxes_sorted, thresh):
+    """boxes already sorted by descending score; returns int64 keep indices."""
+    bx = _f(boxes_sorted)
+    keep = np.zeros(bx.shape[0], dtype=np.int64)
+    n = lib().oracle_nms(_p(bx), bx.shape[0], ctypes.c_float(thresh), _p(keep))
+    return keep[:n]
+
+
+def nms_normal(boxes_sorted, thresh):
+    bx = _f(boxes_sorted)
+    keep = np.zeros(bx.shape[0], dtype=np.int64)
+    n = lib().oracle_nms_normal(_p(bx), bx.shape[0], ctypes.c_float(thresh), _p(keep))
+    return keep[:n]
+
+
+def roipool3d(pts, pts_feature, boxes3d, sampled_pt_num=512):
+    """Native-level semantics (no box enlargement): returns (pooled, empty_flag)."""
+    pts, pts_feature, boxes3d = _f(pts), _f(pts_feature), _f(boxes3d)
+    b, n, _ = pts.shape
+    m = boxes3d.shape[1]
+    c = pts_feature.shape[2]
+    pooled = np.zeros((b, m, sampled_pt_num, 3 + c), dtype=np.float32)
+    flag = np.zeros((b, m), dtype=np.int32)
+    lib().oracle_roipool3d(b, n, m, c, int(sampled_pt_num), _p(pts), _p(boxes3d), _p(pts_feature),
+                           _p(pooled), _p(flag))
+    return pooled, flag
+
+
+def pts_in_boxes3d_cpu(pts, boxes3d):
+    pts, boxes3d = _f(pts), _f(boxes3d)
+    flag = np.zeros((boxes3d.shape[0], pts.shape[0]), dtype=np.int64)
+    lib().oracle_pts_in_boxes3d_cpu(_p(flag), _p(pts), _p(boxes3d), boxes3d.shape[0], pts.shape[0])
+    return flag
+
+
+def roipool3d_cpu(pts, boxes3d, pts_feature, sampled_pt_num):
+    pts, boxes3d, pts_feature = _f(pts), _f(boxes3d), _f(pts_feature)
+    m, c = boxes3d.shape[0], pts_feature.shape[1]
+    pooled_pts = np.zeros((m, sampled_pt_num, 3), dtype=np.float32)
+    pooled_feat = np.zeros((m, sampled_pt_num, c), dtype=np.float32)
+    flag = np.zeros(m, dtype=np.int64)
+    lib().oracle_roipool3d_cpu(_p(pts), _p(boxes3d), _p(pts_feature), _p(pooled_pts), _p(pooled_feat),
+                               _p(flag), m, pts.shape[0], c, int(sampled_pt_num))
+    return pooled_pts, pooled_feat, flag

@@ -1,0 +1,433 @@
+// Furthest point sampling for B200.
+//
+// Replaces pointnet2_lib/pointnet2/src/sampling_gpu.cu:93-253 (one 1024-thread CTA per
+// cloud, xyz and the running min-distance re-read from global memory every iteration,
+// ten __syncthreads per iteration).
+//
+// Design: FPS is a latency chain of m-1 dependent iterations, not a bandwidth problem.
+//   * a cloud is split over a thread-block CLUSTER of C CTAs (C*B ~ number of SMs);
+//   * every thread keeps its P points (x, y, z, running min-distance, tie key) in
+//     REGISTERS for the whole kernel: after the first load nothing touches HBM/L2 again;
+//   * per iteration: P distance updates per thread, a warp arg-max with two redux.sync,
+//     one __syncthreads, warp 0 picks the CTA winner and posts {value, key, xyz} into the
+//     shared memory of every CTA of the cluster with st.async (DSMEM) signalling an
+//     mbarrier there; every warp then picks the cluster winner from C records.
+//   * the sampled coordinates are emitted from the same loop (fused gather).
+//
+// Bit-exactness: the reference's winner is the maximum running distance; ties go to the
+// smallest bit-reversed (k mod BS) -- its shared-memory tree keeps the lower slot of each
+// pair -- and then to the smallest k (strict '>' inside a thread), BS = opt_n_threads(n).
+// That order is encoded as a 32-bit key (smaller wins) so any thread/CTA decomposition
+// reproduces it.  Distances use the reference's rounding order (sqdist_ref).
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace ws3d {
+namespace {
+
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+constexpr int kMaxCluster = 16;
+
+// key(k): top L bits = bit-reversed (k mod 2^L), low 32-L bits = k >> L.
+__host__ __device__ __forceinline__ uint32_t brev32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __brev(v);
+#else
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+  return (v >> 16) | (v << 16);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t fps_key(uint32_t k, int L) {
+  if (L == 0) return k;
+  const uint32_t lowmask = 0xFFFFFFFFu >> L;
+  return (brev32(k) & ~lowmask) | (k >> L);
+}
+__host__ __device__ __forceinline__ uint32_t fps_unkey(uint32_t key, int L) {
+  if (L == 0) return key;
+  const uint32_t lowmask = 0xFFFFFFFFu >> L;
+  return ((key & lowmask) << L) | brev32(key & ~lowmask);
+}
+
+// ---- cluster / mbarrier / DSMEM primitives (raw PTX) --------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a),
+               "r"(rbar)
+               : "memory");
+}
+
+struct __align__(16) Rec {  // one candidate: 20 payload bytes in a 32-byte slot
+  int v;                    // running-distance bits (>= 0 for real points)
+  uint32_t key;
+  float x, y;
+  float z;
+  float pad[3];
+};
+
+struct FpsParams {
+  int n, m, L;       // points, samples, log2(reference block size)
+  int log2T;         // blockDim.x == 1 << log2T
+  const float *xyz;  // (B,N,3)
+  float *temp;       // (B,N) or null
+  int *idx;          // (B,M)
+  float *new_xyz;    // (B,M,3) or null
+};
+
+template <int P>
+__device__ __forceinline__ void sort_by_key(uint32_t (&key)[P], float (&x)[P], float (&y)[P], float (&z)[P],
+                                            float (&t)[P]) {
+  // odd-even transposition network on registers (fully unrolled, init-time only)
+#pragma unroll
+  for (int round = 0; round < P; ++round) {
+#pragma unroll
+    for (int i = (round & 1); i + 1 < P; i += 2) {
+      if (key[i + 1] < key[i]) {
+        uint32_t tk = key[i]; key[i] = key[i + 1]; key[i + 1] = tk;
+        float f;
+        f = x[i]; x[i] = x[i + 1]; x[i + 1] = f;
+        f = y[i]; y[i] = y[i + 1]; y[i + 1] = f;
+        f = z[i]; z[i] = z[i + 1]; z[i + 1] = f;
+        f = t[i]; t[i] = t[i + 1]; t[i + 1] = f;
+      }
+    }
+  }
+}
+
+// One cluster of C CTAs (C == 1 when !CLUSTER) per cloud; grid = (C, B).
+template <int P, bool CLUSTER>
+__global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
+  extern __shared__ float4 s_pts[];                 // P*T own points, slot = p*T + tid (load order)
+  __shared__ int2 s_wrec[2][32];                    // per-warp candidate {v, key}
+  __shared__ Rec s_crec[2][kMaxCluster];            // per-CTA candidates of the cluster
+  __shared__ __align__(8) unsigned long long s_bar[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = blockDim.x, nwarps = T >> 5;
+  const uint32_t rank = CLUSTER ? cluster_ctarank() : 0u;
+  const uint32_t C = CLUSTER ? cluster_nctarank() : 1u;
+  const int CT = (int)C * T;
+  const int g = (int)rank * T + tid;
+  const int n = prm.n, m = prm.m, L = prm.L;
+  const size_t cloud = blockIdx.y;
+  const float *xyz = prm.xyz + cloud * (size_t)n * 3;
+  float *temp = prm.temp ? prm.temp + cloud * (size_t)n : nullptr;
+  int *idx = prm.idx + cloud * (size_t)m;
+  float *new_xyz = prm.new_xyz ? prm.new_xyz + cloud * (size_t)m * 3 : nullptr;
+
+  const uint32_t bar_base = smem_u32(&s_bar[0]);
+  if (CLUSTER) {
+    if (tid == 0) {
+      mbar_init(bar_base, 1);
+      mbar_init(bar_base + 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+
+  float x[P], y[P], z[P], t[P];
+  uint32_t key[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int k = p * CT + g;
+    if (k < n) {
+      x[p] = __ldg(xyz + (size_t)k * 3 + 0);
+      y[p] = __ldg(xyz + (size_t)k * 3 + 1);
+      z[p] = __ldg(xyz + (size_t)k * 3 + 2);
+      t[p] = temp ? temp[k] : 1e10f;
+      key[p] = fps_key((uint32_t)k, L);
+    } else {
+      x[p] = y[p] = z[p] = 0.f;
+      t[p] = -1.f;  // never beats a real point (real running distances are >= 0)
+      key[p] = kNoKey;
+    }
+    s_pts[p * T + tid] = make_float4(x[p], y[p], z[p], 0.f);
+  }
+  // strict '>' below must meet a thread's points in ascending key order
+  sort_by_key<P>(key, x, y, z, t);
+
+  float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // idx[0] = 0
+  if (g == 0 && m > 0) {
+    idx[0] = 0;
+    if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
+  }
+  if (CLUSTER) cluster_sync_all(); else __syncthreads();
+
+  for (int it = 0; it + 1 < m; ++it) {
+    const int par = it & 1;
+    const uint32_t bar = bar_base + 8u * (uint32_t)par;
+    float best = -1.f;
+    uint32_t bkey = kNoKey;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const float d = sqdist_ref(x[p] - cx, y[p] - cy, z[p] - cz);
+      t[p] = fminf(d, t[p]);
+      if (t[p] > best) { best = t[p]; bkey = key[p]; }
+    }
+    const int vb = __float_as_int(best);
+    const int wv = __reduce_max_sync(0xFFFFFFFFu, vb);
+    const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, vb == wv ? bkey : kNoKey);
+    if (lane == 0) s_wrec[par][warp] = make_int2(wv, (int)wk);
+    __syncthreads();
+
+    if (warp == 0) {
+      int2 r = lane < nwarps ? s_wrec[par][lane] : make_int2(INT_MIN, (int)kNoKey);
+      const int bv = __reduce_max_sync(0xFFFFFFFFu, r.x);
+      const uint32_t bk = __reduce_min_sync(0xFFFFFFFFu, r.x == bv ? (uint32_t)r.y : kNoKey);
+      float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bk != kNoKey) {
+        const int k = (int)fps_unkey(bk, L);
+        const int p = k / CT, gg = k - p * CT;
+        pt = s_pts[p * T + (gg - (int)rank * T)];
+      }
+      if (CLUSTER) {
+        if (lane == 0) mbar_expect_tx(bar, C * 20u);
+        if (lane < (int)C) {
+          const uint32_t dst = mapa(smem_u32(&s_crec[par][rank]), (uint32_t)lane);
+          const uint32_t rbar = mapa(bar, (uint32_t)lane);
+          st_async_v4(dst, (uint32_t)bv, bk, __float_as_uint(pt.x), __float_as_uint(pt.y), rbar);
+          st_async_b32(dst + 16, __float_as_uint(pt.z), rbar);
+        }
+      } else if (lane == 0) {
+        Rec rc;
+        rc.v = bv; rc.key = bk; rc.x = pt.x; rc.y = pt.y; rc.z = pt.z;
+        s_crec[par][0] = rc;
+      }
+    }
+
+    uint32_t win_key;
+    if (CLUSTER) {
+      mbar_wait(bar, (uint32_t)(it >> 1) & 1u);
+      int v = INT_MIN;
+      uint32_t kk = kNoKey;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (lane < (int)C) {
+        const Rec &rc = s_crec[par][lane];
+        v = rc.v; kk = rc.key; rx = rc.x; ry = rc.y; rz = rc.z;
+      }
+      const int bv = __reduce_max_sync(0xFFFFFFFFu, v);
+      win_key = __reduce_min_sync(0xFFFFFFFFu, v == bv ? kk : kNoKey);
+      const int src = __ffs(__ballot_sync(0xFFFFFFFFu, v == bv && kk == win_key)) - 1;
+      cx = __shfl_sync(0xFFFFFFFFu, rx, src);
+      cy = __shfl_sync(0xFFFFFFFFu, ry, src);
+      cz = __shfl_sync(0xFFFFFFFFu, rz, src);
+    } else {
+      __syncthreads();
+      const Rec &rc = s_crec[par][0];
+      win_key = rc.key; cx = rc.x; cy = rc.y; cz = rc.z;
+    }
+    if (g == 0) {
+      idx[it + 1] = (int)fps_unkey(win_key, L);
+      if (new_xyz) {
+        new_xyz[(size_t)(it + 1) * 3 + 0] = cx;
+        new_xyz[(size_t)(it + 1) * 3 + 1] = cy;
+        new_xyz[(size_t)(it + 1) * 3 + 2] = cz;
+      }
+    }
+  }
+
+  if (temp) {
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+      if (key[p] != kNoKey) temp[fps_unkey(key[p], L)] = t[p];
+  }
+  if (CLUSTER) cluster_sync_all();  // nobody leaves while a peer could still post to it
+}
+
+// Any-size fallback: one CTA per cloud, running distances in global memory (L2-resident).
+__global__ void __launch_bounds__(1024, 1) fps_generic_kernel(FpsParams prm) {
+  __shared__ int2 s_wrec[32];
+  __shared__ int s_win[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, nwarps = T >> 5;
+  const int n = prm.n, m = prm.m, L = prm.L;
+  const size_t cloud = blockIdx.x;
+  const float *xyz = prm.xyz + cloud * (size_t)n * 3;
+  float *temp = prm.temp + cloud * (size_t)n;  // required here
+  int *idx = prm.idx + cloud * (size_t)m;
+  float *new_xyz = prm.new_xyz ? prm.new_xyz + cloud * (size_t)m * 3 : nullptr;
+  int old = 0;
+  if (tid == 0 && m > 0) idx[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const float cx = xyz[(size_t)old * 3], cy = xyz[(size_t)old * 3 + 1], cz = xyz[(size_t)old * 3 + 2];
+    if (tid == 0 && new_xyz) {
+      new_xyz[(size_t)(j - 1) * 3] = cx; new_xyz[(size_t)(j - 1) * 3 + 1] = cy; new_xyz[(size_t)(j - 1) * 3 + 2] = cz;
+    }
+    float best = -1.f;
+    uint32_t bkey = kNoKey;
+    for (int k = tid; k < n; k += T) {
+      const float d = sqdist_ref(xyz[(size_t)k * 3] - cx, xyz[(size_t)k * 3 + 1] - cy, xyz[(size_t)k * 3 + 2] - cz);
+      const float d2 = fminf(d, temp[k]);
+      temp[k] = d2;
+      const uint32_t kk = fps_key((uint32_t)k, L);
+      if (d2 > best || (d2 == best && kk < bkey)) { best = d2; bkey = kk; }
+    }
+    const int vb = __float_as_int(best);
+    const int wv = __reduce_max_sync(0xFFFFFFFFu, vb);
+    const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, vb == wv ? bkey : kNoKey);
+    if (lane == 0) s_wrec[warp] = make_int2(wv, (int)wk);
+    __syncthreads();
+    if (warp == 0) {
+      int2 r = lane < nwarps ? s_wrec[lane] : make_int2(INT_MIN, (int)kNoKey);
+      const int bv = __reduce_max_sync(0xFFFFFFFFu, r.x);
+      const uint32_t bk = __reduce_min_sync(0xFFFFFFFFu, r.x == bv ? (uint32_t)r.y : kNoKey);
+      if (lane == 0) s_win[j & 1] = (int)fps_unkey(bk, L);
+    }
+    __syncthreads();
+    old = s_win[j & 1];
+    if (tid == 0) idx[j] = old;
+  }
+  if (tid == 0 && new_xyz && m > 0) {
+    new_xyz[(size_t)(m - 1) * 3] = xyz[(size_t)old * 3];
+    new_xyz[(size_t)(m - 1) * 3 + 1] = xyz[(size_t)old * 3 + 1];
+    new_xyz[(size_t)(m - 1) * 3 + 2] = xyz[(size_t)old * 3 + 2];
+  }
+}
+
+__global__ void fill_kernel(float *p, size_t n, float v) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// pointnet2_lib/pointnet2/src/cuda_utils.h:10-14 -- same expression, same libm.
+int ref_block_size(int work_size) {
+  const int pow_2 = (int)(log((double)work_size) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 1024) t = 1024;
+  if (t < 1) t = 1;
+  return t;
+}
+int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+template <int P, bool CLUSTER>
+int launch_cluster(const FpsParams &prm, int b, int C, int T, cudaStream_t stream) {
+  auto kern = fps_cluster_kernel<P, CLUSTER>;
+  const size_t smem = (size_t)P * T * sizeof(float4);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && C > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) { set_error("fps: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C, (unsigned)b, 1);
+  cfg.blockDim = dim3((unsigned)T, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CLUSTER ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, prm);
+  if (e != cudaSuccess) { set_error("fps: launch (P=%d C=%d T=%d): %s", P, C, T, cudaGetErrorString(e)); return (int)e; }
+  return check_launch("furthest_point_sampling");
+}
+
+int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || (b > 0 && n > 0 && m > 0 && (!xyz || !idx))) return fail_arg("furthest_point_sampling");
+  if (b == 0 || m == 0) return 0;
+  if (n == 0) return fail_arg("furthest_point_sampling (n == 0 with m > 0)");
+  if (b > 65535) {  // gridDim.y limit: split the batch
+    for (int b0 = 0; b0 < b; b0 += 32768) {
+      const int bb = (b - b0 < 32768) ? b - b0 : 32768;
+      int rc = fps_dispatch(bb, n, m, xyz + (size_t)b0 * n * 3, temp ? temp + (size_t)b0 * n : nullptr,
+                            idx + (size_t)b0 * m, new_xyz ? new_xyz + (size_t)b0 * m * 3 : nullptr, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  FpsParams prm;
+  prm.n = n; prm.m = m; prm.L = ilog2(ref_block_size(n));
+  prm.xyz = xyz; prm.temp = temp; prm.idx = idx; prm.new_xyz = new_xyz;
+
+  // --- decomposition: C CTAs per cloud, T threads per CTA, P points per thread
+  int cmax = kNumSMs / (b < 1 ? 1 : b);
+  cmax = cmax >= 16 ? 16 : cmax >= 8 ? 8 : cmax >= 4 ? 4 : cmax >= 2 ? 2 : 1;
+  if (cmax > 8) cmax = env_int("WS3D_FPS_ALLOW16", 0) ? 16 : 8;
+  int C = pow2_ceil(ceil_div(n, 1024));  // no point in splitting below ~1k points per CTA
+  if (C > cmax) C = cmax;
+  while (ceil_div(n, C) > 8 * 1024 && C < 8) C <<= 1;  // registers: P <= 8 at T = 1024
+  C = env_int("WS3D_FPS_C", C);
+  int npc = ceil_div(n, C);
+  int T = pow2_ceil(ceil_div(npc, env_int("WS3D_FPS_PPT", 4)));
+  if (T < 32) T = 32;
+  if (T > 1024) T = 1024;
+  T = env_int("WS3D_FPS_T", T);
+  int P = pow2_ceil(ceil_div(npc, T));
+  prm.log2T = ilog2(T);
+
+  const bool ok = (C >= 1 && C <= kMaxCluster && (C & (C - 1)) == 0 && T >= 32 && T <= 1024 && (T & (T - 1)) == 0 &&
+                   P <= 8 && (long long)P * T * C >= n);
+  if (!ok) {
+    // generic path needs the scratch array
+    float *tp = temp;
+    if (!tp) {
+      tp = (float *)scratch((size_t)b * n * sizeof(float), 0);
+      if (!tp) return (int)cudaErrorMemoryAllocation;
+      const size_t tot = (size_t)b * n;
+      fill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(tp, tot, 1e10f);
+      int rc = check_launch("fps fill");
+      if (rc) return rc;
+    }
+    prm.temp = tp;
+    fps_generic_kernel<<<b, 1024, 0, stream>>>(prm);
+    return check_launch("furthest_point_sampling (generic)");
+  }
+#define WS3D_FPS_CASE(PP)                                                          \
+  case PP:                                                                         \
+    return C > 1 ? launch_cluster<PP, true>(prm, b, C, T, stream)                  \
+                 : launch_cluster<PP, false>(prm, b, C, T, stream);
+  switch (P) {
+    WS3D_FPS_CASE(1)
+    WS3D_FPS_CASE(2)
+    WS3D_FPS_CASE(4)
+    WS3D_FPS_CASE(8)
+  }
+#undef WS3D_FPS_CASE
+  return fail_arg("furthest_point_sampling (no kernel for P)");
+}
+
+}  // namespace
+}  // namespace ws3d
+
+WS3D_API int ws3d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                          ws3d_stream_t stream) {
+  return ws3d::fps_dispatch(b, n, m, xyz, temp, idx, nullptr, ws3d::to_stream(stream));
+}
+
+WS3D_API int ws3d_furthest_point_sampling_gather(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                                 float *new_xyz, ws3d_stream_t stream) {
+  return ws3d::fps_dispatch(b, n, m, xyz, temp, idx, new_xyz, ws3d::to_stream(stream));
+}

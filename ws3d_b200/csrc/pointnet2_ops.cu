@@ -1,0 +1,458 @@
+// ball_query, group/gather (+grad), three_nn, three_interpolate (+grad) for B200.
+//
+// Replaces pointnet2_lib/pointnet2/src/{ball_query_gpu,group_points_gpu,interpolate_gpu}.cu and
+// the gather kernels of sampling_gpu.cu.  The reference kernels are thread-per-query scans that
+// stream the whole cloud through L1/L2 per thread and thread-per-output-element gathers that
+// re-read idx once per channel.  Here:
+//   * ball_query: the cloud (<= 18432 points, 216 KB) is staged ONCE per CTA into shared memory by
+//     TMA bulk copies (cp.async.bulk + mbarrier); one WARP per query scans it 32 points per step
+//     (packed xyz, stride-3 words: bank-conflict free), hit lanes are compacted in index order by
+//     ballot + popc, and the warp stops at the K-th hit.  Queries are handed to warps dynamically.
+//     Up to two radii are scanned in one pass (multi-scale grouping shares the distance).
+//   * group/gather/interpolate: idx (and weights) are loaded once per thread and reused across
+//     all channels; stores are 16-byte wide and coalesced.
+//   * three_nn: known points staged in shared memory as float4, thread per unknown point.
+// Index-producing ops are bit-exact with the reference (same rounding order, same tie rules).
+#include <limits.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace ws3d {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// ball_query
+constexpr int kBqMaxChunkPts = 18432;  // 216 KB of packed xyz
+
+template <int NR>
+struct BqParams {
+  int n, m;
+  float r2[NR];
+  int nsample[NR];
+  const float *new_xyz;  // (B,M,3)
+  const float *xyz;      // (B,N,3)
+  int *idx[NR];          // (B,M,nsample[r]) zero-filled by the caller
+  int q_per_cta;
+};
+
+template <int NR>
+__global__ void __launch_bounds__(1024, 1) ball_query_kernel(BqParams<NR> prm) {
+  extern __shared__ __align__(16) float s_xyz[];  // n*3 packed
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_next;
+  const int lane = threadIdx.x & 31;
+  const int n = prm.n, m = prm.m;
+  const size_t cloud = blockIdx.y;
+  const int q0 = blockIdx.x * prm.q_per_cta;
+  const int q1 = min(m, q0 + prm.q_per_cta);
+  if (q0 >= q1) return;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_next = 0;
+  }
+  __syncthreads();
+  stage_floats(s_xyz, prm.xyz + cloud * (size_t)n * 3, n * 3, &s_bar, 0);
+
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = q0 + atomicAdd(&s_next, 1);
+    q = __shfl_sync(0xFFFFFFFFu, q, 0);
+    if (q >= q1) break;
+    const float *qp = prm.new_xyz + (cloud * (size_t)m + q) * 3;
+    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    int cnt[NR], first[NR];
+    int *row[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      cnt[r] = 0; first[r] = 0;
+      row[r] = prm.idx[r] + (cloud * (size_t)m + q) * prm.nsample[r];
+    }
+    for (int base = 0; base < n; base += 128) {
+      float d2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = base + u * 32 + lane;
+        if (k < n) {
+          const float x = s_xyz[k * 3], y = s_xyz[k * 3 + 1], z = s_xyz[k * 3 + 2];
+          d2[u] = sqdist_ref(qx - x, qy - y, qz - z);
+        } else {
+          d2[u] = __int_as_float(0x7f800000);  // +inf: never inside
+        }
+      }
+      bool all_full = true;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int K = prm.nsample[r];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (cnt[r] < K) {
+            const bool hit = d2[u] < prm.r2[r];
+            const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
+            if (hits) {
+              const int k = base + u * 32 + lane;
+              if (cnt[r] == 0) first[r] = base + u * 32 + __ffs(hits) - 1;
+              const int pos = cnt[r] + __popc(hits & lt_mask);
+              if (hit && pos < K) row[r][pos] = k;
+              cnt[r] += __popc(hits);
+            }
+          }
+        }
+        all_full = all_full && (cnt[r] >= K);
+      }
+      if (all_full) break;
+    }
+    // the first hit fills every slot that found no neighbour of its own (ball_query_gpu.cu:35-39)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int K = prm.nsample[r];
+      if (cnt[r] > 0)
+        for (int s = cnt[r] + lane; s < K; s += 32) row[r][s] = first[r];
+    }
+  }
+}
+
+// Any-size fallback (n > kBqMaxChunkPts): thread per query over global memory.
+__global__ void ball_query_generic_kernel(int n, int m, float r2, int K, const float *__restrict__ new_xyz,
+                                          const float *__restrict__ xyz, int *__restrict__ idx) {
+  const size_t cloud = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const float *qp = new_xyz + (cloud * (size_t)m + q) * 3;
+  const float *p = xyz + cloud * (size_t)n * 3;
+  int *row = idx + (cloud * (size_t)m + q) * K;
+  const float qx = qp[0], qy = qp[1], qz = qp[2];
+  int cnt = 0, first = 0;
+  for (int k = 0; k < n && cnt < K; ++k) {
+    const float d2 = sqdist_ref(qx - p[(size_t)k * 3], qy - p[(size_t)k * 3 + 1], qz - p[(size_t)k * 3 + 2]);
+    if (d2 < r2) {
+      if (cnt == 0) first = k;
+      row[cnt++] = k;
+    }
+  }
+  if (cnt > 0)
+    for (int s = cnt; s < K; ++s) row[s] = first;
+}
+
+template <int NR>
+int launch_ball_query(int b, int n, int m, const float *radius, const int *nsample, const float *new_xyz,
+                      const float *xyz, int *const *idx, cudaStream_t stream) {
+  BqParams<NR> prm;
+  prm.n = n; prm.m = m; prm.new_xyz = new_xyz; prm.xyz = xyz;
+  for (int r = 0; r < NR; ++r) {
+    prm.r2[r] = radius[r] * radius[r];  // f32 product, as ball_query_gpu.cu:23
+    prm.nsample[r] = nsample[r];
+    prm.idx[r] = idx[r];
+  }
+  const int threads = n > 8192 ? 1024 : (n > 1024 ? 512 : 256);
+  const int warps = threads / 32;
+  const size_t smem = (size_t)n * 3 * sizeof(float);
+  int ctas_per_cloud, q_per_cta;
+  if (smem > 100 * 1024) {
+    // one resident CTA per SM: exactly one wave, queries handed out dynamically inside the CTA
+    ctas_per_cloud = kNumSMs / b > 0 ? kNumSMs / b : 1;
+    q_per_cta = ceil_div(m, ctas_per_cloud);
+  } else {
+    ctas_per_cloud = ceil_div(2 * kNumSMs, b);
+    q_per_cta = ceil_div(m, ctas_per_cloud);
+    if (q_per_cta < warps) q_per_cta = warps;  // do not reload the cloud for less than a query per warp
+  }
+  prm.q_per_cta = q_per_cta;
+  auto kern = ball_query_kernel<NR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("ball_query: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+  dim3 grid((unsigned)ceil_div(m, q_per_cta), (unsigned)b);
+  kern<<<grid, threads, smem, stream>>>(prm);
+  return check_launch("ball_query");
+}
+
+int ball_query_dispatch(int nr, int b, int n, int m, const float *radius, const int *nsample, const float *new_xyz,
+                        const float *xyz, int *const *idx, cudaStream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return fail_arg("ball_query");
+  for (int r = 0; r < nr; ++r)
+    if (nsample[r] < 0) return fail_arg("ball_query (nsample)");
+  if (b == 0 || m == 0 || n == 0) return 0;
+  if (!new_xyz || !xyz) return fail_arg("ball_query (null pointer)");
+  if (b > 65535) return fail_arg("ball_query (batch > 65535)");
+  if (n > kBqMaxChunkPts) {
+    for (int r = 0; r < nr; ++r) {
+      if (nsample[r] == 0) continue;
+      dim3 grid((unsigned)ceil_div(m, 128), (unsigned)b);
+      ball_query_generic_kernel<<<grid, 128, 0, stream>>>(n, m, radius[r] * radius[r], nsample[r], new_xyz, xyz, idx[r]);
+      int rc = check_launch("ball_query (generic)");
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (nr == 1) return launch_ball_query<1>(b, n, m, radius, nsample, new_xyz, xyz, idx, stream);
+  if (nr == 2) return launch_ball_query<2>(b, n, m, radius, nsample, new_xyz, xyz, idx, stream);
+  return fail_arg("ball_query (1 or 2 radii)");
+}
+
+// ---------------------------------------------------------------------------------------------
+// group_points / gather_points:  out[b,c,e] = points[b,c,idx[b,e]],  e over npoints*nsample
+constexpr int kGatherThreads = 256;
+
+template <bool VEC>
+__global__ void __launch_bounds__(kGatherThreads) group_points_kernel(int c, int n, long long per_cloud,
+                                                                        const float *__restrict__ points,
+                                                                        const int *__restrict__ idx,
+                                                                        float *__restrict__ out) {
+  const size_t cloud = blockIdx.y;
+  const long long e0 = ((long long)blockIdx.x * kGatherThreads + threadIdx.x) * (VEC ? 4 : 1);
+  if (e0 >= per_cloud) return;
+  const int *ip = idx + cloud * per_cloud + e0;
+  const float *src = points + cloud * (size_t)c * n;
+  float *dst = out + cloud * (size_t)c * per_cloud + e0;
+  if (VEC) {
+    const int4 id = __ldg(reinterpret_cast<const int4 *>(ip));
+#pragma unroll 4
+    for (int ci = 0; ci < c; ++ci) {
+      const float *row = src + (size_t)ci * n;
+      float4 v;
+      v.x = __ldg(row + id.x); v.y = __ldg(row + id.y); v.z = __ldg(row + id.z); v.w = __ldg(row + id.w);
+      __stcs(reinterpret_cast<float4 *>(dst + (size_t)ci * per_cloud), v);
+    }
+  } else {
+    const int id = __ldg(ip);
+#pragma unroll 4
+    for (int ci = 0; ci < c; ++ci) dst[(size_t)ci * per_cloud] = __ldg(src + (size_t)ci * n + id);
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kGatherThreads) group_points_grad_kernel(int c, int n, long long per_cloud,
+                                                                             const float *__restrict__ grad_out,
+                                                                             const int *__restrict__ idx,
+                                                                             float *__restrict__ grad_points) {
+  const size_t cloud = blockIdx.y;
+  const long long e0 = ((long long)blockIdx.x * kGatherThreads + threadIdx.x) * (VEC ? 4 : 1);
+  if (e0 >= per_cloud) return;
+  const int *ip = idx + cloud * per_cloud + e0;
+  const float *g = grad_out + cloud * (size_t)c * per_cloud + e0;
+  float *dst = grad_points + cloud * (size_t)c * n;
+  if (VEC) {
+    const int4 id = __ldg(reinterpret_cast<const int4 *>(ip));
+#pragma unroll 2
+    for (int ci = 0; ci < c; ++ci) {
+      const float4 v = __ldcs(reinterpret_cast<const float4 *>(g + (size_t)ci * per_cloud));
+      float *row = dst + (size_t)ci * n;
+      atomicAdd(row + id.x, v.x); atomicAdd(row + id.y, v.y); atomicAdd(row + id.z, v.z); atomicAdd(row + id.w, v.w);
+    }
+  } else {
+    const int id = __ldg(ip);
+    for (int ci = 0; ci < c; ++ci) atomicAdd(dst + (size_t)ci * n + id, g[(size_t)ci * per_cloud]);
+  }
+}
+
+int group_dispatch(bool grad, int b, int c, int n, long long per_cloud, const float *a, const int *idx, float *o,
+                   cudaStream_t stream, const char *what) {
+  if (b < 0 || c < 0 || n < 0 || per_cloud < 0) return fail_arg(what);
+  if (b == 0 || c == 0 || per_cloud == 0) return 0;
+  if (!a || !idx || !o) return fail_arg(what);
+  if (b > 65535) return fail_arg(what);
+  const bool vec = (per_cloud % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(grad ? (const void *)a : (const void *)o) & 15u) == 0);
+  const long long per_thread = vec ? 4 : 1;
+  dim3 grid((unsigned)((per_cloud + kGatherThreads * per_thread - 1) / (kGatherThreads * per_thread)), (unsigned)b);
+  if (!grad) {
+    if (vec) group_points_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
+    else group_points_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
+  } else {
+    if (vec) group_points_grad_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
+    else group_points_grad_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
+  }
+  return check_launch(what);
+}
+
+// ---------------------------------------------------------------------------------------------
+// three_nn: thread per unknown point, known points staged as float4 in shared memory
+constexpr int kNnThreads = 256;
+constexpr int kNnChunk = 4096;  // known points per stage (64 KB)
+
+__global__ void __launch_bounds__(kNnThreads) three_nn_kernel(int n, int m, const float *__restrict__ unknown,
+                                                               const float *__restrict__ known,
+                                                               float *__restrict__ dist2, int *__restrict__ idx) {
+  extern __shared__ __align__(16) float4 s_known[];
+  const size_t cloud = blockIdx.y;
+  const int i = blockIdx.x * kNnThreads + threadIdx.x;
+  const float *kn = known + cloud * (size_t)m * 3;
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (i < n) {
+    const float *u = unknown + (cloud * (size_t)n + i) * 3;
+    ux = __ldg(u); uy = __ldg(u + 1); uz = __ldg(u + 2);
+  }
+  // The reference keeps doubles initialised to 1e40 and stores (float)1e40 == +inf for slots it
+  // never fills (interpolate_gpu.cu:30,50); a float +inf start is equivalent: "d < best" is false
+  // for d == +inf in both.
+  const float kInf = __int_as_float(0x7f800000);
+  float b1 = kInf, b2 = kInf, b3 = kInf;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int c0 = 0; c0 < m; c0 += kNnChunk) {
+    const int cn = min(kNnChunk, m - c0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cn; k += kNnThreads) {
+      const float *p = kn + (size_t)(c0 + k) * 3;
+      s_known[k] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < cn; ++k) {
+      const float4 p = s_known[k];
+      const float d = sqdist_ref(ux - p.x, uy - p.y, uz - p.z);
+      if (d < b3) {
+        const int kk = c0 + k;
+        if (d < b1) {
+          b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = kk;
+        } else if (d < b2) {
+          b3 = b2; i3 = i2; b2 = d; i2 = kk;
+        } else {
+          b3 = d; i3 = kk;
+        }
+      }
+    }
+  }
+  if (i < n) {
+    float *od = dist2 + (cloud * (size_t)n + i) * 3;
+    int *oi = idx + (cloud * (size_t)n + i) * 3;
+    od[0] = b1; od[1] = b2; od[2] = b3;
+    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+  }
+}
+
+// three_interpolate: out[b,c,i] = fma(w2,p2, fma(w0,p0, rn(w1*p1)))  (reference SASS order)
+constexpr int kInterpThreads = 256;
+constexpr int kInterpChannels = 32;  // channels per CTA (idx/weight loaded once for all of them)
+
+__global__ void __launch_bounds__(kInterpThreads) three_interpolate_kernel(int c, int m, int n,
+                                                                            const float *__restrict__ points,
+                                                                            const int *__restrict__ idx,
+                                                                            const float *__restrict__ weight,
+                                                                            float *__restrict__ out) {
+  const size_t cloud = blockIdx.z;
+  const int i = blockIdx.x * kInterpThreads + threadIdx.x;
+  if (i >= n) return;
+  const int c0 = blockIdx.y * kInterpChannels, c1 = min(c, c0 + kInterpChannels);
+  const int *ip = idx + (cloud * (size_t)n + i) * 3;
+  const float *wp = weight + (cloud * (size_t)n + i) * 3;
+  const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+  const float w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+#pragma unroll 4
+  for (int ci = c0; ci < c1; ++ci) {
+    const float *row = points + (cloud * (size_t)c + ci) * m;
+    float t = __fmul_rn(w1, __ldg(row + i1));
+    t = __fmaf_rn(w0, __ldg(row + i0), t);
+    t = __fmaf_rn(w2, __ldg(row + i2), t);
+    __stcs(out + (cloud * (size_t)c + ci) * n + i, t);
+  }
+}
+
+__global__ void __launch_bounds__(kInterpThreads) three_interpolate_grad_kernel(int c, int n, int m,
+                                                                                 const float *__restrict__ grad_out,
+                                                                                 const int *__restrict__ idx,
+                                                                                 const float *__restrict__ weight,
+                                                                                 float *__restrict__ grad_points) {
+  const size_t cloud = blockIdx.z;
+  const int i = blockIdx.x * kInterpThreads + threadIdx.x;
+  if (i >= n) return;
+  const int c0 = blockIdx.y * kInterpChannels, c1 = min(c, c0 + kInterpChannels);
+  const int *ip = idx + (cloud * (size_t)n + i) * 3;
+  const float *wp = weight + (cloud * (size_t)n + i) * 3;
+  const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+  const float w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+  for (int ci = c0; ci < c1; ++ci) {
+    const float g = __ldcs(grad_out + (cloud * (size_t)c + ci) * n + i);
+    float *row = grad_points + (cloud * (size_t)c + ci) * m;
+    atomicAdd(row + i0, __fmul_rn(g, w0));
+    atomicAdd(row + i1, __fmul_rn(g, w1));
+    atomicAdd(row + i2, __fmul_rn(g, w2));
+  }
+}
+
+}  // namespace
+
+// used by query_and_group.cu
+int ball_query_multi(int nr, int b, int n, int m, const float *radius, const int *nsample, const float *new_xyz,
+                     const float *xyz, int *const *idx, cudaStream_t stream) {
+  return ball_query_dispatch(nr, b, n, m, radius, nsample, new_xyz, xyz, idx, stream);
+}
+
+}  // namespace ws3d
+
+using namespace ws3d;
+
+WS3D_API int ws3d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                             int *idx, ws3d_stream_t stream) {
+  if (nsample > 0 && !idx) return fail_arg("ball_query (idx)");
+  int *rows[1] = {idx};
+  return ball_query_dispatch(1, b, n, m, &radius, &nsample, new_xyz, xyz, rows, to_stream(stream));
+}
+
+WS3D_API int ws3d_ball_query2(int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
+                              const float *new_xyz, const float *xyz, int *idx0, int *idx1, ws3d_stream_t stream) {
+  const float rr[2] = {radius0, radius1};
+  const int kk[2] = {nsample0, nsample1};
+  int *rows[2] = {idx0, idx1};
+  if ((nsample0 > 0 && !idx0) || (nsample1 > 0 && !idx1)) return fail_arg("ball_query2 (idx)");
+  return ball_query_dispatch(2, b, n, m, rr, kk, new_xyz, xyz, rows, to_stream(stream));
+}
+
+WS3D_API int ws3d_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                               float *out, ws3d_stream_t stream) {
+  return group_dispatch(false, b, c, n, (long long)npoints * nsample, points, idx, out, to_stream(stream), "group_points");
+}
+
+WS3D_API int ws3d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                                    const int *idx, float *grad_points, ws3d_stream_t stream) {
+  return group_dispatch(true, b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points, to_stream(stream),
+                        "group_points_grad");
+}
+
+WS3D_API int ws3d_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                                ws3d_stream_t stream) {
+  return group_dispatch(false, b, c, n, (long long)npoints, points, idx, out, to_stream(stream), "gather_points");
+}
+
+WS3D_API int ws3d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                                     float *grad_points, ws3d_stream_t stream) {
+  return group_dispatch(true, b, c, n, (long long)npoints, grad_out, idx, grad_points, to_stream(stream),
+                        "gather_points_grad");
+}
+
+WS3D_API int ws3d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                           ws3d_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return fail_arg("three_nn");
+  if (b == 0 || n == 0) return 0;
+  if (!unknown || !dist2 || !idx || (m > 0 && !known)) return fail_arg("three_nn (null pointer)");
+  if (b > 65535) return fail_arg("three_nn (batch > 65535)");
+  const size_t smem = (size_t)(m < kNnChunk ? (m > 0 ? m : 1) : kNnChunk) * sizeof(float4);
+  cudaError_t e = cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNnChunk * sizeof(float4)));
+  if (e != cudaSuccess) { set_error("three_nn: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  dim3 grid((unsigned)ceil_div(n, kNnThreads), (unsigned)b);
+  three_nn_kernel<<<grid, kNnThreads, smem, to_stream(stream)>>>(n, m, unknown, known, dist2, idx);
+  return check_launch("three_nn");
+}
+
+WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                                    const float *weight, float *out, ws3d_stream_t stream) {
+  if (b < 0 || c < 0 || m < 0 || n < 0) return fail_arg("three_interpolate");
+  if (b == 0 || c == 0 || n == 0) return 0;
+  if (!points || !idx || !weight || !out) return fail_arg("three_interpolate (null pointer)");
+  if (b > 65535 || ceil_div(c, kInterpChannels) > 65535) return fail_arg("three_interpolate (grid too large)");
+  dim3 grid((unsigned)ceil_div(n, kInterpThreads), (unsigned)ceil_div(c, kInterpChannels), (unsigned)b);
+  three_interpolate_kernel<<<grid, kInterpThreads, 0, to_stream(stream)>>>(c, m, n, points, idx, weight, out);
+  return check_launch("three_interpolate");
+}
+
+WS3D_API int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                         const float *weight, float *grad_points, ws3d_stream_t stream) {
+  if (b < 0 || c < 0 || m < 0 || n < 0) return fail_arg("three_interpolate_grad");
+  if (b == 0 || c == 0 || n == 0) return 0;
+  if (!grad_out || !idx || !weight || !grad_points) return fail_arg("three_interpolate_grad (null pointer)");
+  if (b > 65535 || ceil_div(c, kInterpChannels) > 65535) return fail_arg("three_interpolate_grad (grid too large)");
+  dim3 grid((unsigned)ceil_div(n, kInterpThreads), (unsigned)ceil_div(c, kInterpChannels), (unsigned)b);
+  three_interpolate_grad_kernel<<<grid, kInterpThreads, 0, to_stream(stream)>>>(c, n, m, grad_out, idx, weight, grad_points);
+  return check_launch("three_interpolate_grad");
+}

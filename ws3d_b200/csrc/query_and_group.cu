@@ -1,0 +1,130 @@
+// QueryAndGroup.forward (pointnet2_lib/pointnet2/pointnet2_utils.py:241-264) as two launches:
+// ball_query (pointnet2_ops.cu) and ONE grouping pass that gathers the neighbour coordinates,
+// subtracts the ball centre, gathers every feature channel and writes the concatenated
+// (B, 3+C, M, K) tensor once -- the reference runs transpose + group(xyz) + subtract +
+// group(features) + cat, i.e. writes the big tensor about twice and re-reads idx per channel.
+#include "common.cuh"
+
+namespace ws3d {
+
+int ball_query_multi(int nr, int b, int n, int m, const float *radius, const int *nsample, const float *new_xyz,
+                     const float *xyz, int *const *idx, cudaStream_t stream);
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// Each thread owns EPT consecutive neighbours of one centre (K % EPT == 0).
+template <int EPT>
+__global__ void __launch_bounds__(kThreads) group_concat_kernel(int c, int n, int m, int K, int use_xyz,
+                                                                 const float *__restrict__ xyz,
+                                                                 const float *__restrict__ new_xyz,
+                                                                 const float *__restrict__ features,
+                                                                 const int *__restrict__ idx, float *__restrict__ out) {
+  const size_t cloud = blockIdx.y;
+  const long long per_cloud = (long long)m * K;
+  const long long e0 = ((long long)blockIdx.x * kThreads + threadIdx.x) * EPT;
+  if (e0 >= per_cloud) return;
+  const int j = (int)(e0 / K);
+  int id[EPT];
+  const int *ip = idx + cloud * per_cloud + e0;
+  if (EPT == 4) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(ip));
+    id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) id[t] = __ldg(ip + t);
+  }
+  const int cout = c + (use_xyz ? 3 : 0);
+  float *dst = out + cloud * (size_t)cout * per_cloud + e0;
+  if (use_xyz) {
+    const float *ctr = new_xyz + (cloud * (size_t)m + j) * 3;
+    const float *pts = xyz + cloud * (size_t)n * 3;
+    float v[3][EPT];
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) {
+      const float *p = pts + (size_t)id[t] * 3;
+      v[0][t] = __ldg(p); v[1][t] = __ldg(p + 1); v[2][t] = __ldg(p + 2);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float cc = __ldg(ctr + a);
+#pragma unroll
+      for (int t = 0; t < EPT; ++t) v[a][t] = __fsub_rn(v[a][t], cc);
+      if (EPT == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(v[a][0], v[a][1], v[a][2], v[a][3]));
+      else {
+#pragma unroll
+        for (int t = 0; t < EPT; ++t) dst[t] = v[a][t];
+      }
+      dst += per_cloud;
+    }
+  }
+  if (c > 0) {
+    const float *src = features + cloud * (size_t)c * n;
+#pragma unroll 4
+    for (int ci = 0; ci < c; ++ci) {
+      const float *row = src + (size_t)ci * n;
+      if (EPT == 4) {
+        float4 f;
+        f.x = __ldg(row + id[0]); f.y = __ldg(row + id[1]); f.z = __ldg(row + id[2]); f.w = __ldg(row + id[3]);
+        __stcs(reinterpret_cast<float4 *>(dst), f);
+      } else {
+#pragma unroll
+        for (int t = 0; t < EPT; ++t) dst[t] = __ldg(row + id[t]);
+      }
+      dst += per_cloud;
+    }
+  }
+}
+
+}  // namespace
+
+int group_concat(int b, int n, int m, int c, int K, int use_xyz, const float *xyz, const float *new_xyz,
+                 const float *features, const int *idx, float *out, cudaStream_t stream) {
+  if (b == 0 || m == 0 || K == 0) return 0;
+  const long long per_cloud = (long long)m * K;
+  const bool vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+  if (vec) {
+    dim3 grid((unsigned)((per_cloud + kThreads * 4 - 1) / (kThreads * 4)), (unsigned)b);
+    group_concat_kernel<4><<<grid, kThreads, 0, stream>>>(c, n, m, K, use_xyz, xyz, new_xyz, features, idx, out);
+  } else {
+    dim3 grid((unsigned)((per_cloud + kThreads - 1) / kThreads), (unsigned)b);
+    group_concat_kernel<1><<<grid, kThreads, 0, stream>>>(c, n, m, K, use_xyz, xyz, new_xyz, features, idx, out);
+  }
+  return check_launch("query_and_group (group)");
+}
+
+}  // namespace ws3d
+
+using namespace ws3d;
+
+WS3D_API int ws3d_group_concat(int b, int n, int m, int c, int nsample, int use_xyz, const float *xyz,
+                               const float *new_xyz, const float *features, const int *idx, float *out,
+                               ws3d_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || c < 0 || nsample < 0) return fail_arg("group_concat");
+  if (b > 65535) return fail_arg("group_concat (batch > 65535)");
+  if (b && m && nsample && (!idx || !out || (use_xyz && (!xyz || !new_xyz)) || (c > 0 && !features)))
+    return fail_arg("group_concat (null pointer)");
+  if (!use_xyz && c == 0) return fail_arg("group_concat (no channels)");
+  return group_concat(b, n, m, c, nsample, use_xyz, xyz, new_xyz, features, idx, out, to_stream(stream));
+}
+
+WS3D_API int ws3d_query_and_group(int b, int n, int m, int c, float radius, int nsample, int use_xyz,
+                                  const float *xyz, const float *new_xyz, const float *features, float *out,
+                                  int *idx_out, ws3d_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || c < 0 || nsample < 0) return fail_arg("query_and_group");
+  if (b == 0 || m == 0 || nsample == 0) return 0;
+  int *idx = idx_out;
+  if (!idx) {
+    const size_t bytes = (size_t)b * m * nsample * sizeof(int);
+    idx = (int *)scratch(bytes, 1);
+    if (!idx) return (int)cudaErrorMemoryAllocation;
+    cudaError_t e = cudaMemsetAsync(idx, 0, bytes, to_stream(stream));
+    if (e != cudaSuccess) { set_error("query_and_group: memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  int *rows[1] = {idx};
+  int rc = ball_query_multi(1, b, n, m, &radius, &nsample, new_xyz, xyz, rows, to_stream(stream));
+  if (rc) return rc;
+  return ws3d_group_concat(b, n, m, c, nsample, use_xyz, xyz, new_xyz, features, idx, out, stream);
+}
