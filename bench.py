@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of ws3d_b200 (contract in the task statement).
+
+Workload (BASELINE.json configs[1]): full PointNet++-MSG backbone forward (4 SA + 4 FP layers,
+tools/cfgs/weaklyRPN.yaml shapes) on a batch of 16 synthetic KITTI-shaped clouds (16384 points x 4
+channels) per GPU.  Metric: set-abstraction path throughput in Mpoints/s = clouds x 16384 / time.
+
+  python bench.py [--gpus N --steps K --warmup W]          this repo's CUDA path (one rank per GPU)
+  python bench.py --impl reference ...                     the CPU path (oracle port, all host cores)
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same forward called
+with HOST (pinned) input, H2D copy and a D2H read of the per-cloud result checksum inside the timed
+region.  `roofline`: the dominant kernel of the step, timed live with CUDA events on the launching
+stream.  `cpu_baseline`: the oracle port on the host cores for a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SA-layer Mpoints/sec (PointNet++-MSG backbone forward: 4 SA + 4 FP)"
+UNIT = "Mpoints/s"
+NPTS = 16384
+BATCH = 16
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (rank 0 only)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._th.join(timeout=6)
+        return False
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port).  This is the only place besides tests/ and smoke() that touches oracle/.
+def cpu_backbone_throughput(clouds, repeats=1, threads=None):
+    import torch
+
+    import oracle
+    from oracle import cpu_backbone
+    from ws3d_b200 import models, synth
+    if threads:
+        oracle.set_num_threads(threads)
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = models.Pointnet2MSG(input_channels=1).eval()
+    pts = synth.make_batch(clouds)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_backbone.backbone_forward(model, pts)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return clouds * NPTS / best / 1e6, best, oracle.num_threads()
+
+
+def run_reference_cpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0))
+    clouds = 2
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_backbone_throughput(1, threads=cores)
+    times = []
+    for _ in range(args.steps):
+        _, dt, thr = cpu_backbone_throughput(clouds, threads=cores)
+        times.append(dt)
+    ms = float(np.mean(times)) * 1e3
+    value = clouds * NPTS / (ms / 1e3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PointNet++-MSG backbone forward (4 SA + 4 FP), synthetic KITTI clouds 16384x4",
+                   "clouds_per_step": clouds, "note": "CPU port of the reference algorithms (the reference has no CPU "
+                   "implementation of these ops); each step is a bounded sample of the GPU arm's 16-cloud batch"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{clouds} clouds x {NPTS} points per step, oracle ops (OpenMP) + PyTorch CPU MLPs"},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+ALG_BYTES = {
+    # SURVEY.md section 8d, per launch; b = clouds in the launch
+    "fps": lambda b, n, m, **k: b * (12 * n + 4 * m),
+    "ball_query2": lambda b, n, m, k0, k1, **k: b * (12 * n + 12 * m + 4 * m * (k0 + k1)),
+    "group_concat": lambda b, n, m, c, k, **kw: b * (4 * m * k + 12 * n + 4 * c * n + 12 * m + 4 * (3 + c) * m * k),
+    "three_nn": lambda b, n, m, **k: b * (12 * n + 12 * m + 24 * n),
+    "three_interpolate": lambda b, c, m, n, **k: b * (4 * c * m + 24 * n + 4 * c * n),
+}
+
+
+class OpProfiler:
+    """CUDA-event timing of this repo's kernels inside the timed region (same stream)."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.records = []  # (op, dims, start, end)
+
+    def wrap(self, native):
+        t = self.torch
+        prof = self
+
+        def timed(name, fn, dims_fn):
+            def inner(*a):
+                s, e = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                s.record()
+                r = fn(*a)
+                e.record()
+                prof.records.append((name, dims_fn(*a), s, e))
+                return r
+            return inner
+
+        self._orig = {}
+        table = {
+            "furthest_point_sampling_gather": ("fps", lambda b, n, m, *r: dict(b=b, n=n, m=m)),
+            "ball_query2": ("ball_query2", lambda b, n, m, r0, k0, r1, k1, *r: dict(b=b, n=n, m=m, k0=k0, k1=k1)),
+            "group_concat": ("group_concat", lambda b, n, m, c, k, *r: dict(b=b, n=n, m=m, c=c, k=k)),
+            "three_nn_wrapper": ("three_nn", lambda b, n, m, *r: dict(b=b, n=n, m=m)),
+            "three_interpolate_wrapper": ("three_interpolate", lambda b, c, m, n, *r: dict(b=b, c=c, m=m, n=n)),
+        }
+        for attr, (name, dims) in table.items():
+            self._orig[attr] = getattr(native, attr)
+            setattr(native, attr, timed(name, self._orig[attr], dims))
+        self._native = native
+
+    def unwrap(self):
+        for attr, fn in self._orig.items():
+            setattr(self._native, attr, fn)
+
+    def summarize(self, steps):
+        agg = {}
+        for name, dims, s, e in self.records:
+            ms = s.elapsed_time(e)
+            key = (name, tuple(sorted(dims.items())))
+            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "bytes": ALG_BYTES[name](**dims)})
+            a["ms"] += ms
+            a["launches"] += 1
+        out = []
+        for (name, dims), a in agg.items():
+            avg = a["ms"] / a["launches"]
+            out.append({"kernel": name, "dims": dict(dims), "avg_ms": avg, "ms_per_step": a["ms"] / steps,
+                        "alg_bytes": a["bytes"], "GBps": a["bytes"] / avg / 1e6})
+        out.sort(key=lambda r: -r["ms_per_step"])
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from ws3d_b200 import _C, models, native, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = models.Pointnet2MSG(input_channels=1).to(dev).eval()
+    # every rank works on its own clouds (scenes shard across GPUs; no data-path collective)
+    host = torch.from_numpy(synth.make_batch(BATCH, NPTS, first_scene=rank * BATCH)).pin_memory()
+    resident = host.to(dev)
+
+    def step_resident():
+        with torch.no_grad():
+            return model(resident)[1]
+
+    def step_e2e():
+        with torch.no_grad():
+            x = host.to(dev, non_blocking=True)
+            feats = model(x)[1]
+            return feats.sum(dim=(1, 2)).cpu()  # D2H read of the per-cloud checksum (synchronises)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed_region(step_fn, steps, profile):
+        prof = None
+        if profile:
+            prof = OpProfiler(torch)
+            prof.wrap(native)
+        launches0 = _C.launch_count()
+        total = 0.0
+        sync_all()
+        t_wall = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(0)  # L2 flush between timed iterations (outside the event pair)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step_fn()
+            e.record()
+            e.synchronize()
+            total += s.elapsed_time(e)
+        sync_all()
+        wall = time.perf_counter() - t_wall
+        launches = _C.launch_count() - launches0
+        if prof:
+            prof.unwrap()
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, prof, wall
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    sync_all()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.__enter__()
+    ms_total, launches, prof, _ = timed_region(step_resident, args.steps, profile=True)
+    ms_e2e, _, _, _ = timed_region(step_e2e, args.steps, profile=False)
+    if sampler:
+        sampler.__exit__(None, None, None)
+
+    ms_step = ms_total / args.steps
+    value = world * BATCH * NPTS / (ms_step / 1e3) / 1e6
+    e2e_value = world * BATCH * NPTS / (ms_e2e / args.steps / 1e3) / 1e6
+    peak, peak_src = measured_peaks()
+    roof = None
+    kernels = []
+    if prof:
+        kernels = prof.summarize(args.steps)
+        top = kernels[0]
+        roof = {"bound": "hbm", "kernel": top["kernel"], "dims": top["dims"], "achieved": round(top["GBps"], 3), "peak": peak,
+                "unit": "GB/s", "frac": round(top["GBps"] / peak, 6), "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": round(top["avg_ms"], 4), "share_of_step": round(top["ms_per_step"] / ms_step, 4),
+                "note": "FPS is a latency chain of m-1 dependent iterations (SURVEY.md 8d): its HBM fraction is "
+                        "reported for the record; us/iteration is the meaningful figure" if top["kernel"] == "fps" else ""}
+        if top["kernel"] == "fps":
+            roof["us_per_iteration"] = round(top["avg_ms"] * 1e3 / (top["dims"]["m"] - 1), 4)
+
+    if rank == 0:
+        cores = len(os.sched_getaffinity(0))
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, thr = cpu_backbone_throughput(2, threads=cores)
+            cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"2 clouds x {NPTS} points, one pass ({dt:.1f} s): oracle ops (OpenMP, {thr} threads) + PyTorch CPU MLPs"}
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "PointNet++-MSG backbone forward (4 SA + 4 FP, weaklyRPN.yaml shapes), batch 16 synthetic "
+                                   "KITTI clouds 16384x4 per GPU (BASELINE configs[1])",
+                       "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": "flushed between timed iterations (256 MiB write)",
+                       "mlp": "PyTorch/cuDNN fp32 (TF32 " + ("on" if torch.backends.cudnn.allow_tf32 else "off") + ")",
+                       "sharding": "scenes per rank, no data-path collective"},
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4) * world,
+                    "d2h_bytes_per_step": BATCH * 4 * world, "ms_per_step": round(ms_e2e / args.steps, 4),
+                    "note": "pinned host cloud -> H2D -> backbone forward -> per-cloud feature checksum -> D2H"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+        }
+        if roof:
+            line["roofline"] = roof
+            line["kernels"] = [{"kernel": k["kernel"], "dims": k["dims"], "avg_ms": round(k["avg_ms"], 4),
+                                "ms_per_step": round(k["ms_per_step"], 4), "GBps": round(k["GBps"], 2),
+                                "frac": round(k["GBps"] / peak, 5)} for k in kernels]
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_cpu(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

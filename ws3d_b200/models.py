@@ -1,0 +1,110 @@
+"""The callers of the hot path, at the reference's shapes: the Stage-1 PointNet++-MSG backbone
+(lib/net/pointnet2_msg.py) and the RPN heads on top of it (lib/net/rpn.py:20-45,67-81).
+
+Host side stays PyTorch (north star): these are ordinary nn.Modules whose SA / FP layers call the
+B200 ops.  Structure and parameter names follow the reference so its checkpoints load unchanged
+(`backbone_net.SA_modules.0.mlps.0.layer0.conv.weight`, ...).  The network shape comes from
+tools/cfgs/weaklyRPN.yaml:43-56 (= lib/config.py:57-70), restated here as RPN_SA_CONFIG.
+"""
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import pytorch_utils as pt_utils
+from .pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+
+RPN_SA_CONFIG = {
+    "NPOINTS": [4096, 1024, 256, 64],
+    "RADIUS": [[0.1, 0.5], [0.5, 1.0], [1.0, 2.0], [2.0, 4.0]],
+    "NSAMPLE": [[16, 32], [16, 32], [16, 32], [16, 32]],
+    "MLPS": [[[16, 16, 32], [32, 32, 64]],
+             [[64, 64, 128], [64, 96, 128]],
+             [[128, 196, 256], [128, 196, 256]],
+             [[256, 256, 512], [256, 384, 512]]],
+}
+RPN_FP_MLPS = [[128, 128], [256, 256], [512, 512], [512, 512]]
+RPN_CLS_FC = [128]
+RPN_REG_FC = [128]
+RPN_DP_RATIO = 0.5
+RPN_LOC_SCOPE = 4.0      # weaklyRPN.yaml:37
+RPN_LOC_BIN_SIZE = 0.8   # weaklyRPN.yaml:38
+RPN_NUM_POINTS = 16384
+
+
+class Pointnet2MSG(nn.Module):
+    """4 x PointnetSAModuleMSG + 4 x PointnetFPModule (lib/net/pointnet2_msg.py:11-70)."""
+
+    def __init__(self, input_channels: int = 1, use_xyz: bool = True, sa_config=None, fp_mlps=None, bn: bool = True):
+        super().__init__()
+        sa = copy.deepcopy(sa_config or RPN_SA_CONFIG)
+        fp = copy.deepcopy(fp_mlps or RPN_FP_MLPS)
+        self.SA_modules = nn.ModuleList()
+        channel_in = input_channels
+        skip_channels = [input_channels]
+        channel_out = channel_in
+        for k in range(len(sa["NPOINTS"])):
+            mlps = [[channel_in] + list(m) for m in sa["MLPS"][k]]
+            channel_out = sum(m[-1] for m in mlps)
+            self.SA_modules.append(PointnetSAModuleMSG(npoint=sa["NPOINTS"][k], radii=sa["RADIUS"][k],
+                                                       nsamples=sa["NSAMPLE"][k], mlps=mlps, use_xyz=use_xyz, bn=bn))
+            skip_channels.append(channel_out)
+            channel_in = channel_out
+        self.FP_modules = nn.ModuleList()
+        for k in range(len(fp)):
+            pre = fp[k + 1][-1] if k + 1 < len(fp) else channel_out
+            self.FP_modules.append(PointnetFPModule(mlp=[pre + skip_channels[k]] + fp[k], bn=True))
+
+    @staticmethod
+    def _break_up_pc(pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def forward(self, pointcloud: torch.Tensor):
+        """pointcloud (B,N,3+C) -> (xyz (B,N,3), per-point features (B,128,N))."""
+        xyz, features = self._break_up_pc(pointcloud)
+        l_xyz, l_features = [xyz], [features]
+        for sa in self.SA_modules:
+            nx, nf = sa(l_xyz[-1], l_features[-1])
+            l_xyz.append(nx)
+            l_features.append(nf)
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+            l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+        return l_xyz[0], l_features[0]
+
+
+class RPN(nn.Module):
+    """Backbone + per-point classification / bin-regression heads (lib/net/rpn.py:10-81)."""
+
+    def __init__(self, use_xyz: bool = True, use_intensity: bool = True, focal_init: bool = True):
+        super().__init__()
+        self.backbone_net = Pointnet2MSG(input_channels=int(use_intensity), use_xyz=use_xyz)
+
+        def head(fc, out_channels):
+            layers, pre = [], RPN_FP_MLPS[0][-1]
+            for width in fc:
+                layers.append(pt_utils.Conv1d(pre, width, bn=True))
+                pre = width
+            layers.append(pt_utils.Conv1d(pre, out_channels, activation=None))
+            if RPN_DP_RATIO >= 0:
+                layers.insert(1, nn.Dropout(RPN_DP_RATIO))
+            return nn.Sequential(*layers)
+
+        per_loc_bin_num = int(RPN_LOC_SCOPE / RPN_LOC_BIN_SIZE) * 2
+        self.reg_channel = per_loc_bin_num * 4
+        self.rpn_cls_layer = head(RPN_CLS_FC, 1)
+        self.rpn_reg_layer = head(RPN_REG_FC, self.reg_channel)
+        if focal_init:  # rpn.py:60-65
+            pi = 0.01
+            nn.init.constant_(self.rpn_cls_layer[2].conv.bias, -np.log((1 - pi) / pi))
+        nn.init.normal_(self.rpn_reg_layer[-1].conv.weight, mean=0, std=0.001)
+
+    def forward(self, input_data):
+        pts_input = input_data['pts_input'] if isinstance(input_data, dict) else input_data
+        backbone_xyz, backbone_features = self.backbone_net(pts_input)
+        rpn_cls = self.rpn_cls_layer(backbone_features).transpose(1, 2).contiguous()
+        rpn_reg = self.rpn_reg_layer(backbone_features).transpose(1, 2).contiguous()
+        return {'rpn_cls': rpn_cls, 'rpn_reg': rpn_reg, 'backbone_xyz': backbone_xyz,
+                'backbone_features': backbone_features}

@@ -1,0 +1,202 @@
+"""Tensor-level entry points with the reference's pybind signatures.
+
+One function per entry of the three reference extension modules
+(pointnet2_lib/pointnet2/src/pointnet2_api.cpp:11-23, lib/utils/iou3d/src/iou3d.cpp:175-178,
+lib/utils/roipool3d/src/roipool3d.cpp:199-202): same names, same positional arguments, the
+caller allocates every output.  They forward raw pointers to libws3d_ops.so on torch's current
+stream.  ws3d_b200/dropin/{pointnet2_cuda,iou3d_cuda,roipool3d_cuda}.py re-export them under
+the reference module names so the reference's Python wrappers run on top unmodified.
+"""
+import torch
+
+from . import _C
+from ._C import check, device_of, lib, ptr, require_cuda, stream
+
+
+# ---- pointnet2_cuda ---------------------------------------------------------------------------
+def furthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_tensor):
+    require_cuda(points_tensor, temp_tensor, idx_tensor)
+    with device_of(points_tensor):
+        check(lib().ws3d_furthest_point_sampling(b, n, m, ptr(points_tensor), ptr(temp_tensor), ptr(idx_tensor),
+                                                 stream()), "furthest_point_sampling")
+    return 1
+
+
+def gather_points_wrapper(b, c, n, npoints, points_tensor, idx_tensor, out_tensor):
+    require_cuda(points_tensor, idx_tensor, out_tensor)
+    with device_of(points_tensor):
+        check(lib().ws3d_gather_points(b, c, n, npoints, ptr(points_tensor), ptr(idx_tensor), ptr(out_tensor),
+                                       stream()), "gather_points")
+    return 1
+
+
+def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, grad_points_tensor):
+    require_cuda(grad_out_tensor, idx_tensor, grad_points_tensor)
+    with device_of(grad_out_tensor):
+        check(lib().ws3d_gather_points_grad(b, c, n, npoints, ptr(grad_out_tensor), ptr(idx_tensor),
+                                            ptr(grad_points_tensor), stream()), "gather_points_grad")
+    return 1
+
+
+def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx_tensor):
+    require_cuda(new_xyz_tensor, xyz_tensor, idx_tensor)
+    with device_of(xyz_tensor):
+        check(lib().ws3d_ball_query(b, n, m, float(radius), nsample, ptr(new_xyz_tensor), ptr(xyz_tensor),
+                                    ptr(idx_tensor), stream()), "ball_query")
+    return 1
+
+
+def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, out_tensor):
+    require_cuda(points_tensor, idx_tensor, out_tensor)
+    with device_of(points_tensor):
+        check(lib().ws3d_group_points(b, c, n, npoints, nsample, ptr(points_tensor), ptr(idx_tensor),
+                                      ptr(out_tensor), stream()), "group_points")
+    return 1
+
+
+def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_tensor, grad_points_tensor):
+    require_cuda(grad_out_tensor, idx_tensor, grad_points_tensor)
+    with device_of(grad_out_tensor):
+        check(lib().ws3d_group_points_grad(b, c, n, npoints, nsample, ptr(grad_out_tensor), ptr(idx_tensor),
+                                           ptr(grad_points_tensor), stream()), "group_points_grad")
+    return 1
+
+
+def three_nn_wrapper(b, n, m, unknown_tensor, known_tensor, dist2_tensor, idx_tensor):
+    require_cuda(unknown_tensor, known_tensor, dist2_tensor, idx_tensor)
+    with device_of(unknown_tensor):
+        check(lib().ws3d_three_nn(b, n, m, ptr(unknown_tensor), ptr(known_tensor), ptr(dist2_tensor),
+                                  ptr(idx_tensor), stream()), "three_nn")
+
+
+def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tensor, out_tensor):
+    require_cuda(points_tensor, idx_tensor, weight_tensor, out_tensor)
+    with device_of(points_tensor):
+        check(lib().ws3d_three_interpolate(b, c, m, n, ptr(points_tensor), ptr(idx_tensor), ptr(weight_tensor),
+                                           ptr(out_tensor), stream()), "three_interpolate")
+
+
+def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor):
+    require_cuda(grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor)
+    with device_of(grad_out_tensor):
+        check(lib().ws3d_three_interpolate_grad(b, c, n, m, ptr(grad_out_tensor), ptr(idx_tensor),
+                                                ptr(weight_tensor), ptr(grad_points_tensor), stream()),
+              "three_interpolate_grad")
+
+
+# ---- extensions (no reference counterpart; used by ws3d_b200.pointnet2_utils) -------------------
+def furthest_point_sampling_gather(b, n, m, xyz, temp, idx, new_xyz):
+    require_cuda(xyz, temp, idx, new_xyz)
+    with device_of(xyz):
+        check(lib().ws3d_furthest_point_sampling_gather(b, n, m, ptr(xyz), ptr(temp), ptr(idx), ptr(new_xyz),
+                                                        stream()), "furthest_point_sampling_gather")
+
+
+def ball_query2(b, n, m, radius0, nsample0, radius1, nsample1, new_xyz, xyz, idx0, idx1):
+    require_cuda(new_xyz, xyz, idx0, idx1)
+    with device_of(xyz):
+        check(lib().ws3d_ball_query2(b, n, m, float(radius0), nsample0, float(radius1), nsample1, ptr(new_xyz),
+                                     ptr(xyz), ptr(idx0), ptr(idx1), stream()), "ball_query2")
+
+
+def group_concat(b, n, m, c, nsample, use_xyz, xyz, new_xyz, features, idx, out):
+    require_cuda(xyz, new_xyz, features, idx, out)
+    with device_of(out):
+        check(lib().ws3d_group_concat(b, n, m, c, nsample, int(bool(use_xyz)), ptr(xyz), ptr(new_xyz), ptr(features),
+                                      ptr(idx), ptr(out), stream()), "group_concat")
+
+
+def query_and_group(b, n, m, c, radius, nsample, use_xyz, xyz, new_xyz, features, out, idx_out):
+    require_cuda(xyz, new_xyz, features, out, idx_out)
+    with device_of(out):
+        check(lib().ws3d_query_and_group(b, n, m, c, float(radius), nsample, int(bool(use_xyz)), ptr(xyz),
+                                         ptr(new_xyz), ptr(features), ptr(out), ptr(idx_out), stream()),
+              "query_and_group")
+
+
+# ---- iou3d_cuda -------------------------------------------------------------------------------
+def _check_boxes(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("boxes must be a CUDAtensor ")
+        if not t.is_contiguous():
+            raise RuntimeError("boxes must be contiguous ")
+
+
+def boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap):
+    _check_boxes(boxes_a, boxes_b, ans_overlap)
+    with device_of(boxes_a):
+        check(lib().ws3d_boxes_overlap_bev(boxes_a.size(0), ptr(boxes_a), boxes_b.size(0), ptr(boxes_b),
+                                           ptr(ans_overlap), stream()), "boxes_overlap_bev_gpu")
+    return 1
+
+
+def boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou):
+    _check_boxes(boxes_a, boxes_b, ans_iou)
+    with device_of(boxes_a):
+        check(lib().ws3d_boxes_iou_bev(boxes_a.size(0), ptr(boxes_a), boxes_b.size(0), ptr(boxes_b), ptr(ans_iou),
+                                       stream()), "boxes_iou_bev_gpu")
+    return 1
+
+
+def _nms_host(fn, name, boxes, keep, thresh):
+    _check_boxes(boxes)
+    if keep.is_cuda or keep.dtype != torch.int64 or not keep.is_contiguous():
+        raise RuntimeError("keep must be a contiguous CPU int64 tensor")
+    with device_of(boxes):
+        n = fn(ptr(boxes), boxes.size(0), float(thresh), ptr(keep), stream())
+    if n < 0:
+        raise RuntimeError(f"ws3d_b200.{name} failed (code {-n}): {_C.last_error()}")
+    return n
+
+
+def nms_gpu(boxes, keep, nms_overlap_thresh):
+    """Reference signature (iou3d.cpp:73): boxes (N,5) CUDA sorted by score, keep (N) CPU int64."""
+    return _nms_host(lib().ws3d_nms_host, "nms_gpu", boxes, keep, nms_overlap_thresh)
+
+
+def nms_normal_gpu(boxes, keep, nms_overlap_thresh):
+    return _nms_host(lib().ws3d_nms_normal_host, "nms_normal_gpu", boxes, keep, nms_overlap_thresh)
+
+
+def nms_device(boxes, thresh, rotated=True):
+    """Extension: all-device NMS.  Returns (keep int64 CUDA (N), num_keep int32 CUDA (1)); no sync."""
+    _check_boxes(boxes)
+    n = boxes.size(0)
+    keep = torch.empty(n, dtype=torch.int64, device=boxes.device)
+    num = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    fn = lib().ws3d_nms if rotated else lib().ws3d_nms_normal
+    with device_of(boxes):
+        check(fn(ptr(boxes), n, float(thresh), ptr(keep), ptr(num), None, stream()), "nms")
+    return keep, num
+
+
+# ---- roipool3d_cuda ---------------------------------------------------------------------------
+def roipool3d_forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
+    """Reference `forward` (roipool3d.cpp:48): xyz (B,N,3), boxes3d (B,M,7), pts_feature (B,N,C),
+    pooled_features (B,M,S,3+C) and pooled_empty_flag (B,M) int32 zero-filled by the caller."""
+    _check_boxes(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag)
+    with device_of(xyz):
+        check(lib().ws3d_roipool3d(xyz.size(0), xyz.size(1), boxes3d.size(1), pts_feature.size(2),
+                                   pooled_features.size(2), ptr(xyz), ptr(boxes3d), ptr(pts_feature),
+                                   ptr(pooled_features), ptr(pooled_empty_flag), stream()), "roipool3d forward")
+    return 1
+
+
+def pts_in_boxes3d_cpu(pts_flag, pts, boxes3d):
+    for t in (pts_flag, pts, boxes3d):
+        if t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("pts_in_boxes3d_cpu expects contiguous CPU tensors")
+    check(lib().ws3d_pts_in_boxes3d_cpu(ptr(pts_flag), ptr(pts), ptr(boxes3d), boxes3d.size(0), pts.size(0)),
+          "pts_in_boxes3d_cpu")
+    return 1
+
+
+def roipool3d_cpu(pts, boxes3d, pts_feature, pooled_pts, pooled_features, pooled_empty_flag):
+    for t in (pts, boxes3d, pts_feature, pooled_pts, pooled_features, pooled_empty_flag):
+        if t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("roipool3d_cpu expects contiguous CPU tensors")
+    check(lib().ws3d_roipool3d_cpu(ptr(pts), ptr(boxes3d), ptr(pts_feature), ptr(pooled_pts), ptr(pooled_features),
+                                   ptr(pooled_empty_flag), boxes3d.size(0), pts.size(0), pts_feature.size(1),
+                                   pooled_pts.size(1)), "roipool3d_cpu")
+    return 1

@@ -1,0 +1,115 @@
+"""Host-side mirror of the reference's set-abstraction / feature-propagation modules
+(pointnet2_lib/pointnet2/pointnet2_modules.py): PointnetSAModuleMSG, PointnetSAModule and
+PointnetFPModule with the same constructor arguments, sub-module names (`groupers`, `mlps`, `mlp`)
+and therefore the same state_dict keys.  The forward passes sequence the B200 ops:
+
+  SA layer (reference :19-55)                 here
+  ------------------------------------------  ------------------------------------------------
+  transpose + FPS + gather + transpose        one FPS launch that also emits new_xyz
+  per scale: ball_query                       one scan for both radii (ball_query_pair)
+  per scale: group xyz, subtract, group       one grouping pass writing the concatenated
+             features, cat                    (3+C, npoint, nsample) tensor once
+  SharedMLP + max-pool                        unchanged (PyTorch / cuDNN)
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils
+from . import pytorch_utils as pt_utils
+
+
+class _PointnetSAModuleBase(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.npoint = None
+        self.groupers = None
+        self.mlps = None
+        self.pool_method = 'max_pool'
+
+    def _neighbour_indices(self, xyz, new_xyz):
+        """ball_query for every scale; scales are scanned two at a time."""
+        specs = [(g.radius, g.nsample) for g in self.groupers]
+        out = [None] * len(specs)
+        k = 0
+        while k + 1 < len(specs):
+            (r0, s0), (r1, s1) = specs[k], specs[k + 1]
+            out[k], out[k + 1] = pointnet2_utils.ball_query_pair((r0, r1), (s0, s1), xyz, new_xyz)
+            k += 2
+        if k < len(specs):
+            out[k] = pointnet2_utils.ball_query(specs[k][0], specs[k][1], xyz, new_xyz)
+        return out
+
+    def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor] = None,
+                new_xyz: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B, sum_k mlps[k][-1], npoint)."""
+        if new_xyz is None and self.npoint is not None:
+            _, new_xyz = pointnet2_utils.sample_and_gather(xyz, self.npoint)
+        if self.npoint is not None:
+            indices = self._neighbour_indices(xyz, new_xyz)
+        else:
+            indices = [None] * len(self.groupers)  # GroupAll
+        pooled = []
+        for grouper, mlp, idx in zip(self.groupers, self.mlps, indices):
+            grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
+            grouped = mlp(grouped)
+            if self.pool_method == 'max_pool':
+                grouped = F.max_pool2d(grouped, kernel_size=[1, grouped.size(3)])
+            elif self.pool_method == 'avg_pool':
+                grouped = F.avg_pool2d(grouped, kernel_size=[1, grouped.size(3)])
+            else:
+                raise NotImplementedError
+            pooled.append(grouped.squeeze(-1))
+        return new_xyz, torch.cat(pooled, dim=1)
+
+
+class PointnetSAModuleMSG(_PointnetSAModuleBase):
+    """Set abstraction with multi-scale grouping (reference :58-92)."""
+
+    def __init__(self, *, npoint: int, radii: List[float], nsamples: List[int], mlps: List[List[int]], bn: bool = True,
+                 use_xyz: bool = True, pool_method='max_pool', instance_norm=False):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint = npoint
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        for radius, nsample, spec in zip(radii, nsamples, mlps):
+            self.groupers.append(pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz)
+                                 if npoint is not None else pointnet2_utils.GroupAll(use_xyz))
+            if use_xyz:
+                spec[0] += 3  # in place, like the reference (:86-87): callers observe the widened spec
+            self.mlps.append(pt_utils.SharedMLP(spec, bn=bn, instance_norm=instance_norm))
+        self.pool_method = pool_method
+
+
+class PointnetSAModule(PointnetSAModuleMSG):
+    """Single-scale set abstraction (reference :95-113)."""
+
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None, nsample: int = None,
+                 bn: bool = True, use_xyz: bool = True, pool_method='max_pool', instance_norm=False):
+        super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample], bn=bn, use_xyz=use_xyz,
+                         pool_method=pool_method, instance_norm=instance_norm)
+
+
+class PointnetFPModule(nn.Module):
+    """Feature propagation (reference :116-156): three_nn -> inverse-distance weights ->
+    three_interpolate -> concat skip features -> SharedMLP."""
+
+    def __init__(self, *, mlp: List[int], bn: bool = True):
+        super().__init__()
+        self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
+
+    def forward(self, unknown: torch.Tensor, known: Optional[torch.Tensor], unknow_feats: Optional[torch.Tensor],
+                known_feats: torch.Tensor) -> torch.Tensor:
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+        else:
+            interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+        new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
+        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
