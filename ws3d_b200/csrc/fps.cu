@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
     if (lane == 0) s_wrec[par][warp] = make_int2(wv, (int)wk);
     __syncthreads();
 
-    if (warp == 0) {
+    // CTA winner: every warp reduces the <= 32 warp candidates redundantly (no second barrier);
+    // in cluster mode only warp 0 needs it, to post the CTA's candidate to its peers.
+    uint32_t win_key = kNoKey;
+    if (!CLUSTER || warp == 0) {
       int2 r = lane < nwarps ? s_wrec[par][lane] : make_int2(INT_MIN, (int)kNoKey);
       const int bv = __reduce_max_sync(0xFFFFFFFFu, r.x);
       const uint32_t bk = __reduce_min_sync(0xFFFFFFFFu, r.x == bv ? (uint32_t)r.y : kNoKey);
@@ -216,14 +219,11 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
           st_async_v4(dst, (uint32_t)bv, bk, __float_as_uint(pt.x), __float_as_uint(pt.y), rbar);
           st_async_b32(dst + 16, __float_as_uint(pt.z), rbar);
         }
-      } else if (lane == 0) {
-        Rec rc;
-        rc.v = bv; rc.key = bk; rc.x = pt.x; rc.y = pt.y; rc.z = pt.z;
-        s_crec[par][0] = rc;
+      } else {
+        win_key = bk; cx = pt.x; cy = pt.y; cz = pt.z;
       }
     }
 
-    uint32_t win_key;
     if (CLUSTER) {
       mbar_wait(bar, (uint32_t)(it >> 1) & 1u);
       int v = INT_MIN;
@@ -239,10 +239,6 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
       cx = __shfl_sync(0xFFFFFFFFu, rx, src);
       cy = __shfl_sync(0xFFFFFFFFu, ry, src);
       cz = __shfl_sync(0xFFFFFFFFu, rz, src);
-    } else {
-      __syncthreads();
-      const Rec &rc = s_crec[par][0];
-      win_key = rc.key; cx = rc.x; cy = rc.y; cz = rc.z;
     }
     if (g == 0) {
       idx[it + 1] = (int)fps_unkey(win_key, L);
@@ -376,12 +372,14 @@ int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, f
   int cmax = kNumSMs / (b < 1 ? 1 : b);
   cmax = cmax >= 16 ? 16 : cmax >= 8 ? 8 : cmax >= 4 ? 4 : cmax >= 2 ? 2 : 1;
   if (cmax > 8) cmax = env_int("WS3D_FPS_ALLOW16", 0) ? 16 : 8;
-  int C = pow2_ceil(ceil_div(n, 1024));  // no point in splitting below ~1k points per CTA
+  // measured on B200 (profiles/r1_op_bench_v2.json): one CTA (T=512, P=8) beats any cluster up to 4096 points;
+  // above that a cluster of 8 x 512 threads x 4 points is best when the SMs are there
+  int C = n <= 4096 ? 1 : pow2_ceil(ceil_div(n, 2048));
   if (C > cmax) C = cmax;
   while (ceil_div(n, C) > 8 * 1024 && C < 8) C <<= 1;  // registers: P <= 8 at T = 1024
   C = env_int("WS3D_FPS_C", C);
   int npc = ceil_div(n, C);
-  int T = pow2_ceil(ceil_div(npc, env_int("WS3D_FPS_PPT", 4)));
+  int T = pow2_ceil(ceil_div(npc, env_int("WS3D_FPS_PPT", npc > 2048 ? 8 : 4)));
   if (T < 32) T = 32;
   if (T > 1024) T = 1024;
   T = env_int("WS3D_FPS_T", T);

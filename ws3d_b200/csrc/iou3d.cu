@@ -195,8 +195,11 @@ template <bool IOU>
 __global__ void __launch_bounds__(256) pair_matrix_kernel(int num_a, const float *__restrict__ boxes_a, int num_b,
                                                            const float *__restrict__ boxes_b, float *__restrict__ ans) {
   __shared__ BoxPre sa[kTile], sb[kTile];
+  __shared__ unsigned short s_queue[kTile * kTile];  // pairs that need the exact clipping: r * 64 + c
+  __shared__ int s_count;
   const int a0 = blockIdx.y * kTile, b0 = blockIdx.x * kTile;
   const int na = min(kTile, num_a - a0), nb = min(kTile, num_b - b0);
+  if (threadIdx.x == 0) s_count = 0;
   if (threadIdx.x < 2 * kTile) {
     const int t = threadIdx.x & (kTile - 1);
     if (threadIdx.x < kTile) {
@@ -206,14 +209,25 @@ __global__ void __launch_bounds__(256) pair_matrix_kernel(int num_a, const float
     }
   }
   __syncthreads();
+  // phase 1: AABB screen.  Apart => the result is exactly 0 (overlap and IoU alike): coalesced store.
   const int cb = threadIdx.x & (kTile - 1);
-  if (cb >= nb) return;
-  const BoxPre &bb = sb[cb];
-  for (int r = threadIdx.x >> 6; r < na; r += 4) {
+  if (cb < nb) {
+    const BoxPre &bb = sb[cb];
+    for (int r = threadIdx.x >> 6; r < na; r += 4) {
+      if (aabb_apart(sa[r], bb)) __stcs(ans + (size_t)(a0 + r) * num_b + (b0 + cb), 0.f);
+      else s_queue[atomicAdd(&s_count, 1)] = (unsigned short)(r * kTile + cb);
+    }
+  }
+  __syncthreads();
+  // phase 2: the surviving pairs, densely packed over the threads (no divergence against cheap pairs)
+  const int count = s_count;
+  for (int q = threadIdx.x; q < count; q += 256) {
+    const int r = s_queue[q] >> 6, c = s_queue[q] & (kTile - 1);
     const BoxPre &aa = sa[r];
-    float s = overlap_pair(aa, bb);
+    const BoxPre &bb = sb[c];
+    float s = overlap_exact(aa, bb);
     if (IOU) s = iou_from_overlap(aa, bb, s);
-    __stcs(ans + (size_t)(a0 + r) * num_b + (b0 + cb), s);
+    ans[(size_t)(a0 + r) * num_b + (b0 + c)] = s;
   }
 }
 
@@ -241,30 +255,38 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const
     const int row_size = min(64, n - rb * 64), col_size = min(64, n - cbk * 64);
     const int tid = threadIdx.x;
     if (ROTATED) {
-      __shared__ BoxPre scol[64];
+      __shared__ BoxPre scol[64], srow[64];
+      __shared__ unsigned short s_queue[64 * 64];
+      __shared__ unsigned int s_bits[64][2];
+      __shared__ int s_count;
+      if (tid == 0) s_count = 0;
+      s_bits[tid][0] = 0u; s_bits[tid][1] = 0u;
       if (tid < col_size) precompute(boxes + (size_t)(cbk * 64 + tid) * 5, scol[tid]);
+      if (tid < row_size) precompute(boxes + (size_t)(rb * 64 + tid) * 5, srow[tid]);
       __syncthreads();
       if (tid < row_size) {
-        BoxPre me;
-        precompute(boxes + (size_t)(rb * 64 + tid) * 5, me);
-        unsigned long long bits = 0;
+        const BoxPre &me = srow[tid];
         const int start = (rb == cbk) ? tid + 1 : 0;
-        for (int j = start; j < col_size; ++j) {
-          const BoxPre &o = scol[j];
-          if (aabb_apart(me, o)) continue;  // overlap 0 -> iou 0 -> "> thresh" iff thresh < 0
-          const float s = overlap_exact(me, o);
-          if (iou_from_overlap(me, o, s) > thresh) bits |= 1ULL << j;
+        if (thresh < 0.f) {
+          // degenerate threshold: zero-overlap pairs are suppressed too, so nothing can be screened out
+          for (int j = start; j < col_size; ++j) s_queue[atomicAdd(&s_count, 1)] = (unsigned short)(tid * 64 + j);
+        } else {
+          // AABB apart => overlap 0 => IoU 0 => not "> thresh"
+          for (int j = start; j < col_size; ++j)
+            if (!aabb_apart(me, scol[j])) s_queue[atomicAdd(&s_count, 1)] = (unsigned short)(tid * 64 + j);
         }
-        if (thresh < 0.f) {  // degenerate threshold: even zero-overlap pairs are suppressed
-          bits = 0;
-          for (int j = start; j < col_size; ++j) {
-            const BoxPre &o = scol[j];
-            const float s = overlap_pair(me, o);
-            if (iou_from_overlap(me, o, s) > thresh) bits |= 1ULL << j;
-          }
-        }
-        mask[(size_t)(rb * 64 + tid) * col_blocks + cbk] = bits;
       }
+      __syncthreads();
+      const int count = s_count;
+      for (int q = tid; q < count; q += 64) {
+        const int r = s_queue[q] >> 6, j = s_queue[q] & 63;
+        const float s = overlap_pair(srow[r], scol[j]);
+        if (iou_from_overlap(srow[r], scol[j], s) > thresh) atomicOr(&s_bits[r][j >> 5], 1u << (j & 31));
+      }
+      __syncthreads();
+      if (tid < row_size)
+        mask[(size_t)(rb * 64 + tid) * col_blocks + cbk] =
+            (unsigned long long)s_bits[tid][0] | ((unsigned long long)s_bits[tid][1] << 32);
     } else {
       __shared__ float scol[64 * 5];
       if (tid < col_size)
@@ -304,8 +326,12 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, const uns
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long rem = remv[c], kb = 0;
-      for (int r = 0; r < rows; ++r)
-        if (!((rem >> r) & 1ULL)) { kb |= 1ULL << r; rem |= s_diag[r]; }
+#pragma unroll 8
+      for (int r = 0; r < 64; ++r) {
+        const unsigned long long d = s_diag[r];  // rows beyond `rows` hold 0 and are masked below
+        if (!((rem >> r) & 1ULL)) { kb |= 1ULL << r; rem |= d; }
+      }
+      if (rows < 64) kb &= (1ULL << rows) - 1ULL;
       s_keepbits = kb;
     }
     __syncthreads();
@@ -313,16 +339,20 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, const uns
     const int base = s_total;
     if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ULL))
       keep[base + __popcll(kb & ((1ULL << threadIdx.x) - 1ULL))] = (long long)c * 64 + threadIdx.x;
-    // OR the kept rows into the removal words of the later column blocks
-    for (int j = c + 1 + (int)threadIdx.x; j < col_blocks; j += kScanThreads) {
-      unsigned long long acc = remv[j];
-      unsigned long long bits = kb;
-      while (bits) {
-        const int r = __ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        acc |= mask[(size_t)(c * 64 + r) * col_blocks + j];
+    // OR the kept rows into the removal words of the later column blocks: 16 threads per row, all
+    // loads independent (the mask lives in L2), merged with 32-bit shared/global atomics
+    {
+      const int r = threadIdx.x >> 4, sub = threadIdx.x & 15;
+      if ((kb >> r) & 1ULL) {
+        const unsigned long long *row = mask + (size_t)(c * 64 + r) * col_blocks;
+        unsigned int *remv32 = reinterpret_cast<unsigned int *>(remv);
+#pragma unroll 4
+        for (int j = c + 1 + sub; j < col_blocks; j += 16) {
+          const unsigned long long v = row[j];
+          if ((unsigned int)v) atomicOr(remv32 + 2 * j, (unsigned int)v);
+          if ((unsigned int)(v >> 32)) atomicOr(remv32 + 2 * j + 1, (unsigned int)(v >> 32));
+        }
       }
-      remv[j] = acc;
     }
     __syncthreads();
     if (threadIdx.x == 0) s_total = base + __popcll(kb);

@@ -196,20 +196,21 @@ int ball_query_dispatch(int nr, int b, int n, int m, const float *radius, const 
 constexpr int kGatherThreads = 256;
 
 template <bool VEC>
-__global__ void __launch_bounds__(kGatherThreads) group_points_kernel(int c, int n, long long per_cloud,
+__global__ void __launch_bounds__(kGatherThreads) group_points_kernel(int c, int n, long long per_cloud, int c_per_cta,
                                                                         const float *__restrict__ points,
                                                                         const int *__restrict__ idx,
                                                                         float *__restrict__ out) {
   const size_t cloud = blockIdx.y;
   const long long e0 = ((long long)blockIdx.x * kGatherThreads + threadIdx.x) * (VEC ? 4 : 1);
   if (e0 >= per_cloud) return;
+  const int cb = blockIdx.z * c_per_cta, ce = min(c, cb + c_per_cta);
   const int *ip = idx + cloud * per_cloud + e0;
   const float *src = points + cloud * (size_t)c * n;
   float *dst = out + cloud * (size_t)c * per_cloud + e0;
   if (VEC) {
     const int4 id = __ldg(reinterpret_cast<const int4 *>(ip));
 #pragma unroll 4
-    for (int ci = 0; ci < c; ++ci) {
+    for (int ci = cb; ci < ce; ++ci) {
       const float *row = src + (size_t)ci * n;
       float4 v;
       v.x = __ldg(row + id.x); v.y = __ldg(row + id.y); v.z = __ldg(row + id.z); v.w = __ldg(row + id.w);
@@ -218,33 +219,45 @@ __global__ void __launch_bounds__(kGatherThreads) group_points_kernel(int c, int
   } else {
     const int id = __ldg(ip);
 #pragma unroll 4
-    for (int ci = 0; ci < c; ++ci) dst[(size_t)ci * per_cloud] = __ldg(src + (size_t)ci * n + id);
+    for (int ci = cb; ci < ce; ++ci) dst[(size_t)ci * per_cloud] = __ldg(src + (size_t)ci * n + id);
   }
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(kGatherThreads) group_points_grad_kernel(int c, int n, long long per_cloud,
+__global__ void __launch_bounds__(kGatherThreads) group_points_grad_kernel(int c, int n, long long per_cloud, int c_per_cta,
                                                                              const float *__restrict__ grad_out,
                                                                              const int *__restrict__ idx,
                                                                              float *__restrict__ grad_points) {
   const size_t cloud = blockIdx.y;
   const long long e0 = ((long long)blockIdx.x * kGatherThreads + threadIdx.x) * (VEC ? 4 : 1);
   if (e0 >= per_cloud) return;
+  const int cb = blockIdx.z * c_per_cta, ce = min(c, cb + c_per_cta);
   const int *ip = idx + cloud * per_cloud + e0;
   const float *g = grad_out + cloud * (size_t)c * per_cloud + e0;
   float *dst = grad_points + cloud * (size_t)c * n;
   if (VEC) {
     const int4 id = __ldg(reinterpret_cast<const int4 *>(ip));
 #pragma unroll 2
-    for (int ci = 0; ci < c; ++ci) {
+    for (int ci = cb; ci < ce; ++ci) {
       const float4 v = __ldcs(reinterpret_cast<const float4 *>(g + (size_t)ci * per_cloud));
       float *row = dst + (size_t)ci * n;
       atomicAdd(row + id.x, v.x); atomicAdd(row + id.y, v.y); atomicAdd(row + id.z, v.z); atomicAdd(row + id.w, v.w);
     }
   } else {
     const int id = __ldg(ip);
-    for (int ci = 0; ci < c; ++ci) atomicAdd(dst + (size_t)ci * n + id, g[(size_t)ci * per_cloud]);
+    for (int ci = cb; ci < ce; ++ci) atomicAdd(dst + (size_t)ci * n + id, g[(size_t)ci * per_cloud]);
   }
+}
+
+// Channels handled by one CTA: all of them when the (element tile x cloud) grid already fills the
+// GPU, otherwise split so that at least ~4 CTAs per SM exist (idx is re-read once per split only).
+int channels_per_cta(long long ctas_without_split, int c) {
+  const long long want = 4LL * kNumSMs;
+  if (ctas_without_split >= want || c <= 8) return c > 0 ? c : 1;
+  long long splits = (want + ctas_without_split - 1) / ctas_without_split;
+  int per = (int)((c + splits - 1) / splits);
+  if (per < 8) per = 8;
+  return per;
 }
 
 int group_dispatch(bool grad, int b, int c, int n, long long per_cloud, const float *a, const int *idx, float *o,
@@ -256,13 +269,15 @@ int group_dispatch(bool grad, int b, int c, int n, long long per_cloud, const fl
   const bool vec = (per_cloud % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(grad ? (const void *)a : (const void *)o) & 15u) == 0);
   const long long per_thread = vec ? 4 : 1;
-  dim3 grid((unsigned)((per_cloud + kGatherThreads * per_thread - 1) / (kGatherThreads * per_thread)), (unsigned)b);
+  const long long gx = (per_cloud + kGatherThreads * per_thread - 1) / (kGatherThreads * per_thread);
+  const int c_per_cta = channels_per_cta(gx * b, c);
+  dim3 grid((unsigned)gx, (unsigned)b, (unsigned)ceil_div(c, c_per_cta));
   if (!grad) {
-    if (vec) group_points_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
-    else group_points_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
+    if (vec) group_points_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
+    else group_points_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
   } else {
-    if (vec) group_points_grad_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
-    else group_points_grad_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, a, idx, o);
+    if (vec) group_points_grad_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
+    else group_points_grad_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
   }
   return check_launch(what);
 }
@@ -346,6 +361,42 @@ __global__ void __launch_bounds__(kInterpThreads) three_interpolate_kernel(int c
     t = __fmaf_rn(w0, __ldg(row + i0), t);
     t = __fmaf_rn(w2, __ldg(row + i2), t);
     __stcs(out + (cloud * (size_t)c + ci) * n + i, t);
+  }
+}
+
+// Shared-memory variant for the common case (m*4 bytes per channel row fits): the CB feature rows
+// of a channel chunk are staged once per CTA (one contiguous TMA bulk copy: rows of consecutive
+// channels are adjacent in (B,C,M)), so the three random reads per output become shared-memory reads
+// (a few-way bank conflict) instead of 32 L1 sector look-ups per warp instruction.
+constexpr int kInterpSmemThreads = 512;
+__global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem_kernel(
+    int c, int m, int n, int cb, int n_per_cta, const float *__restrict__ points, const int *__restrict__ idx,
+    const float *__restrict__ weight, float *__restrict__ out) {
+  extern __shared__ __align__(16) float s_rows[];  // cb * m
+  __shared__ __align__(8) unsigned long long s_bar;
+  const size_t cloud = blockIdx.z;
+  const int c0 = blockIdx.x * cb, cn = min(cb, c - c0);
+  const int i_begin = blockIdx.y * n_per_cta, i_end = min(n, i_begin + n_per_cta);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  stage_floats(s_rows, points + (cloud * (size_t)c + c0) * m, cn * m, &s_bar, 0);
+  for (int i = i_begin + (int)threadIdx.x; i < i_end; i += kInterpSmemThreads) {
+    const int *ip = idx + (cloud * (size_t)n + i) * 3;
+    const float *wp = weight + (cloud * (size_t)n + i) * 3;
+    const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+    const float w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+    float *o = out + (cloud * (size_t)c + c0) * n + i;
+#pragma unroll 4
+    for (int cc = 0; cc < cn; ++cc) {
+      const float *row = s_rows + cc * m;
+      float t = __fmul_rn(w1, row[i1]);
+      t = __fmaf_rn(w0, row[i0], t);
+      t = __fmaf_rn(w2, row[i2], t);
+      __stcs(o + (size_t)cc * n, t);
+    }
   }
 }
 
@@ -441,6 +492,26 @@ WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *poi
   if (b == 0 || c == 0 || n == 0) return 0;
   if (!points || !idx || !weight || !out) return fail_arg("three_interpolate (null pointer)");
   if (b > 65535 || ceil_div(c, kInterpChannels) > 65535) return fail_arg("three_interpolate (grid too large)");
+  if (m > 0 && (size_t)m * 4 <= 32 * 1024 && n >= 256) {
+    // channel rows per CTA: as many as fit in ~128 KB, at least 4 CTAs per SM worth of work overall
+    int cb = (int)((128 * 1024) / ((size_t)m * 4));
+    if (cb > 64) cb = 64;
+    if (cb > c) cb = c;
+    while (cb > 8 && (long long)ceil_div(c, cb) * b < 2LL * kNumSMs) cb >>= 1;
+    const int chunks = ceil_div(c, cb);
+    int nsplit = 1;
+    while ((long long)chunks * b * nsplit < 2LL * kNumSMs && ceil_div(n, nsplit * 2) >= 2 * kInterpSmemThreads) nsplit <<= 1;
+    const int n_per_cta = ceil_div(n, nsplit);
+    const size_t smem = (size_t)cb * m * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(three_interpolate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("three_interpolate: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    if (chunks <= 65535 * 32 && nsplit <= 65535) {
+      dim3 grid((unsigned)chunks, (unsigned)nsplit, (unsigned)b);
+      three_interpolate_smem_kernel<<<grid, kInterpSmemThreads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx,
+                                                                                         weight, out);
+      return check_launch("three_interpolate");
+    }
+  }
   dim3 grid((unsigned)ceil_div(n, kInterpThreads), (unsigned)ceil_div(c, kInterpChannels), (unsigned)b);
   three_interpolate_kernel<<<grid, kInterpThreads, 0, to_stream(stream)>>>(c, m, n, points, idx, weight, out);
   return check_launch("three_interpolate");

@@ -16,7 +16,7 @@ constexpr int kThreads = 256;
 
 // Each thread owns EPT consecutive neighbours of one centre (K % EPT == 0).
 template <int EPT>
-__global__ void __launch_bounds__(kThreads) group_concat_kernel(int c, int n, int m, int K, int use_xyz,
+__global__ void __launch_bounds__(kThreads) group_concat_kernel(int c, int n, int m, int K, int use_xyz, int c_per_cta,
                                                                  const float *__restrict__ xyz,
                                                                  const float *__restrict__ new_xyz,
                                                                  const float *__restrict__ features,
@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(kThreads) group_concat_kernel(int c, int n, in
   }
   const int cout = c + (use_xyz ? 3 : 0);
   float *dst = out + cloud * (size_t)cout * per_cloud + e0;
-  if (use_xyz) {
+  const int cb = blockIdx.z * c_per_cta, ce = min(c, cb + c_per_cta);
+  if (use_xyz && blockIdx.z == 0) {
     const float *ctr = new_xyz + (cloud * (size_t)m + j) * 3;
     const float *pts = xyz + cloud * (size_t)n * 3;
     float v[3][EPT];
@@ -58,11 +59,14 @@ __global__ void __launch_bounds__(kThreads) group_concat_kernel(int c, int n, in
       }
       dst += per_cloud;
     }
+  } else if (use_xyz) {
+    dst += 3 * per_cloud;
   }
-  if (c > 0) {
+  if (cb < ce) {
     const float *src = features + cloud * (size_t)c * n;
+    dst += (size_t)cb * per_cloud;
 #pragma unroll 4
-    for (int ci = 0; ci < c; ++ci) {
+    for (int ci = cb; ci < ce; ++ci) {
       const float *row = src + (size_t)ci * n;
       if (EPT == 4) {
         float4 f;
@@ -85,13 +89,16 @@ int group_concat(int b, int n, int m, int c, int K, int use_xyz, const float *xy
   const long long per_cloud = (long long)m * K;
   const bool vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-  if (vec) {
-    dim3 grid((unsigned)((per_cloud + kThreads * 4 - 1) / (kThreads * 4)), (unsigned)b);
-    group_concat_kernel<4><<<grid, kThreads, 0, stream>>>(c, n, m, K, use_xyz, xyz, new_xyz, features, idx, out);
-  } else {
-    dim3 grid((unsigned)((per_cloud + kThreads - 1) / kThreads), (unsigned)b);
-    group_concat_kernel<1><<<grid, kThreads, 0, stream>>>(c, n, m, K, use_xyz, xyz, new_xyz, features, idx, out);
+  const long long gx = (per_cloud + kThreads * (vec ? 4 : 1) - 1) / (kThreads * (vec ? 4 : 1));
+  int c_per_cta = c > 0 ? c : 1;
+  if (gx * b < 4LL * kNumSMs && c > 8) {
+    const long long splits = (4LL * kNumSMs + gx * b - 1) / (gx * b);
+    c_per_cta = (int)((c + splits - 1) / splits);
+    if (c_per_cta < 8) c_per_cta = 8;
   }
+  dim3 grid((unsigned)gx, (unsigned)b, (unsigned)(c > 0 ? ceil_div(c, c_per_cta) : 1));
+  if (vec) group_concat_kernel<4><<<grid, kThreads, 0, stream>>>(c, n, m, K, use_xyz, c_per_cta, xyz, new_xyz, features, idx, out);
+  else group_concat_kernel<1><<<grid, kThreads, 0, stream>>>(c, n, m, K, use_xyz, c_per_cta, xyz, new_xyz, features, idx, out);
   return check_launch("query_and_group (group)");
 }
 
