@@ -146,6 +146,9 @@ ALG_BYTES = {
     "group_concat": lambda b, n, m, c, k, **kw: b * (4 * m * k + 12 * n + 4 * c * n + 12 * m + 4 * (3 + c) * m * k),
     "three_nn": lambda b, n, m, **k: b * (12 * n + 12 * m + 24 * n),
     "three_interpolate": lambda b, c, m, n, **k: b * (4 * c * m + 24 * n + 4 * c * n),
+    # one shared-MLP layer: read (c1+c2) x cols, write c_out x cols (or cols/pool), read the folded weights once
+    "mlp_layer": lambda b, c_out, c_in, cols, pool, **k: 4 * (b * c_in * cols + b * c_out * (cols // pool if pool else cols)
+                                                              + c_out * c_in),
 }
 
 
@@ -177,6 +180,8 @@ class OpProfiler:
             "group_concat": ("group_concat", lambda b, n, m, c, k, *r: dict(b=b, n=n, m=m, c=c, k=k)),
             "three_nn_wrapper": ("three_nn", lambda b, n, m, *r: dict(b=b, n=n, m=m)),
             "three_interpolate_wrapper": ("three_interpolate", lambda b, c, m, n, *r: dict(b=b, c=c, m=m, n=n)),
+            "mlp_layer": ("mlp_layer", lambda b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool:
+                          dict(b=b, c_out=c_out, c_in=c1 + c2, cols=cols, pool=pool)),
         }
         for attr, (name, dims) in table.items():
             self._orig[attr] = getattr(native, attr)
@@ -312,7 +317,8 @@ def run_gpu(args):
             "config": {"workload": "PointNet++-MSG backbone forward (4 SA + 4 FP, weaklyRPN.yaml shapes), batch 16 synthetic "
                                    "KITTI clouds 16384x4 per GPU (BASELINE configs[1])",
                        "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": "flushed between timed iterations (256 MiB write)",
-                       "mlp": "PyTorch/cuDNN fp32 (TF32 " + ("on" if torch.backends.cudnn.allow_tf32 else "off") + ")",
+                       "mlp": ("tcgen05 TF32 shared-MLP layers (conv1x1+BN+ReLU[+max-pool] per launch, FP32 accumulate)"
+                               if torch.backends.cudnn.allow_tf32 else "PyTorch/cuDNN fp32 (TF32 off)"),
                        "sharding": "scenes per rank, no data-path collective"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4) * world,
                     "d2h_bytes_per_step": BATCH * 4 * world, "ms_per_step": round(ms_e2e / args.steps, 4),

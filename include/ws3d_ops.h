@@ -126,6 +126,19 @@ int ws3d_three_interpolate(int b, int c, int m, int n, const float *points, cons
 int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                 const float *weight, float *grad_points, ws3d_stream_t stream);
 
+/* Extension: one shared-MLP layer -- 1x1 conv with BatchNorm(eval) folded
+ * in, optional ReLU, optional max-pool over runs of `pool` consecutive columns -- on the tcgen05 tensor
+ * cores (TF32 inputs, FP32 accumulate), replacing the conv / BN / ReLU / max-pool kernel sequence of
+ * pointnet2_modules.py:40-44,154 + pytorch_utils.py:5-32 in inference.
+ *   w (c_out_pad, 32*(ceil(c1/32)+ceil(c2/32))) row-major, zero padded, c_out_pad % 128 == 0;
+ *   x1 (B, c1, cols), x2 (B, c2, cols) or NULL (second K range, e.g. skip features); shift (c_out_pad);
+ *   out (B, c_out, cols) or, when pool > 0, (B, c_out, cols / pool).  cols % 4 == 0; pool divides 256 and cols.
+ *   relu: bit 0 = apply ReLU; bit 1 = round the stored output to the nearest TF32 value (use for every layer
+ *   whose output feeds another ws3d_mlp_layer: the tensor core truncates FP32 operands to TF32). */
+int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w,
+                   const float *shift, const float *x1, const float *x2, float *out, int relu, int pool,
+                   ws3d_stream_t stream);
+
 /* ---- iou3d_cuda ------------------------------------------------------------ */
 
 /* Replaces boxesoverlapLauncher (lib/utils/iou3d/src/iou3d.cpp:26, iou3d_kernel.cu:354-363).

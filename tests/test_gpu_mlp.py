@@ -1,0 +1,91 @@
+"""GPU: the tcgen05 shared-MLP layer vs PyTorch (conv1x1 + BN(eval) + ReLU [+ max-pool]).
+TF32 inputs / FP32 accumulate.  The FP32 torch result (TF32 disabled) is the reference; tolerance
+TOL = 3e-3 of the output scale over up to three chained layers: weights and intermediate activations
+are rounded to nearest TF32 (2^-11 relative each), the raw first-layer input is truncated by the
+tensor core (2^-10) -- the same class of error as cuDNN's default TF32 convolutions."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+TOL = 3e-3
+
+
+def _mlp(spec, seed):
+    from ws3d_b200 import pytorch_utils as pt_utils
+    torch.manual_seed(seed)
+    mlp = pt_utils.SharedMLP(list(spec), bn=True).to(dev).eval()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for m in mlp.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
+    return mlp
+
+
+def _ref(mlp, x, pool):
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            y = mlp(x)
+            if pool:
+                y = F.max_pool2d(y, kernel_size=[1, y.size(3)]).squeeze(-1)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return y
+
+
+@pytest.mark.parametrize("spec,B,M,K", [((4, 16, 16, 32), 2, 512, 16), ((4, 32, 32, 64), 1, 1024, 32), ((99, 64, 96, 128), 2, 256, 32),
+                                        ((259, 128, 196, 256), 2, 64, 16), ((515, 256, 384, 512), 1, 64, 32), ((35, 40), 3, 100, 4)])
+def test_folded_mlp_with_pool_matches_torch(spec, B, M, K):
+    from ws3d_b200 import fused_mlp
+    mlp = _mlp(spec, seed=sum(spec))
+    x = torch.randn(B, spec[0], M, K, device=dev)
+    want = _ref(mlp, x, pool=True)
+    with torch.no_grad():
+        got = fused_mlp.FoldedMLP(mlp)(x.view(B, spec[0], M * K), pool=K)
+    assert got.shape == want.shape
+    scale = float(want.abs().max()) + 1e-6
+    assert float((got - want).abs().max()) <= TOL * scale + 1e-4, float((got - want).abs().max()) / scale
+    # and without pooling (every layer's full output)
+    want_full = _ref(mlp, x, pool=False).view(B, spec[-1], M * K)
+    with torch.no_grad():
+        got_full = fused_mlp.FoldedMLP(mlp)(x.view(B, spec[0], M * K))
+    assert float((got_full - want_full).abs().max()) <= TOL * (float(want_full.abs().max()) + 1e-6) + 1e-4
+
+
+@pytest.mark.parametrize("c1,c2,spec,n", [(256, 1, (257, 128, 128), 1024), (512, 96, (608, 256, 256), 512), (1024, 512, (1536, 512, 512), 64),
+                                           (40, 0, (40, 24), 300)])
+def test_two_input_first_layer_equals_concat(c1, c2, spec, n):
+    from ws3d_b200 import fused_mlp
+    mlp = _mlp(spec, seed=c1 + c2)
+    B = 2
+    a = torch.randn(B, c1, n, device=dev)
+    b = torch.randn(B, c2, n, device=dev) if c2 else None
+    x = a if b is None else torch.cat([a, b], dim=1)
+    want = _ref(mlp, x.unsqueeze(-1), pool=False).squeeze(-1)
+    with torch.no_grad():
+        got = fused_mlp.FoldedMLP(mlp, first_split=(c1, c2))(a, b)
+    assert float((got - want).abs().max()) <= TOL * (float(want.abs().max()) + 1e-6) + 1e-4
+
+
+def test_backbone_fused_eval_path_close_to_fp32_path():
+    from ws3d_b200 import models, synth
+    torch.manual_seed(0)
+    model = models.Pointnet2MSG(input_channels=1).to(dev).eval()
+    pts = torch.from_numpy(synth.make_batch(2)).to(dev)
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = True
+        _, fused = model(pts)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        _, exact = model(pts)
+        torch.backends.cudnn.allow_tf32 = True
+    rel = float((fused - exact).abs().max()) / (float(exact.abs().max()) + 1e-6)
+    assert rel < 2e-2, rel     # 8 layers of TF32 rounding, same order as cuDNN's TF32 path
+    assert torch.isfinite(fused).all()

@@ -95,6 +95,58 @@ def test_ball_query_matches_oracle_and_reference(b, n, m, r, k, kind):
         assert torch.equal(ridx, idx)
 
 
+GRID_CASES = ["dense_cluster", "duplicates", "flat", "line", "nonfinite", "tiny_radius", "huge_radius", "offset", "integer_lattice"]
+
+
+@pytest.mark.parametrize("kind", GRID_CASES)
+def test_ball_query_cell_grid_edge_cases(kind):
+    """n >= 2048 takes the cell-grid path (csrc/ball_query_grid.cu); every case must equal the plain scan."""
+    from ws3d_b200 import pointnet2_utils
+    rng = np.random.default_rng(len(kind) * 977)
+    b, n, m, r, k = 2, 4096, 512, 0.5, 32
+    xyz = rng.uniform(-20, 20, (b, n, 3)).astype(np.float32)
+    if kind == "dense_cluster":      # > 128 hits per ball: hit-buffer overflow -> in-order early-exit scan
+        xyz[:, : n // 2] = rng.normal(0, 0.15, (b, n // 2, 3)).astype(np.float32)
+    elif kind == "duplicates":
+        xyz[:, 1::2] = xyz[:, 0::2]
+    elif kind == "flat":             # one cell layer in y
+        xyz[..., 1] = 1.5
+    elif kind == "line":             # 1-D: per-axis cell cap and enlargement of the cell edge
+        xyz[..., 1:] = 0.0
+        xyz[..., 0] = rng.uniform(-3000, 3000, (b, n)).astype(np.float32)
+    elif kind == "nonfinite":
+        xyz[:, 5, 0] = np.nan; xyz[:, 9, 1] = np.inf; xyz[:, 11, 2] = -np.inf
+    elif kind == "tiny_radius":
+        r = 1e-4
+    elif kind == "huge_radius":      # a single cell: everything is a candidate
+        r, k = 100.0, 16
+    elif kind == "offset":           # large coordinates: rounding of the cell coordinate
+        xyz += np.float32(5000.0)
+    elif kind == "integer_lattice":  # many points exactly on cell boundaries and at distance exactly r
+        xyz = rng.integers(-8, 9, (b, n, 3)).astype(np.float32) * np.float32(0.5)
+    pick = rng.integers(0, n, (b, m))
+    new_xyz = np.take_along_axis(xyz, pick[..., None], 1).copy()
+    new_xyz[:, :16] += np.float32(0.3)           # centres that are not points
+    new_xyz[:, 16:24] += np.float32(1000.0)      # far outside the bounding box
+    new_xyz[:, 24:28, 0] -= np.float32(0.4)      # just outside / on the box faces
+    if kind == "nonfinite":
+        new_xyz[:, 30, 0] = np.nan; new_xyz[:, 31, 2] = np.inf
+    with np.errstate(invalid="ignore", over="ignore"):
+        exp = oracle.ball_query(r, k, xyz, new_xyz)
+    x, q = _t(xyz), _t(new_xyz)
+    idx = pointnet2_utils.ball_query(r, k, x, q)
+    np.testing.assert_array_equal(idx.cpu().numpy(), exp)
+    i0, i1 = pointnet2_utils.ball_query_pair((r * 0.5, r), (16, k), x, q)
+    np.testing.assert_array_equal(i1.cpu().numpy(), exp)
+    with np.errstate(invalid="ignore", over="ignore"):
+        np.testing.assert_array_equal(i0.cpu().numpy(), oracle.ball_query(r * 0.5, 16, xyz, new_xyz))
+    ref = load_ref("pointnet2_cuda")
+    if ref is not None:
+        ridx = torch.zeros((b, m, k), dtype=torch.int32, device=dev)
+        ref.ball_query_wrapper(b, n, m, r, k, q, x, ridx)
+        assert torch.equal(ridx, idx)
+
+
 def test_ball_query_pair_equals_two_queries():
     from ws3d_b200 import pointnet2_utils
     rng = np.random.default_rng(5)

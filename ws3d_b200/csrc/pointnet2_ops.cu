@@ -14,11 +14,18 @@
 //   * three_nn: known points staged in shared memory as float4, thread per unknown point.
 // Index-producing ops are bit-exact with the reference (same rounding order, same tie rules).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tma.cuh"
 
 namespace ws3d {
+
+// ball_query_grid.cu: cell-list pruned scan for clouds that are large against the ball
+bool ball_query_grid_applicable(int nr, int b, int n, int m, const float *radius);
+int ball_query_grid(int nr, int b, int n, int m, const float *radius, const int *nsample, const float *new_xyz,
+                    const float *xyz, int *const *idx, cudaStream_t stream);
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -176,6 +183,11 @@ int ball_query_dispatch(int nr, int b, int n, int m, const float *radius, const 
   if (b == 0 || m == 0 || n == 0) return 0;
   if (!new_xyz || !xyz) return fail_arg("ball_query (null pointer)");
   if (b > 65535) return fail_arg("ball_query (batch > 65535)");
+  {
+    static const int use_grid = []() { const char *e = getenv("WS3D_BQ_GRID"); return (e && *e) ? atoi(e) : 1; }();
+    if (use_grid && ball_query_grid_applicable(nr, b, n, m, radius))
+      return ball_query_grid(nr, b, n, m, radius, nsample, new_xyz, xyz, idx, stream);
+  }
   if (n > kBqMaxChunkPts) {
     for (int r = 0; r < nr; ++r) {
       if (nsample[r] == 0) continue;

@@ -1,0 +1,109 @@
+"""Inference-time SharedMLP on the tcgen05 tensor cores.
+
+`FoldedMLP` is a read-only view of a `pytorch_utils.SharedMLP` (conv1x1 [+ BN] [+ ReLU] per layer):
+BatchNorm (eval statistics) is folded into the conv weight and a per-channel shift, weights are
+zero-padded to the kernel's tile sizes once, and every layer runs as one `ws3d_mlp_layer` launch
+(GEMM + shift + ReLU, and for the last layer of a set-abstraction scale the max-pool over nsample).
+Numerics: TF32 inputs with FP32 accumulation -- what PyTorch's cuDNN convolutions use by default
+(`torch.backends.cudnn.allow_tf32`); when TF32 is disallowed the modules keep the PyTorch FP32 path.
+Training (batch statistics, autograd) always uses the PyTorch path.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import native
+
+_TILE_M = 128
+_CHUNK_K = 32
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def _round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """Round FP32 to the nearest TF32 (10-bit mantissa), ties away from zero."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def enabled_for(module: nn.Module) -> bool:
+    """The fused path is taken in eval mode, without autograd, when TF32 convolutions are allowed."""
+    return (not module.training) and (not torch.is_grad_enabled()) and torch.backends.cudnn.allow_tf32
+
+
+class _Layer:
+    __slots__ = ("w", "shift", "c_out", "c_out_pad", "relu", "splits")
+
+
+class FoldedMLP:
+    """Folded, padded weights of one SharedMLP.  `first_split=(c1, c2)` says the first layer's input
+    arrives as two tensors (channels c1 then c2), which are read in place instead of concatenated."""
+
+    def __init__(self, mlp: nn.Sequential, first_split: Optional[Tuple[int, int]] = None):
+        self.layers: List[_Layer] = []
+        self._versions = None
+        self._mlp = mlp
+        self._first_split = first_split
+        self._build()
+
+    def _params(self):
+        return [p for p in self._mlp.parameters()] + [b for b in self._mlp.buffers()]
+
+    def _stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self._params())
+
+    def _build(self):
+        self.layers = []
+        for li, block in enumerate(self._mlp):
+            conv = block.conv
+            assert conv.kernel_size in ((1, 1), (1,)) and conv.stride in ((1, 1), (1,)), "shared MLPs are 1x1 convolutions"
+            w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
+            shift = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+            if hasattr(block, "bn"):
+                bn = block.bn.bn
+                scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+                w = w * scale[:, None]
+                shift = (shift - bn.running_mean) * scale + bn.bias.detach()
+            c_out, c_in = w.shape
+            splits = self._first_split if (li == 0 and self._first_split is not None and self._first_split[1] > 0) else (c_in, 0)
+            assert sum(splits) == c_in
+            k1, k2 = _ceil(splits[0], _CHUNK_K), (_ceil(splits[1], _CHUNK_K) if splits[1] else 0)
+            lay = _Layer()
+            lay.c_out, lay.c_out_pad = c_out, _ceil(c_out, _TILE_M)
+            w = _round_tf32(w)  # the tensor core truncates FP32 operands to TF32: round the weights to nearest first
+            wp = torch.zeros((lay.c_out_pad, k1 + k2), dtype=torch.float32, device=w.device)
+            wp[:c_out, :splits[0]] = w[:, :splits[0]]
+            if splits[1]:
+                wp[:c_out, k1:k1 + splits[1]] = w[:, splits[0]:]
+            sp = torch.zeros(lay.c_out_pad, dtype=torch.float32, device=w.device)
+            sp[:c_out] = shift
+            lay.w, lay.shift, lay.splits = wp.contiguous(), sp, splits
+            lay.relu = hasattr(block, "activation")
+            self.layers.append(lay)
+        self._versions = self._stamp()
+
+    def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, pool: int = 0) -> torch.Tensor:
+        """x1 (B, c1, cols) [, x2 (B, c2, cols)] -> (B, c_last, cols) or (B, c_last, cols // pool)."""
+        if self._versions != self._stamp():
+            self._build()  # parameters were updated (training step, load_state_dict, .to())
+        B, _, cols = x1.shape
+        cur1, cur2 = x1, x2
+        for li, lay in enumerate(self.layers):
+            last = li == len(self.layers) - 1
+            p = pool if last else 0
+            out = torch.empty((B, lay.c_out, cols // p if p else cols), dtype=torch.float32, device=x1.device)
+            c1 = cur1.shape[1]
+            c2 = cur2.shape[1] if cur2 is not None else 0
+            assert (c1, c2) == tuple(lay.splits), ((c1, c2), lay.splits)
+            flags = int(lay.relu) | (0 if last else 2)  # intermediate activations are stored TF32-rounded
+            native.mlp_layer(B, lay.c_out, lay.c_out_pad, c1, c2, cols, lay.w, lay.shift, cur1, cur2, out, flags, p)
+            cur1, cur2 = out, None
+        return cur1
+
+
+def supported(cols: int, pool: int) -> bool:
+    """Shapes the kernel accepts: 16-byte aligned rows; pooling groups that divide the 256-column tile."""
+    return cols % 4 == 0 and (pool == 0 or (256 % pool == 0 and cols % pool == 0))

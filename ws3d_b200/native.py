@@ -114,6 +114,15 @@ def query_and_group(b, n, m, c, radius, nsample, use_xyz, xyz, new_xyz, features
               "query_and_group")
 
 
+def mlp_layer(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool):
+    """One BN-folded shared-MLP layer on the tcgen05 tensor cores (see include/ws3d_ops.h).
+    `relu`: bit 0 = ReLU, bit 1 = round the output to TF32 (it feeds another layer)."""
+    require_cuda(w, shift, x1, x2, out)
+    with device_of(out):
+        check(lib().ws3d_mlp_layer(b, c_out, c_out_pad, c1, c2, cols, ptr(w), ptr(shift), ptr(x1), ptr(x2), ptr(out),
+                                   int(relu), int(pool), stream()), "mlp_layer")
+
+
 # ---- iou3d_cuda -------------------------------------------------------------------------------
 def _check_boxes(*ts):
     for t in ts:

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused_mlp
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
@@ -28,6 +29,12 @@ class _PointnetSAModuleBase(nn.Module):
         self.groupers = None
         self.mlps = None
         self.pool_method = 'max_pool'
+
+    def _folded(self, k):
+        cache = self.__dict__.setdefault("_folded_mlps", {})
+        if k not in cache:
+            cache[k] = fused_mlp.FoldedMLP(self.mlps[k])
+        return cache[k]
 
     def _neighbour_indices(self, xyz, new_xyz):
         """ball_query for every scale; scales are scanned two at a time."""
@@ -52,8 +59,14 @@ class _PointnetSAModuleBase(nn.Module):
         else:
             indices = [None] * len(self.groupers)  # GroupAll
         pooled = []
-        for grouper, mlp, idx in zip(self.groupers, self.mlps, indices):
+        fused = fused_mlp.enabled_for(self) and self.pool_method == 'max_pool'
+        for k, (grouper, mlp, idx) in enumerate(zip(self.groupers, self.mlps, indices)):
             grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
+            B, C, M, K = grouped.shape
+            if fused and fused_mlp.supported(M * K, K):
+                # inference: every layer is one tensor-core launch; the last one also max-pools over nsample
+                pooled.append(self._folded(k)(grouped.view(B, C, M * K), pool=K))
+                continue
             grouped = mlp(grouped)
             if self.pool_method == 'max_pool':
                 grouped = F.max_pool2d(grouped, kernel_size=[1, grouped.size(3)])
@@ -111,5 +124,13 @@ class PointnetFPModule(nn.Module):
             interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+        if fused_mlp.enabled_for(self) and fused_mlp.supported(unknown.size(1), 0) and interpolated.is_contiguous():
+            # inference: the skip features are read in place as the second K range (no torch.cat)
+            split = (interpolated.shape[1], 0 if unknow_feats is None else unknow_feats.shape[1])
+            folded = self.__dict__.get("_folded_mlp")
+            if folded is None or folded._first_split != split:
+                folded = self.__dict__["_folded_mlp"] = fused_mlp.FoldedMLP(self.mlp, first_split=split)
+            skip = None if unknow_feats is None else unknow_feats.contiguous()
+            return folded(interpolated, skip)
         new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
