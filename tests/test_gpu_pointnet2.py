@@ -35,6 +35,8 @@ FPS_CASES = [
     (1, 1, 1, "uniform"), (2, 5000, 100, "uniform"), (2, 2048, 512, "grid"), (1, 300, 300, "grid"),
     (1, 64, 100, "uniform"),  # m > n: the sampler keeps re-selecting (all distances 0)
     (200, 512, 128, "uniform"), (1, 20000, 64, "uniform"), (20, 16384, 16, "uniform"),
+    # batches that leave < 4 SMs per cloud take the spatially bucketed single-CTA kernel (csrc/fps_bucket.cu)
+    (40, 2048, 128, "uniform"), (38, 4096, 64, "grid"), (40, 5000, 300, "scene"), (38, 16384, 256, "scene"),
 ]
 
 

@@ -24,67 +24,13 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "fps_common.cuh"
 #include "tma.cuh"
 
 namespace ws3d {
 namespace {
 
-constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kMaxCluster = 16;
-
-// key(k): top L bits = bit-reversed (k mod 2^L), low 32-L bits = k >> L.
-__host__ __device__ __forceinline__ uint32_t brev32(uint32_t v) {
-#ifdef __CUDA_ARCH__
-  return __brev(v);
-#else
-  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
-  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
-  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
-  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
-  return (v >> 16) | (v << 16);
-#endif
-}
-__host__ __device__ __forceinline__ uint32_t fps_key(uint32_t k, int L) {
-  if (L == 0) return k;
-  const uint32_t lowmask = 0xFFFFFFFFu >> L;
-  return (brev32(k) & ~lowmask) | (k >> L);
-}
-__host__ __device__ __forceinline__ uint32_t fps_unkey(uint32_t key, int L) {
-  if (L == 0) return key;
-  const uint32_t lowmask = 0xFFFFFFFFu >> L;
-  return ((key & lowmask) << L) | brev32(key & ~lowmask);
-}
-
-// ---- cluster / mbarrier / DSMEM primitives (raw PTX) --------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
-                                            uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
-               "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
-               : "memory");
-}
-__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a),
-               "r"(rbar)
-               : "memory");
-}
 
 struct __align__(16) Rec {  // one candidate: 20 payload bytes in a 32-byte slot
   int v;                    // running-distance bits (>= 0 for real points)
@@ -94,14 +40,6 @@ struct __align__(16) Rec {  // one candidate: 20 payload bytes in a 32-byte slot
   float pad[3];
 };
 
-struct FpsParams {
-  int n, m, L;       // points, samples, log2(reference block size)
-  int log2T;         // blockDim.x == 1 << log2T
-  const float *xyz;  // (B,N,3)
-  float *temp;       // (B,N) or null
-  int *idx;          // (B,M)
-  float *new_xyz;    // (B,M,3) or null
-};
 
 template <int P>
 __device__ __forceinline__ void sort_by_key(uint32_t (&key)[P], float (&x)[P], float (&y)[P], float (&z)[P],
@@ -367,6 +305,9 @@ int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, f
   FpsParams prm;
   prm.n = n; prm.m = m; prm.L = ilog2(ref_block_size(n));
   prm.xyz = xyz; prm.temp = temp; prm.idx = idx; prm.new_xyz = new_xyz;
+  prm.log2T = 0;
+  // large clouds: spatially bucketed kernel, one CTA per cloud (fps_bucket.cu)
+  if (fps_bucket_applicable(b, n, m)) return fps_bucket_launch(prm, b, stream);
 
   // --- decomposition: C CTAs per cloud, T threads per CTA, P points per thread
   int cmax = kNumSMs / (b < 1 ? 1 : b);
