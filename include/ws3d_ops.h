@@ -134,7 +134,9 @@ int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_ou
  *   x1 (B, c1, cols), x2 (B, c2, cols) or NULL (second K range, e.g. skip features); shift (c_out_pad);
  *   out (B, c_out, cols) or, when pool > 0, (B, c_out, cols / pool).  cols % 4 == 0; pool divides 256 and cols.
  *   relu: bit 0 = apply ReLU; bit 1 = round the stored output to the nearest TF32 value (use for every layer
- *   whose output feeds another ws3d_mlp_layer: the tensor core truncates FP32 operands to TF32). */
+ *   whose output feeds another ws3d_mlp_layer: the tensor core truncates FP32 operands to TF32);
+ *   bits 4-5 = log2(r), r in {1, 2, 4}: rows [k*128/r, (k+1)*128/r) of w (and shift) each hold a copy of the
+ *   c_out <= 128/r real rows (c_out_pad must be 128) -- lets all four epilogue warps work on narrow layers. */
 int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w,
                    const float *shift, const float *x1, const float *x2, float *out, int relu, int pool,
                    ws3d_stream_t stream);

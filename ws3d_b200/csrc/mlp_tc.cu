@@ -21,6 +21,7 @@
 // A second input tensor can supply the tail of the K range (the skip features of a feature-propagation
 // layer), so the torch.cat of pointnet2_modules.py:149 is never materialised.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -28,7 +29,6 @@
 namespace ws3d {
 namespace {
 
-constexpr int kStages = 4;
 constexpr int kChunkK = 32;        // fp32 elements per K chunk = one 128-byte swizzle row
 constexpr int kTileM = 128;        // output channels per CTA (UMMA M)
 constexpr int kThreads = 192;
@@ -38,7 +38,7 @@ struct MlpParams {
   int cols;         // grouped points per cloud (npoint * nsample, or n)
   int nk1, nk2;     // K chunks taken from input 1 / input 2
   int pool;         // 0: write (B, c_out, cols); else nsample: write (B, c_out, cols / nsample)
-  int flags;        // bit 0: ReLU, bit 1: round the stored output to TF32 (input of a following layer)
+  int flags;        // bit 0: ReLU, bit 1: round the stored output to TF32, bits 4-5: log2(copies of the weight rows)
   const float *shift;  // (c_out_padded)
   float *out;
 };
@@ -96,8 +96,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const __grid_constant__ CUtensorMap map_w,
+template <int NT, int kStages, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const __grid_constant__ CUtensorMap map_w,
                                                                 const __grid_constant__ CUtensorMap map_x1,
                                                                 const __grid_constant__ CUtensorMap map_x2,
                                                                 const MlpParams prm) {
@@ -178,21 +178,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const __grid_con
     }
   } else {
     // ---- epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
+    // With few output channels the weight rows are REPLICATED over the 128 MMA rows (rep = 2 or 4 copies, made
+    // by the host): every TMEM quarter then holds real channels and the four epilogue warps split the columns,
+    // instead of one warp draining the whole tile.
     const int quarter = warp & 3;
-    const int co = m0 + quarter * 32 + lane;
+    const int rep_log2 = (prm.flags >> 4) & 3;
+    const int rows_per_copy = kTileM >> rep_log2;                 // 128, 64 or 32
+    const int co = m0 + ((quarter * 32 + lane) & (rows_per_copy - 1));
+    const int part = (quarter * 32) / rows_per_copy;              // which column share this warp drains
+    const int cbeg = part * (NT >> rep_log2), cend = cbeg + (NT >> rep_log2);
     mbar_wait(smem_u32(&s_tmem_full), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const bool live = co < prm.c_out;
     const float shift = live ? __ldg(prm.shift + co) : 0.f;
     const bool relu = (prm.flags & 1) != 0, round_out = (prm.flags & 2) != 0;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const bool warp_live = m0 + quarter * 32 < prm.c_out;  // a quarter with no real channel has nothing to read
+    const bool warp_live = m0 + ((quarter * 32) & (rows_per_copy - 1)) < prm.c_out;  // a quarter with no real channel has nothing to read
     if (warp_live && prm.pool == 0) {
-      float *dst = prm.out + ((size_t)cloud * prm.c_out + co) * prm.cols + col0;
-      for (int c = 0; c < NT && col0 + c < prm.cols; c += 32) {
+      // Each lane holds one channel row (32 consecutive columns per TMEM load).  Storing that directly would touch
+      // 32 different cache lines with 16 bytes each per instruction; the chunk is transposed through shared memory
+      // (the operand ring is free once the accumulator is complete) so that every store instruction writes four
+      // full 128-byte lines.
+      float *stage = reinterpret_cast<float *>(s_raw + (stage_base - smem_u32(s_raw))) + quarter * (32 * 36);
+      const int co_base = m0 + ((quarter * 32) & (rows_per_copy - 1));
+      const int srow = lane >> 3, scol = (lane & 7) * 4;
+      for (int c = cbeg; c < cend && col0 + c < prm.cols; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(trow + (uint32_t)c, r);
-        if (!live) continue;
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
           float v = __uint_as_float(r[t]) + shift;
@@ -200,22 +212,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_layer_kernel(const __grid_con
           // round to the nearest TF32 so that the next layer's tensor-core truncation is exact
           r[t] = round_out ? ((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u) : __float_as_uint(v);
         }
-        if (col0 + c + 32 <= prm.cols) {
 #pragma unroll
-          for (int t = 0; t < 32; t += 4)
-            __stcs(reinterpret_cast<uint4 *>(dst + c + t), make_uint4(r[t], r[t + 1], r[t + 2], r[t + 3]));
-        } else {
+        for (int t = 0; t < 32; t += 4)
+          *reinterpret_cast<uint4 *>(stage + lane * 36 + t) = make_uint4(r[t], r[t + 1], r[t + 2], r[t + 3]);
+        __syncwarp();
+        if (col0 + c + scol < prm.cols) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (col0 + c + t < prm.cols) dst[c + t] = __uint_as_float(r[t]);
+          for (int k = 0; k < 8; ++k) {
+            const int row = k * 4 + srow;
+            const uint4 val = *reinterpret_cast<const uint4 *>(stage + row * 36 + scol);
+            if (co_base + row < prm.c_out)
+              __stcs(reinterpret_cast<uint4 *>(prm.out + ((size_t)cloud * prm.c_out + co_base + row) * prm.cols + col0 + c + scol), val);
+          }
         }
+        __syncwarp();
       }
     } else if (warp_live) {
       const int ns = prm.pool;                  // power of two dividing NT: a pooling group never straddles two CTAs
       const int lg = __ffs(ns) - 1;
       float *dst = prm.out + ((size_t)cloud * prm.c_out + co) * (prm.cols >> lg) + (col0 >> lg);
       float run = -INFINITY;
-      for (int c = 0; c < NT && col0 + c < prm.cols; c += 32) {
+      for (int c = cbeg; c < cend && col0 + c < prm.cols; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(trow + (uint32_t)c, r);
         if (!live) continue;
@@ -301,8 +318,19 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
   if (b == 0 || cols == 0) return 0;
   if (!w || !shift || !x1 || !out || (c2 > 0 && !x2)) return fail_arg(what);
   if (cols % 4 || b > 65535) return fail_arg("mlp_layer (cols % 4 != 0 or batch > 65535)");
-  constexpr int NT = 256;
-  if (pool < 0 || (pool > 0 && (cols % pool != 0 || NT % pool != 0 || (pool & (pool - 1)) != 0))) return fail_arg("mlp_layer (pool must divide 256 and cols)");
+  {
+    const int rep_log2 = (relu >> 4) & 3;
+    if (rep_log2 > 2 || (rep_log2 > 0 && (c_out_pad != kTileM || c_out > (kTileM >> rep_log2))))
+      return fail_arg("mlp_layer (row replication needs c_out_pad == 128 and c_out <= 128 / copies)");
+    if (pool > 0 && ((128 >> rep_log2) % pool) != 0) return fail_arg("mlp_layer (pool must divide the per-warp column share)");
+  }
+  // tile configuration: (columns per tile, smem stages, CTAs per SM).  Several small CTAs per SM overlap one
+  // CTA's TMA / MMA phase with another's epilogue; WS3D_MLP_CFG overrides for experiments.
+  static const int cfg_env = []() { const char *e = getenv("WS3D_MLP_CFG"); return (e && *e) ? atoi(e) : -1; }();
+  int cfg = cfg_env >= 0 ? cfg_env : 1;
+  const int max_nt = cfg == 0 ? 256 : cfg == 1 ? 256 : 128;
+  if (pool < 0 || (pool > 0 && (cols % pool != 0 || max_nt % pool != 0 || (pool & (pool - 1)) != 0)))
+    return fail_arg("mlp_layer (pool must be a power of two dividing the column tile and cols)");
   MlpParams prm;
   prm.c_out = c_out; prm.cols = cols; prm.pool = pool; prm.flags = relu; prm.shift = shift; prm.out = out;
   prm.nk1 = ceil_div(c1, kChunkK);
@@ -329,11 +357,22 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
   } else {
     m2 = m1;
   }
-  const size_t smem = (size_t)kStages * (kTileM * kChunkK * 4 + NT * kChunkK * 4) + 1024;
-  auto kern = mlp_layer_kernel<NT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_error("mlp_layer: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-  dim3 grid((unsigned)ceil_div(cols, NT), (unsigned)(c_out_pad / kTileM), (unsigned)b);
-  kern<<<grid, kThreads, smem, to_stream(stream)>>>(mw, m1, m2, prm);
+  cudaError_t e = cudaSuccess;
+#define WS3D_MLP_LAUNCH(NT_, ST_, MB_)                                                                              \
+  {                                                                                                                 \
+    const size_t smem = (size_t)(ST_) * (kTileM * kChunkK * 4 + (NT_) * kChunkK * 4) + 1024;                        \
+    auto kern = mlp_layer_kernel<NT_, ST_, MB_>;                                                                    \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+    if (e != cudaSuccess) { set_error("mlp_layer: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }     \
+    dim3 grid((unsigned)ceil_div(cols, NT_), (unsigned)(c_out_pad / kTileM), (unsigned)b);                          \
+    kern<<<grid, kThreads, smem, to_stream(stream)>>>(mw, m1, m2, prm);                                             \
+  }
+  switch (cfg) {
+    case 0: WS3D_MLP_LAUNCH(256, 4, 1) break;   // one big CTA per SM, deep ring
+    case 1: WS3D_MLP_LAUNCH(256, 2, 2) break;   // two CTAs per SM
+    case 2: WS3D_MLP_LAUNCH(128, 3, 3) break;   // three CTAs per SM, 128-column tiles
+    default: WS3D_MLP_LAUNCH(128, 2, 4) break;  // four CTAs per SM
+  }
+#undef WS3D_MLP_LAUNCH
   return check_launch(what);
 }

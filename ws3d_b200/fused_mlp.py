@@ -35,7 +35,7 @@ def enabled_for(module: nn.Module) -> bool:
 
 
 class _Layer:
-    __slots__ = ("w", "shift", "c_out", "c_out_pad", "relu", "splits")
+    __slots__ = ("w", "shift", "c_out", "c_out_pad", "relu", "splits", "rep_log2")
 
 
 class FoldedMLP:
@@ -73,6 +73,8 @@ class FoldedMLP:
             k1, k2 = _ceil(splits[0], _CHUNK_K), (_ceil(splits[1], _CHUNK_K) if splits[1] else 0)
             lay = _Layer()
             lay.c_out, lay.c_out_pad = c_out, _ceil(c_out, _TILE_M)
+            # narrow layers: replicate the rows over the 128 MMA rows so that every epilogue warp has channels
+            lay.rep_log2 = 2 if c_out <= 32 else (1 if c_out <= 64 else 0)
             w = _round_tf32(w)  # the tensor core truncates FP32 operands to TF32: round the weights to nearest first
             wp = torch.zeros((lay.c_out_pad, k1 + k2), dtype=torch.float32, device=w.device)
             wp[:c_out, :splits[0]] = w[:, :splits[0]]
@@ -80,6 +82,10 @@ class FoldedMLP:
                 wp[:c_out, k1:k1 + splits[1]] = w[:, splits[0]:]
             sp = torch.zeros(lay.c_out_pad, dtype=torch.float32, device=w.device)
             sp[:c_out] = shift
+            for r in range(1, 1 << lay.rep_log2):
+                o = r * (_TILE_M >> lay.rep_log2)
+                wp[o:o + c_out] = wp[:c_out]
+                sp[o:o + c_out] = sp[:c_out]
             lay.w, lay.shift, lay.splits = wp.contiguous(), sp, splits
             lay.relu = hasattr(block, "activation")
             self.layers.append(lay)
@@ -98,12 +104,13 @@ class FoldedMLP:
             c1 = cur1.shape[1]
             c2 = cur2.shape[1] if cur2 is not None else 0
             assert (c1, c2) == tuple(lay.splits), ((c1, c2), lay.splits)
-            flags = int(lay.relu) | (0 if last else 2)  # intermediate activations are stored TF32-rounded
+            flags = int(lay.relu) | (0 if last else 2) | (lay.rep_log2 << 4)  # intermediates are stored TF32-rounded
             native.mlp_layer(B, lay.c_out, lay.c_out_pad, c1, c2, cols, lay.w, lay.shift, cur1, cur2, out, flags, p)
             cur1, cur2 = out, None
         return cur1
 
 
 def supported(cols: int, pool: int) -> bool:
-    """Shapes the kernel accepts: 16-byte aligned rows; pooling groups that divide the 256-column tile."""
-    return cols % 4 == 0 and (pool == 0 or (256 % pool == 0 and cols % pool == 0))
+    """Shapes the kernel accepts: 16-byte aligned rows; pooling groups (nsample) that are a power of two <= 32, so
+    that a group never straddles the column share of one epilogue warp."""
+    return cols % 4 == 0 and (pool == 0 or (pool & (pool - 1) == 0 and pool <= 32 and cols % pool == 0))
