@@ -211,6 +211,55 @@ def test_three_nn(b, n, m):
         assert torch.equal(ridx, gidx) and torch.equal(rd2, gd2)
 
 
+NN_GRID_CASES = ["scene_subset", "lattice_ties", "duplicates", "outliers", "nonfinite", "line", "two_known_cells", "offset"]
+
+
+@pytest.mark.parametrize("kind", NN_GRID_CASES)
+def test_three_nn_cell_grid_edge_cases(kind):
+    """m >= 512 and n >= 1024 take the ring search over a cell grid (csrc/three_nn_grid.cu)."""
+    from ws3d_b200 import native
+    rng = np.random.default_rng(len(kind) * 131 + 7)
+    b, n, m = 2, 4096, 1024
+    unknown = rng.uniform(-20, 20, (b, n, 3)).astype(np.float32)
+    known = rng.uniform(-20, 20, (b, m, 3)).astype(np.float32)
+    if kind == "scene_subset":        # FP-layer geometry: known points are a subset of the unknown ones
+        from ws3d_b200 import synth
+        unknown = synth.make_batch(b, n)[..., :3].copy()
+        known = unknown[:, rng.permutation(n)[:m]].copy()
+    elif kind == "lattice_ties":      # many exactly equal distances: the index order decides
+        unknown = rng.integers(-6, 7, (b, n, 3)).astype(np.float32)
+        known = rng.integers(-6, 7, (b, m, 3)).astype(np.float32)
+    elif kind == "duplicates":
+        known[:, 1::2] = known[:, 0::2]
+    elif kind == "outliers":          # queries far outside the known points' box; two isolated known points
+        unknown[:, :64] += np.float32(500.0)
+        known[:, 0] = np.float32(-900.0); known[:, 1] = np.float32(900.0)
+    elif kind == "nonfinite":
+        known[:, 3, 0] = np.nan; known[:, 4, 1] = np.inf
+        unknown[:, 5, 2] = np.nan; unknown[:, 6, 0] = -np.inf
+    elif kind == "line":
+        known[..., 1:] = 0.0
+        known[..., 0] = rng.uniform(-3000, 3000, (b, m)).astype(np.float32)
+    elif kind == "two_known_cells":   # all known points in two tight clumps: long ring walks in between
+        known[:, : m // 2] = rng.normal(-15, 0.01, (b, m // 2, 3)).astype(np.float32)
+        known[:, m // 2:] = rng.normal(15, 0.01, (b, m - m // 2, 3)).astype(np.float32)
+    elif kind == "offset":
+        unknown += np.float32(7000.0); known += np.float32(7000.0)
+    with np.errstate(invalid="ignore", over="ignore"):
+        d2, idx = oracle.three_nn(unknown, known)
+    u, k = _t(unknown), _t(known)
+    gd2 = torch.empty((b, n, 3), device=dev)
+    gidx = torch.empty((b, n, 3), dtype=torch.int32, device=dev)
+    native.three_nn_wrapper(b, n, m, u, k, gd2, gidx)
+    np.testing.assert_array_equal(gidx.cpu().numpy(), idx)
+    np.testing.assert_array_equal(gd2.cpu().numpy(), d2)
+    ref = load_ref("pointnet2_cuda")
+    if ref is not None:
+        rd2, ridx = torch.empty_like(gd2), torch.empty_like(gidx)
+        ref.three_nn_wrapper(b, n, m, u, k, rd2, ridx)
+        assert torch.equal(ridx, gidx) and torch.equal(rd2, gd2)
+
+
 @pytest.mark.parametrize("b,c,m,n", [(2, 64, 256, 1024), (1, 256, 4096, 16384), (2, 7, 33, 100)])
 def test_three_interpolate(b, c, m, n):
     from ws3d_b200 import pointnet2_utils

@@ -26,6 +26,10 @@ bool ball_query_grid_applicable(int nr, int b, int n, int m, const float *radius
 int ball_query_grid(int nr, int b, int n, int m, const float *radius, const int *nsample, const float *new_xyz,
                     const float *xyz, int *const *idx, cudaStream_t stream);
 
+// three_nn_grid.cu: ring search over a cell grid of the known points
+bool three_nn_grid_applicable(int b, int n, int m);
+int three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, cudaStream_t stream);
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -490,6 +494,7 @@ WS3D_API int ws3d_three_nn(int b, int n, int m, const float *unknown, const floa
   if (b == 0 || n == 0) return 0;
   if (!unknown || !dist2 || !idx || (m > 0 && !known)) return fail_arg("three_nn (null pointer)");
   if (b > 65535) return fail_arg("three_nn (batch > 65535)");
+  if (three_nn_grid_applicable(b, n, m)) return three_nn_grid(b, n, m, unknown, known, dist2, idx, to_stream(stream));
   const size_t smem = (size_t)(m < kNnChunk ? (m > 0 ? m : 1) : kNnChunk) * sizeof(float4);
   cudaError_t e = cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNnChunk * sizeof(float4)));
   if (e != cudaSuccess) { set_error("three_nn: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
