@@ -7,11 +7,13 @@ B200 ops.  Structure and parameter names follow the reference so its checkpoints
 tools/cfgs/weaklyRPN.yaml:43-56 (= lib/config.py:57-70), restated here as RPN_SA_CONFIG.
 """
 import copy
+import os
 
 import numpy as np
 import torch
 import torch.nn as nn
 
+from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
 
@@ -62,9 +64,55 @@ class Pointnet2MSG(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
+    def _forward_two_streams(self, xyz, features):
+        """Same computation as forward(), scheduled on two CUDA streams.
+
+        Sampling (FPS) and the interpolation stencils (three_nn + weights) depend on coordinates only, and FPS is a
+        latency chain that occupies few SMs below the first level.  They run ahead on a side stream while the main
+        stream does ball query / grouping / MLPs of the levels whose samples are already known; events order the
+        two, `record_stream` keeps the caching allocator from recycling a tensor the other stream still reads.
+        """
+        main = torch.cuda.current_stream(xyz.device)
+        side = self.__dict__.get("_side_stream")
+        if side is None or side.device != xyz.device:
+            side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=xyz.device)
+        start = torch.cuda.Event()
+        start.record(main)
+        l_xyz, fps_done, stencil, stencil_done = [xyz], [], {}, {}
+        with torch.cuda.stream(side):
+            side.wait_event(start)
+            for sa in self.SA_modules:
+                _, nx = pointnet2_utils.sample_and_gather(l_xyz[-1], sa.npoint)
+                nx.record_stream(main)
+                l_xyz.append(nx)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                fps_done.append(ev)
+            for i in range(len(self.FP_modules) - 1, -1, -1):  # deepest level is needed first
+                idx, weight = PointnetFPModule.interpolation_weights(l_xyz[i], l_xyz[i + 1])
+                idx.record_stream(main)
+                weight.record_stream(main)
+                stencil[i] = (idx, weight)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                stencil_done[i] = ev
+        l_features = [features]
+        for i, sa in enumerate(self.SA_modules):
+            main.wait_event(fps_done[i])
+            _, nf = sa(l_xyz[i], l_features[i], new_xyz=l_xyz[i + 1])
+            l_features.append(nf)
+        for i in range(len(self.FP_modules) - 1, -1, -1):
+            main.wait_event(stencil_done[i])
+            l_features[i] = self.FP_modules[i](l_xyz[i], l_xyz[i + 1], l_features[i], l_features[i + 1], nn=stencil[i])
+        xyz.record_stream(side)
+        return l_xyz[0], l_features[0]
+
     def forward(self, pointcloud: torch.Tensor):
         """pointcloud (B,N,3+C) -> (xyz (B,N,3), per-point features (B,128,N))."""
         xyz, features = self._break_up_pc(pointcloud)
+        if (xyz.is_cuda and os.environ.get("WS3D_TWO_STREAMS", "1") != "0" and len(self.FP_modules) == len(self.SA_modules)
+                and all(sa.npoint is not None for sa in self.SA_modules)):
+            return self._forward_two_streams(xyz, features)
         l_xyz, l_features = [xyz], [features]
         for sa in self.SA_modules:
             nx, nf = sa(l_xyz[-1], l_features[-1])

@@ -114,13 +114,19 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
 
+    @staticmethod
+    def interpolation_weights(unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """three_nn + inverse-distance weights (reference :139-144).  Depends on coordinates only, so a caller may
+        compute it ahead of time (models.Pointnet2MSG does, on a side stream) and pass it as `nn=`."""
+        dist, idx = pointnet2_utils.three_nn(unknown, known)
+        dist_recip = 1.0 / (dist + 1e-8)
+        norm = torch.sum(dist_recip, dim=2, keepdim=True)
+        return idx, dist_recip / norm
+
     def forward(self, unknown: torch.Tensor, known: Optional[torch.Tensor], unknow_feats: Optional[torch.Tensor],
-                known_feats: torch.Tensor) -> torch.Tensor:
+                known_feats: torch.Tensor, nn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
         if known is not None:
-            dist, idx = pointnet2_utils.three_nn(unknown, known)
-            dist_recip = 1.0 / (dist + 1e-8)
-            norm = torch.sum(dist_recip, dim=2, keepdim=True)
-            weight = dist_recip / norm
+            idx, weight = nn if nn is not None else self.interpolation_weights(unknown, known)
             interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
