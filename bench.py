@@ -31,6 +31,19 @@ METRIC = "SA-layer Mpoints/sec (PointNet++-MSG backbone forward: 4 SA + 4 FP)"
 UNIT = "Mpoints/s"
 NPTS = 16384
 BATCH = 16
+WORKLOAD = ("PointNet++-MSG backbone forward (4 SA + 4 FP, weaklyRPN.yaml shapes), batch 16 synthetic KITTI clouds 16384x4 per GPU "
+            "(BASELINE configs[1])")
+
+
+def measured_traffic(kernel, dims):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)
+    key = kernel + ":" + ",".join(f"{k}={dims[k]}" for k in sorted(dims))
+    return table.get(key)
 
 
 def measured_peaks():
@@ -127,9 +140,9 @@ def run_reference_cpu(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PointNet++-MSG backbone forward (4 SA + 4 FP), synthetic KITTI clouds 16384x4",
-                   "clouds_per_step": clouds, "note": "CPU port of the reference algorithms (the reference has no CPU "
-                   "implementation of these ops); each step is a bounded sample of the GPU arm's 16-cloud batch"},
+        "config": {"workload": WORKLOAD, "clouds_per_step": clouds,
+                   "note": "CPU port of the reference algorithms (the reference has no CPU implementation of these ops); each "
+                           "step is a bounded sample (2 clouds) of the GPU arm's 16-cloud batch, Mpoints/s is size-independent"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{clouds} clouds x {NPTS} points per step, oracle ops (OpenMP) + PyTorch CPU MLPs"},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -281,8 +294,22 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.__enter__()
-    ms_total, launches, prof, _ = timed_region(step_resident, args.steps, profile=True)
+    ms_total, launches, _, _ = timed_region(step_resident, args.steps, profile=False)
     ms_e2e, _, _, _ = timed_region(step_e2e, args.steps, profile=False)
+    # the same K steps once more with a CUDA-event pair round every launch of this library (per-kernel durations
+    # for the roofline entries; kept out of `value` because ~600 extra event records per step cost host time)
+    ms_prof, _, prof, _ = timed_region(step_resident, args.steps, profile=True)
+    # Stage-1 RPN = backbone + the two per-point heads (lib/net/rpn.py:67-81): scenes/s for the metric's second half
+    rpn = models.RPN().to(dev).eval()
+    rpn.backbone_net = model
+
+    def step_rpn():
+        with torch.no_grad():
+            return rpn(resident)["rpn_cls"]
+
+    for _ in range(3):
+        step_rpn()
+    ms_rpn, _, _, _ = timed_region(step_rpn, args.steps, profile=False)
     if sampler:
         sampler.__exit__(None, None, None)
 
@@ -296,8 +323,10 @@ def run_gpu(args):
         kernels = prof.summarize(args.steps)
         top = kernels[0]
         roof = {"bound": "hbm", "kernel": top["kernel"], "dims": top["dims"], "achieved": round(top["GBps"], 3), "peak": peak,
-                "unit": "GB/s", "frac": round(top["GBps"] / peak, 6), "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": round(top["avg_ms"], 4), "share_of_step": round(top["ms_per_step"] / ms_step, 4),
+                "unit": "GB/s", "frac": round(top["GBps"] / peak, 6), "traffic": measured_traffic(top["kernel"], top["dims"]),
+                "peak_source": peak_src, "alg_bytes": int(top["alg_bytes"]),
+                "avg_launch_ms": round(top["avg_ms"], 4), "share_of_step": round(top["ms_per_step"] / (ms_prof / args.steps), 4),
+                "profiled_ms_per_step": round(ms_prof / args.steps, 4),
                 "note": "FPS is a latency chain of m-1 dependent iterations (SURVEY.md 8d): its HBM fraction is "
                         "reported for the record; us/iteration is the meaningful figure" if top["kernel"] == "fps" else ""}
         if top["kernel"] == "fps":
@@ -314,16 +343,18 @@ def run_gpu(args):
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "PointNet++-MSG backbone forward (4 SA + 4 FP, weaklyRPN.yaml shapes), batch 16 synthetic "
-                                   "KITTI clouds 16384x4 per GPU (BASELINE configs[1])",
-                       "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": "flushed between timed iterations (256 MiB write)",
+            "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": "flushed between timed iterations (256 MiB write)",
                        "mlp": ("tcgen05 TF32 shared-MLP layers (conv1x1+BN+ReLU[+max-pool] per launch, FP32 accumulate)"
                                if torch.backends.cudnn.allow_tf32 else "PyTorch/cuDNN fp32 (TF32 off)"),
+                       "streams": "two CUDA streams (FPS chain + interpolation stencils run ahead of grouping / MLPs)"
+                                  if os.environ.get("WS3D_TWO_STREAMS", "1") != "0" else "single stream",
                        "sharding": "scenes per rank, no data-path collective"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4) * world,
                     "d2h_bytes_per_step": BATCH * 4 * world, "ms_per_step": round(ms_e2e / args.steps, 4),
                     "note": "pinned host cloud -> H2D -> backbone forward -> per-cloud feature checksum -> D2H"},
             "gpu_launches": int(launches),
+            "rpn": {"scenes_per_s": round(world * BATCH / (ms_rpn / args.steps / 1e3), 1), "ms_per_step": round(ms_rpn / args.steps, 4),
+                    "note": "Stage-1 RPN forward (backbone + cls/reg heads, lib/net/rpn.py:67-81), same batch, inputs resident"},
             "clocks": sampler.summary() if sampler else None,
         }
         if roof:

@@ -61,3 +61,37 @@ def test_sharding_arithmetic():
     assert all(parts[i][1] == parts[i + 1][0] for i in range(7))
     assert sharding.aggregate_throughput(16 * 16384, 8, 10.0) == 16 * 16384 * 8 / 0.01
     assert sharding.max_over_ranks(3.5) == 3.5
+
+
+def test_folded_mlp_weights_equal_conv_bn_eval_on_cpu():
+    """Host logic of the tensor-core MLP path: BN(eval) folding, TF32 rounding, padding and row replication
+    (ws3d_b200/fused_mlp.py) -- checked on CPU with a plain matmul against the PyTorch module."""
+    import torch
+    from ws3d_b200 import fused_mlp, pytorch_utils as pt_utils
+    torch.manual_seed(3)
+    mlp = pt_utils.SharedMLP([7, 20, 40], bn=True).eval()
+    for m in mlp.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 1.5); m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+    folded = fused_mlp.FoldedMLP(mlp)
+    x = torch.randn(2, 7, 16, 1)
+    with torch.no_grad():
+        want = mlp(x).squeeze(-1)
+    cur = x.squeeze(-1)
+    for lay in folded.layers:
+        assert lay.w.shape[0] % 128 == 0 and lay.w.shape[1] % 32 == 0
+        copies = 1 << lay.rep_log2
+        rows = 128 // copies
+        for r in range(1, copies):   # replicated rows are exact copies
+            assert torch.equal(lay.w[r * rows:r * rows + lay.c_out], lay.w[:lay.c_out])
+            assert torch.equal(lay.shift[r * rows:r * rows + lay.c_out], lay.shift[:lay.c_out])
+        assert torch.equal(lay.w, fused_mlp._round_tf32(lay.w))       # already TF32 values
+        y = torch.einsum("oc,bce->boe", lay.w[:lay.c_out, :cur.shape[1]], cur) + lay.shift[:lay.c_out, None]
+        cur = torch.relu(y) if lay.relu else y
+    assert float((cur - want).abs().max()) < 5e-3 * float(want.abs().max())   # only the weights were rounded
+    # _round_tf32: nearest, ties away from zero, 13 low mantissa bits cleared
+    t = torch.tensor([1.0 + 2 ** -11, 1.0 + 2 ** -12, -(1.0 + 2 ** -11), 3.0])
+    r = fused_mlp._round_tf32(t)
+    assert r.tolist() == [1.0 + 2 ** -10, 1.0, -(1.0 + 2 ** -10), 3.0]
+    assert fused_mlp.supported(4096, 32) and fused_mlp.supported(4096, 0) and not fused_mlp.supported(4098, 0) \
+        and not fused_mlp.supported(4096, 64) and not fused_mlp.supported(4096, 24)

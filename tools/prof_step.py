@@ -1,0 +1,18 @@
+"""Two backbone forward passes at the bench shapes (B=16 x 16384 points) -- the command ncu wraps."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from ws3d_b200 import models, synth
+
+torch.manual_seed(0)
+dev = "cuda:0"
+model = models.Pointnet2MSG(input_channels=1).to(dev).eval()
+pts = torch.from_numpy(synth.make_batch(16, 16384)).to(dev)
+with torch.no_grad():
+    for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
+        out = model(pts)[1]
+torch.cuda.synchronize()
+print("ok", float(out.abs().mean()))
