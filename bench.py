@@ -241,15 +241,31 @@ def run_gpu(args):
     host = torch.from_numpy(synth.make_batch(BATCH, NPTS, first_scene=rank * BATCH)).pin_memory()
     resident = host.to(dev)
 
-    def step_resident():
+    def step_eager():
         with torch.no_grad():
             return model(resident)[1]
 
-    def step_e2e():
-        with torch.no_grad():
-            x = host.to(dev, non_blocking=True)
-            feats = model(x)[1]
-            return feats.sum(dim=(1, 2)).cpu()  # D2H read of the per-cloud checksum (synchronises)
+    use_graph = os.environ.get("WS3D_CUDA_GRAPH", "1") != "0"
+    if use_graph:
+        # the forward (both streams) captured once, replayed per step: same kernels, no per-launch host work
+        from ws3d_b200.graphs import CudaGraphRunner
+        runner = CudaGraphRunner(lambda x: model(x)[1], resident)
+
+        def step_resident():
+            return runner(runner.static_in)
+
+        def step_e2e():
+            runner.static_in.copy_(host, non_blocking=True)   # H2D of this step's clouds (pinned source)
+            feats = runner(runner.static_in)
+            return feats.sum(dim=(1, 2)).cpu()                 # D2H read of the per-cloud checksum (synchronises)
+    else:
+        step_resident = step_eager
+
+        def step_e2e():
+            with torch.no_grad():
+                x = host.to(dev, non_blocking=True)
+                feats = model(x)[1]
+                return feats.sum(dim=(1, 2)).cpu()  # D2H read of the per-cloud checksum (synchronises)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -289,23 +305,35 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
         step_e2e()
+        step_eager()
     sync_all()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.__enter__()
     ms_total, launches, _, _ = timed_region(step_resident, args.steps, profile=False)
+    if use_graph:   # replays do not pass through the C ABI: count the kernels of one eager step instead
+        l0 = _C.launch_count()
+        step_eager()
+        torch.cuda.synchronize()
+        launches = (_C.launch_count() - l0) * args.steps
     ms_e2e, _, _, _ = timed_region(step_e2e, args.steps, profile=False)
     # the same K steps once more with a CUDA-event pair round every launch of this library (per-kernel durations
     # for the roofline entries; kept out of `value` because ~600 extra event records per step cost host time)
-    ms_prof, _, prof, _ = timed_region(step_resident, args.steps, profile=True)
+    ms_prof, _, prof, _ = timed_region(step_eager, args.steps, profile=True)
     # Stage-1 RPN = backbone + the two per-point heads (lib/net/rpn.py:67-81): scenes/s for the metric's second half
     rpn = models.RPN().to(dev).eval()
     rpn.backbone_net = model
 
-    def step_rpn():
-        with torch.no_grad():
-            return rpn(resident)["rpn_cls"]
+    if use_graph:
+        rpn_runner = CudaGraphRunner(lambda x: rpn(x)["rpn_cls"], resident)
+
+        def step_rpn():
+            return rpn_runner(rpn_runner.static_in)
+    else:
+        def step_rpn():
+            with torch.no_grad():
+                return rpn(resident)["rpn_cls"]
 
     for _ in range(3):
         step_rpn()
@@ -346,6 +374,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": "flushed between timed iterations (256 MiB write)",
                        "mlp": ("tcgen05 TF32 shared-MLP layers (conv1x1+BN+ReLU[+max-pool] per launch, FP32 accumulate)"
                                if torch.backends.cudnn.allow_tf32 else "PyTorch/cuDNN fp32 (TF32 off)"),
+                       "launch": "one CUDA graph replay per step" if use_graph else "eager launches",
                        "streams": "two CUDA streams (FPS chain + interpolation stencils run ahead of grouping / MLPs)"
                                   if os.environ.get("WS3D_TWO_STREAMS", "1") != "0" else "single stream",
                        "sharding": "scenes per rank, no data-path collective"},

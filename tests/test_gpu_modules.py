@@ -99,3 +99,27 @@ def test_dropin_modules_expose_reference_tables():
     temp = torch.cuda.FloatTensor(2, 512).fill_(1e10)
     assert pointnet2_cuda.furthest_point_sampling_wrapper(2, 512, 64, xyz, temp, out) == 1
     assert int(out[:, 0].abs().sum()) == 0
+
+
+def test_cuda_graph_replay_equals_eager_two_stream_forward():
+    """ws3d_b200.graphs.CudaGraphRunner: the captured two-stream forward replays to the same features as the eager
+    call, for a new input copied into the static buffer, and the single-stream schedule gives the same result."""
+    import os
+    from ws3d_b200 import models, synth
+    from ws3d_b200.graphs import CudaGraphRunner
+    torch.manual_seed(0)
+    model = models.Pointnet2MSG(input_channels=1).to(dev).eval()
+    a = torch.from_numpy(synth.make_batch(2, 4096)).to(dev)
+    b = torch.from_numpy(synth.make_batch(2, 4096, first_scene=7)).to(dev)
+    with torch.no_grad():
+        want_a, want_b = model(a)[1].clone(), model(b)[1].clone()
+        os.environ["WS3D_TWO_STREAMS"] = "0"
+        try:
+            single = model(b)[1].clone()
+        finally:
+            del os.environ["WS3D_TWO_STREAMS"]
+    assert torch.equal(single, want_b)
+    runner = CudaGraphRunner(lambda x: model(x)[1], a)
+    assert torch.equal(runner(a), want_a)
+    assert torch.equal(runner(b), want_b)
+    assert torch.equal(runner(a), want_a)

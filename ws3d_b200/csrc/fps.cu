@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
   const uint32_t rank = CLUSTER ? cluster_ctarank() : 0u;
   const uint32_t C = CLUSTER ? cluster_nctarank() : 1u;
   const int CT = (int)C * T;
+  const int log2CT = 31 - __clz(CT);
   const int g = (int)rank * T + tid;
   const int n = prm.n, m = prm.m, L = prm.L;
   const size_t cloud = blockIdx.y;
@@ -119,6 +120,16 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
   }
   if (CLUSTER) cluster_sync_all(); else __syncthreads();
 
+  // remote addresses of this CTA's record slot and of the barrier in CTA `lane`, per parity (loop invariant)
+  uint32_t rdst[2] = {0u, 0u}, rbars[2] = {0u, 0u};
+  if (CLUSTER && lane < (int)C) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      rdst[q] = mapa(smem_u32(&s_crec[q][rank]), (uint32_t)lane);
+      rbars[q] = mapa(bar_base + 8u * (uint32_t)q, (uint32_t)lane);
+    }
+  }
+
   for (int it = 0; it + 1 < m; ++it) {
     const int par = it & 1;
     const uint32_t bar = bar_base + 8u * (uint32_t)par;
@@ -146,14 +157,16 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
       float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bk != kNoKey) {
         const int k = (int)fps_unkey(bk, L);
-        const int p = k / CT, gg = k - p * CT;
+        // C and T are powers of two: the slot of point k is a shift and a mask (an integer division here costs
+        // ~20 dependent instructions on the iteration's critical path)
+        const int p = k >> log2CT, gg = k & (CT - 1);
         pt = s_pts[p * T + (gg - (int)rank * T)];
       }
       if (CLUSTER) {
         if (lane == 0) mbar_expect_tx(bar, C * 20u);
         if (lane < (int)C) {
-          const uint32_t dst = mapa(smem_u32(&s_crec[par][rank]), (uint32_t)lane);
-          const uint32_t rbar = mapa(bar, (uint32_t)lane);
+          const uint32_t dst = par ? rdst[1] : rdst[0];
+          const uint32_t rbar = par ? rbars[1] : rbars[0];
           st_async_v4(dst, (uint32_t)bv, bk, __float_as_uint(pt.x), __float_as_uint(pt.y), rbar);
           st_async_b32(dst + 16, __float_as_uint(pt.z), rbar);
         }

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kInterpThreads) three_interpolate_kernel(int c
 // of a channel chunk are staged once per CTA (one contiguous TMA bulk copy: rows of consecutive
 // channels are adjacent in (B,C,M)), so the three random reads per output become shared-memory reads
 // (a few-way bank conflict) instead of 32 L1 sector look-ups per warp instruction.
-constexpr int kInterpSmemThreads = 512;
+constexpr int kInterpSmemThreads = 1024;  // launch bound; 512 threads are used when a CTA has few points
 __global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem_kernel(
     int c, int m, int n, int cb, int n_per_cta, const float *__restrict__ points, const int *__restrict__ idx,
     const float *__restrict__ weight, float *__restrict__ out) {
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem_ker
   }
   __syncthreads();
   stage_floats(s_rows, points + (cloud * (size_t)c + c0) * m, cn * m, &s_bar, 0);
-  for (int i = i_begin + (int)threadIdx.x; i < i_end; i += kInterpSmemThreads) {
+  for (int i = i_begin + (int)threadIdx.x; i < i_end; i += (int)blockDim.x) {
     const int *ip = idx + (cloud * (size_t)n + i) * 3;
     const float *wp = weight + (cloud * (size_t)n + i) * 3;
     const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
@@ -413,6 +413,59 @@ __global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem_ker
       t = __fmaf_rn(w2, row[i2], t);
       __stcs(o + (size_t)cc * n, t);
     }
+  }
+}
+
+// Same, with four channels interleaved per shared-memory slot ([k][4] floats): one 16-byte read per neighbour
+// serves four channels.  The gathers are random in k, so a 4-byte read per lane costs ~3.5 bank-conflict
+// wavefronts per warp instruction; a 16-byte read is issued per quarter warp and costs ~1.6 per 8 lanes,
+// i.e. less than half the shared-memory time per output (the kernel's bottleneck in ncu: 22 % DRAM).
+__global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem4_kernel(
+    int c, int m, int n, int cb, int n_per_cta, const float *__restrict__ points, const int *__restrict__ idx,
+    const float *__restrict__ weight, float *__restrict__ out) {
+  extern __shared__ __align__(16) float s_rows[];  // (cb/4) groups x m x 4
+  const size_t cloud = blockIdx.z;
+  const int c0 = blockIdx.x * cb, cn = min(cb, c - c0);  // cn % 4 == 0 (host guarantees c % 4 == 0 and cb % 4 == 0)
+  const int i_begin = blockIdx.y * n_per_cta, i_end = min(n, i_begin + n_per_cta);
+  const float *src = points + (cloud * (size_t)c + c0) * m;
+  for (int e = threadIdx.x; e < cn * m; e += (int)blockDim.x) {
+    const int cc = e / m, k = e - cc * m;
+    s_rows[((size_t)(cc >> 2) * m + k) * 4 + (cc & 3)] = __ldg(src + e);
+  }
+  __syncthreads();
+  const float4 *s4 = reinterpret_cast<const float4 *>(s_rows);
+  // the stencil (3 indices + 3 weights) of the NEXT point is loaded while the current one is interpolated:
+  // in ncu the kernel waited on these global loads (long scoreboard) more than on anything else
+  int i = i_begin + (int)threadIdx.x;
+  int i0 = 0, i1 = 0, i2 = 0;
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+  if (i < i_end) {
+    const int *ip = idx + (cloud * (size_t)n + i) * 3;
+    const float *wp = weight + (cloud * (size_t)n + i) * 3;
+    i0 = __ldg(ip); i1 = __ldg(ip + 1); i2 = __ldg(ip + 2);
+    w0 = __ldg(wp); w1 = __ldg(wp + 1); w2 = __ldg(wp + 2);
+  }
+  for (; i < i_end; i += (int)blockDim.x) {
+    const int nx = i + (int)blockDim.x;
+    int j0 = 0, j1 = 0, j2 = 0;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (nx < i_end) {
+      const int *ip = idx + (cloud * (size_t)n + nx) * 3;
+      const float *wp = weight + (cloud * (size_t)n + nx) * 3;
+      j0 = __ldg(ip); j1 = __ldg(ip + 1); j2 = __ldg(ip + 2);
+      v0 = __ldg(wp); v1 = __ldg(wp + 1); v2 = __ldg(wp + 2);
+    }
+    float *o = out + (cloud * (size_t)c + c0) * n + i;
+#pragma unroll 2
+    for (int g = 0; g < (cn >> 2); ++g) {
+      const float4 *row = s4 + (size_t)g * m;
+      const float4 p0 = row[i0], p1 = row[i1], p2 = row[i2];
+      __stcs(o + (size_t)(g * 4 + 0) * n, __fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x))));
+      __stcs(o + (size_t)(g * 4 + 1) * n, __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y))));
+      __stcs(o + (size_t)(g * 4 + 2) * n, __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z))));
+      __stcs(o + (size_t)(g * 4 + 3) * n, __fmaf_rn(w2, p2.w, __fmaf_rn(w0, p0.w, __fmul_rn(w1, p1.w))));
+    }
+    i0 = j0; i1 = j1; i2 = j2; w0 = v0; w1 = v1; w2 = v2;
   }
 }
 
@@ -517,14 +570,23 @@ WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *poi
     while (cb > 8 && (long long)ceil_div(c, cb) * b < 2LL * kNumSMs) cb >>= 1;
     const int chunks = ceil_div(c, cb);
     int nsplit = 1;
-    while ((long long)chunks * b * nsplit < 2LL * kNumSMs && ceil_div(n, nsplit * 2) >= 2 * kInterpSmemThreads) nsplit <<= 1;
+    while ((long long)chunks * b * nsplit < 2LL * kNumSMs && ceil_div(n, nsplit * 2) >= 2 * 512) nsplit <<= 1;
     const int n_per_cta = ceil_div(n, nsplit);
+    const int threads = n_per_cta >= 8192 ? 1024 : 512;  // more warps hide the stencil loads when there is enough work
     const size_t smem = (size_t)cb * m * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(three_interpolate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("three_interpolate: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    if (chunks <= 65535 * 32 && nsplit <= 65535 && c % 4 == 0 && cb % 4 == 0) {
+      e = cudaFuncSetAttribute(three_interpolate_smem4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("three_interpolate: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+      dim3 grid((unsigned)chunks, (unsigned)nsplit, (unsigned)b);
+      three_interpolate_smem4_kernel<<<grid, threads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx,
+                                                                                          weight, out);
+      return check_launch("three_interpolate");
+    }
     if (chunks <= 65535 * 32 && nsplit <= 65535) {
       dim3 grid((unsigned)chunks, (unsigned)nsplit, (unsigned)b);
-      three_interpolate_smem_kernel<<<grid, kInterpSmemThreads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx,
+      three_interpolate_smem_kernel<<<grid, threads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx,
                                                                                          weight, out);
       return check_launch("three_interpolate");
     }
