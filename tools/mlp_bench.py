@@ -40,7 +40,7 @@ for (c1, c2, co, cols, pool) in LAYERS:
 print(json.dumps(out))
 ''' % (ROOT, LAYERS)
 res = {}
-for cfg in sys.argv[1:] or ["0", "1", "2", "3"]:
+for cfg in sys.argv[1:] or ["-1", "0", "3"]:
     e = dict(os.environ); e["WS3D_MLP_CFG"] = cfg
     p = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
     if p.returncode: print("cfg", cfg, "FAILED", p.stderr[-1500:]); continue

@@ -14,7 +14,7 @@
 // transposes -- W' is the K-major A operand, X is an MN-major B operand -- and makes the nsample
 // max-pool a per-thread reduction over consecutive TMEM columns.
 //
-// One CTA = one 128-channel x NT-column output tile of one cloud:
+// Persistent CTAs; a tile = 128 output channels x NT columns of one cloud:
 //   warp 0    TMA producer   cp.async.bulk.tensor (W: 128B swizzle; X: 128B swizzle with 32B atoms) of 32-deep K chunks, 4-stage ring
 //   warp 1    MMA issuer     4 x tcgen05.mma.kind::tf32 (M=128, N=NT, K=8) per chunk, tcgen05.commit
 //   warps 2-5 epilogue       tcgen05.ld 32x32b.x32 -> +shift, ReLU, (max over nsample) -> 128-byte stores
@@ -41,6 +41,7 @@ struct MlpParams {
   int flags;        // bit 0: ReLU, bit 1: round the stored output to TF32, bits 4-5: log2(copies of the weight rows)
   const float *shift;  // (c_out_padded)
   float *out;
+  int n_col_tiles, n_m_tiles, n_tiles;   // tile = (cloud, 128-channel block, NT-column block), column block fastest
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
@@ -96,6 +97,46 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Max-pool epilogue of one warp: 32 channels (one per lane) x the columns [cbeg, cend) of the accumulator.
+// NS = nsample when it is 16 or 32 (the backbone's values: everything folds at compile time, one 4-byte store per
+// pooled value), NS = 0 takes any power of two `ns_rt` <= 32.  cols % ns == 0, so a started group is complete.
+template <int NS>
+__device__ __forceinline__ void pooled_chunks(uint32_t trow, int cbeg, int cend, int col0, int cols, bool live, float shift,
+                                              bool relu, float *dst, int ns_rt = 0) {
+  const int ns = NS ? NS : ns_rt;
+  const int lg = __ffs(ns) - 1;
+  for (int c = cbeg; c < cend && col0 + c < cols; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(trow + (uint32_t)c, r);
+    if (!live) continue;
+    float v[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      v[t] = __uint_as_float(r[t]) + shift;
+      if (relu) v[t] = fmaxf(v[t], 0.f);
+    }
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1) {
+      if (w < ns) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 2 * w) v[t] = fmaxf(v[t], v[t + w]);
+      }
+    }
+    if (NS == 32) {
+      dst[c >> 5] = v[0];
+    } else if (NS == 16) {
+      float *o = dst + (c >> 4);
+      const bool second = col0 + c + 16 < cols;   // the row may end in the middle of this 32-column chunk
+      if (second && (reinterpret_cast<uintptr_t>(o) & 7u) == 0) *reinterpret_cast<float2 *>(o) = make_float2(v[0], v[16]);
+      else { o[0] = v[0]; if (second) o[1] = v[16]; }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 32; ++g)
+        if ((g & (ns - 1)) == 0 && col0 + c + g < cols) dst[(c + g) >> lg] = v[g];
+    }
+  }
+}
+
 template <int NT, int kStages, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const __grid_constant__ CUtensorMap map_w,
                                                                 const __grid_constant__ CUtensorMap map_x1,
@@ -104,17 +145,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
   constexpr uint32_t kABytes = kTileM * kChunkK * 4;           // 16 KB
   constexpr uint32_t kBBytes = NT * kChunkK * 4;               // NT columns x 32 k
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = NT;                           // power of two >= 32
+  constexpr uint32_t kTmemCols = 2 * NT;                       // two accumulators: the epilogue of tile j overlaps the MMAs of tile j+1
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, A K-major, B MN-major
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
                               ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
   extern __shared__ uint8_t s_raw[];
-  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages], s_tmem_full;
+  __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages], s_tmem_full[2], s_tmem_empty[2];
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.x * NT, m0 = blockIdx.y * kTileM, cloud = blockIdx.z;
   const uint32_t stage_base = (smem_u32(s_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1 KB alignment
   const int nk = prm.nk1 + prm.nk2;
 
@@ -123,7 +163,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
       mbar_init(smem_u32(&s_full[s]), 1);
       mbar_init(smem_u32(&s_empty[s]), 1);
     }
-    mbar_init(smem_u32(&s_tmem_full), 1);
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(smem_u32(&s_tmem_full[q]), 1);
+      mbar_init(smem_u32(&s_tmem_empty[q]), 4);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x1) : "memory");
@@ -139,44 +182,65 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
 
+  // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles walk the same tile list and
+  // are coupled only through the mbarrier rings (smem stages: full/empty; accumulators: tmem_full/tmem_empty).
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % kStages;
-        if (i >= kStages) mbar_wait(smem_u32(&s_empty[s]), (uint32_t)((i / kStages) - 1) & 1u);
-        const uint32_t bar = smem_u32(&s_full[s]);
-        const uint32_t a_dst = stage_base + (uint32_t)s * kStageBytes, b_dst = a_dst + kABytes;
-        mbar_expect_tx(bar, kStageBytes);
-        tma_load_2d(a_dst, &map_w, i * kChunkK, m0, bar);
-        const bool second = i >= prm.nk1;
-        const CUtensorMap *mx = second ? &map_x2 : &map_x1;
-        const int k0 = (second ? i - prm.nk1 : i) * kChunkK;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+        const int ct = tile % prm.n_col_tiles, rest = tile / prm.n_col_tiles;
+        const int col0 = ct * NT, m0 = (rest % prm.n_m_tiles) * kTileM, cloud = rest / prm.n_m_tiles;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % kStages;
+          if (it >= kStages) mbar_wait(smem_u32(&s_empty[s]), (uint32_t)((it / kStages) - 1) & 1u);
+          const uint32_t bar = smem_u32(&s_full[s]);
+          const uint32_t a_dst = stage_base + (uint32_t)s * kStageBytes, b_dst = a_dst + kABytes;
+          mbar_expect_tx(bar, kStageBytes);
+          tma_load_2d(a_dst, &map_w, i * kChunkK, m0, bar);
+          const bool second = i >= prm.nk1;
+          const CUtensorMap *mx = second ? &map_x2 : &map_x1;
+          const int k0 = (second ? i - prm.nk1 : i) * kChunkK;
 #pragma unroll
-        for (int nb = 0; nb < NT / 32; ++nb) tma_load_3d(b_dst + (uint32_t)nb * 4096u, mx, col0 + nb * 32, k0, cloud, bar);
+          for (int nb = 0; nb < NT / 32; ++nb) tma_load_3d(b_dst + (uint32_t)nb * 4096u, mx, col0 + nb * 32, k0, cloud, bar);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---- MMA issuer
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % kStages;
-        mbar_wait(smem_u32(&s_full[s]), (uint32_t)(i / kStages) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_base = stage_base + (uint32_t)s * kStageBytes, b_base = a_base + kABytes;
-#pragma unroll
-        for (int kk = 0; kk < kChunkK / 8; ++kk) {
-          // A: K-major, rows 128 B apart, 8-row groups 1 KB apart; advance 32 B per K=8 step
-          const uint64_t da = smem_desc(a_base + (uint32_t)kk * 32u, 16u, 1024u, kLayoutSw128);
-          // B: MN-major, 32-column blocks 4 KB apart (LBO), 4-deep K atoms 512 B apart (SBO), 8 k-rows per MMA
-          const uint64_t db = smem_desc(b_base + (uint32_t)kk * 1024u, 4096u, 512u, kLayoutSw128Base32);
-          umma_tf32(tmem_base, da, db, kIdesc, (i | kk) != 0 ? 1u : 0u);
+      int it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++j) {
+        const int buf = j & 1;
+        if (j >= 2) {  // the epilogue must have drained this accumulator (tile j-2)
+          mbar_wait(smem_u32(&s_tmem_empty[buf]), (uint32_t)((j >> 1) - 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        umma_commit(smem_u32(&s_empty[s]));  // frees the stage once these MMAs have read it
+        const uint32_t acc = tmem_base + (uint32_t)(buf * NT);
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % kStages;
+          mbar_wait(smem_u32(&s_full[s]), (uint32_t)(it / kStages) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = stage_base + (uint32_t)s * kStageBytes, b_base = a_base + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / 8; ++kk) {
+            // A: K-major, rows 128 B apart, 8-row groups 1 KB apart; advance 32 B per K=8 step
+            const uint64_t da = smem_desc(a_base + (uint32_t)kk * 32u, 16u, 1024u, kLayoutSw128);
+            // B: MN-major, 32-column blocks 4 KB apart (LBO), 4-deep K atoms 512 B apart (SBO), 8 k-rows per MMA
+            const uint64_t db = smem_desc(b_base + (uint32_t)kk * 1024u, 4096u, 512u, kLayoutSw128Base32);
+            umma_tf32(acc, da, db, kIdesc, (i | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&s_empty[s]));  // frees the stage once these MMAs have read it
+        }
+        umma_commit(smem_u32(&s_tmem_full[buf]));   // accumulator complete
       }
-      umma_commit(smem_u32(&s_tmem_full));   // accumulator complete
     }
   } else {
+   int j = 0;
+   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++j) {
+    const int buf = j & 1;
+    const int ct = tile % prm.n_col_tiles, rest = tile / prm.n_col_tiles;
+    const int col0 = ct * NT, m0 = (rest % prm.n_m_tiles) * kTileM, cloud = rest / prm.n_m_tiles;
     // ---- epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
     // With few output channels the weight rows are REPLICATED over the 128 MMA rows (rep = 2 or 4 copies, made
     // by the host): every TMEM quarter then holds real channels and the four epilogue warps split the columns,
@@ -187,19 +251,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
     const int co = m0 + ((quarter * 32 + lane) & (rows_per_copy - 1));
     const int part = (quarter * 32) / rows_per_copy;              // which column share this warp drains
     const int cbeg = part * (NT >> rep_log2), cend = cbeg + (NT >> rep_log2);
-    mbar_wait(smem_u32(&s_tmem_full), 0);
+    mbar_wait(smem_u32(&s_tmem_full[buf]), (uint32_t)(j >> 1) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const bool live = co < prm.c_out;
     const float shift = live ? __ldg(prm.shift + co) : 0.f;
     const bool relu = (prm.flags & 1) != 0, round_out = (prm.flags & 2) != 0;
-    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * NT);
     const bool warp_live = m0 + ((quarter * 32) & (rows_per_copy - 1)) < prm.c_out;  // a quarter with no real channel has nothing to read
     if (warp_live && prm.pool == 0) {
       // Each lane holds one channel row (32 consecutive columns per TMEM load).  Storing that directly would touch
       // 32 different cache lines with 16 bytes each per instruction; the chunk is transposed through shared memory
-      // (the operand ring is free once the accumulator is complete) so that every store instruction writes four
-      // full 128-byte lines.
-      float *stage = reinterpret_cast<float *>(s_raw + (stage_base - smem_u32(s_raw))) + quarter * (32 * 36);
+      // (a 4.5 KB staging area per epilogue warp behind the operand ring) so that every store instruction writes
+      // four full 128-byte lines.
+      float *stage = reinterpret_cast<float *>(s_raw + (stage_base - smem_u32(s_raw)) + kStages * kStageBytes) + quarter * (32 * 36);
       const int co_base = m0 + ((quarter * 32) & (rows_per_copy - 1));
       const int srow = lane >> 3, scol = (lane & 7) * 4;
       for (int c = cbeg; c < cend && col0 + c < prm.cols; c += 32) {
@@ -228,41 +292,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
         __syncwarp();
       }
     } else if (warp_live) {
-      const int ns = prm.pool;                  // power of two dividing NT: a pooling group never straddles two CTAs
+      const int ns = prm.pool;                  // power of two dividing the warp's column share
       const int lg = __ffs(ns) - 1;
       float *dst = prm.out + ((size_t)cloud * prm.c_out + co) * (prm.cols >> lg) + (col0 >> lg);
-      float run = -INFINITY;
-      for (int c = cbeg; c < cend && col0 + c < prm.cols; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + (uint32_t)c, r);
-        if (!live) continue;
-        float v[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          v[t] = __uint_as_float(r[t]) + shift;
-          if (relu) v[t] = fmaxf(v[t], 0.f);
-        }
-        // in-register max tree over runs of min(ns, 32) columns
-#pragma unroll
-        for (int w = 1; w < 32; w <<= 1) {
-          if (w < ns) {
-#pragma unroll
-            for (int t = 0; t < 32; t += 2 * w) v[t] = fmaxf(v[t], v[t + w]);
-          }
-        }
-        if (ns >= 32) {
-          run = fmaxf(run, v[0]);
-          if (((c + 32) & (ns - 1)) == 0) {
-            dst[(c + 32 - ns) >> lg] = run;   // cols % ns == 0, so a started group is complete
-            run = -INFINITY;
-          }
-        } else {
-#pragma unroll
-          for (int g = 0; g < 32; ++g)
-            if ((g & (ns - 1)) == 0 && col0 + c + g < prm.cols) dst[(c + g) >> lg] = v[g];
-        }
-      }
+      if (ns == 16)
+        pooled_chunks<16>(trow, cbeg, cend, col0, prm.cols, live, shift, relu, dst);
+      else if (ns == 32)
+        pooled_chunks<32>(trow, cbeg, cend, col0, prm.cols, live, shift, relu, dst);
+      else
+        pooled_chunks<0>(trow, cbeg, cend, col0, prm.cols, live, shift, relu, dst, ns);
     }
+      // this accumulator may be overwritten by the MMAs of tile j+2
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tmem_empty[buf])) : "memory");
+   }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -322,19 +366,22 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
     const int rep_log2 = (relu >> 4) & 3;
     if (rep_log2 > 2 || (rep_log2 > 0 && (c_out_pad != kTileM || c_out > (kTileM >> rep_log2))))
       return fail_arg("mlp_layer (row replication needs c_out_pad == 128 and c_out <= 128 / copies)");
-    if (pool > 0 && ((128 >> rep_log2) % pool) != 0) return fail_arg("mlp_layer (pool must divide the per-warp column share)");
+    if (pool > 32 || (pool > 0 && ((128 >> rep_log2) % pool) != 0)) return fail_arg("mlp_layer (pool must be <= 32 and divide the per-warp column share)");
   }
   // tile configuration: (columns per tile, smem stages, CTAs per SM).  Several small CTAs per SM overlap one
   // CTA's TMA / MMA phase with another's epilogue; WS3D_MLP_CFG overrides for experiments.
   static const int cfg_env = []() { const char *e = getenv("WS3D_MLP_CFG"); return (e && *e) ? atoi(e) : -1; }();
-  int cfg = cfg_env >= 0 ? cfg_env : 1;
-  const int max_nt = cfg == 0 ? 256 : cfg == 1 ? 256 : 128;
+  // measured over the backbone's layers (profiles/r1_mlp_bench_v4.json): 128-column tiles with two CTAs per SM win
+  // when the K loop is short (<= 64 input channels) or the layer pools over 16 columns; 256-column tiles otherwise
+  int cfg = cfg_env >= 0 ? cfg_env : ((c1 + c2 <= 64 || (pool > 0 && pool <= 16)) ? 3 : 0);
+  const int max_nt = cfg <= 1 ? 256 : 128;
   if (pool < 0 || (pool > 0 && (cols % pool != 0 || max_nt % pool != 0 || (pool & (pool - 1)) != 0)))
     return fail_arg("mlp_layer (pool must be a power of two dividing the column tile and cols)");
   MlpParams prm;
   prm.c_out = c_out; prm.cols = cols; prm.pool = pool; prm.flags = relu; prm.shift = shift; prm.out = out;
   prm.nk1 = ceil_div(c1, kChunkK);
   prm.nk2 = c2 > 0 ? ceil_div(c2, kChunkK) : 0;
+  prm.n_m_tiles = c_out_pad / kTileM;
   const int k_pad = (prm.nk1 + prm.nk2) * kChunkK;
   CUtensorMap mw, m1, m2;
   {
@@ -360,18 +407,22 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
   cudaError_t e = cudaSuccess;
 #define WS3D_MLP_LAUNCH(NT_, ST_, MB_)                                                                              \
   {                                                                                                                 \
-    const size_t smem = (size_t)(ST_) * (kTileM * kChunkK * 4 + (NT_) * kChunkK * 4) + 1024;                        \
+    const size_t smem = (size_t)(ST_) * (kTileM * kChunkK * 4 + (NT_) * kChunkK * 4) + 4 * 32 * 36 * 4 + 1024;      \
     auto kern = mlp_layer_kernel<NT_, ST_, MB_>;                                                                    \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
     if (e != cudaSuccess) { set_error("mlp_layer: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }     \
-    dim3 grid((unsigned)ceil_div(cols, NT_), (unsigned)(c_out_pad / kTileM), (unsigned)b);                          \
-    kern<<<grid, kThreads, smem, to_stream(stream)>>>(mw, m1, m2, prm);                                             \
+    prm.n_col_tiles = ceil_div(cols, NT_);                                                                          \
+    const long long tiles = (long long)prm.n_col_tiles * prm.n_m_tiles * b;                                         \
+    if (tiles > 0x7FFFFFFFLL) return fail_arg("mlp_layer (too many tiles)");                                        \
+    prm.n_tiles = (int)tiles;                                                                                       \
+    const int ctas = (int)(tiles < (long long)kNumSMs * (MB_) ? tiles : (long long)kNumSMs * (MB_));                \
+    kern<<<ctas, kThreads, smem, to_stream(stream)>>>(mw, m1, m2, prm);                                             \
   }
   switch (cfg) {
-    case 0: WS3D_MLP_LAUNCH(256, 4, 1) break;   // one big CTA per SM, deep ring
-    case 1: WS3D_MLP_LAUNCH(256, 2, 2) break;   // two CTAs per SM
-    case 2: WS3D_MLP_LAUNCH(128, 3, 3) break;   // three CTAs per SM, 128-column tiles
-    default: WS3D_MLP_LAUNCH(128, 2, 4) break;  // four CTAs per SM
+    case 0: WS3D_MLP_LAUNCH(256, 4, 1) break;   // one persistent CTA per SM, 256-column tiles (2 x 256 TMEM columns), deep ring
+    case 1: WS3D_MLP_LAUNCH(256, 3, 1) break;
+    case 2: WS3D_MLP_LAUNCH(128, 3, 2) break;   // two persistent CTAs per SM, 128-column tiles (2 x 128 TMEM columns each)
+    default: WS3D_MLP_LAUNCH(128, 2, 2) break;
   }
 #undef WS3D_MLP_LAUNCH
   return check_launch(what);
