@@ -89,3 +89,20 @@ def test_backbone_fused_eval_path_close_to_fp32_path():
     rel = float((fused - exact).abs().max()) / (float(exact.abs().max()) + 1e-6)
     assert rel < 2e-2, rel     # 8 layers of TF32 rounding, same order as cuDNN's TF32 path
     assert torch.isfinite(fused).all()
+
+
+def test_rpn_heads_on_the_layer_kernel_match_pytorch():
+    """models.RPN: the cls / reg heads (Conv1d + BN + ReLU, Dropout, Conv1d with bias) through FoldedMLP."""
+    from ws3d_b200 import models, synth
+    torch.manual_seed(1)
+    rpn = models.RPN().to(dev).eval()
+    feats = torch.randn(2, 128, 4096, device=dev)
+    with torch.no_grad():
+        old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        want_cls, want_reg = rpn.rpn_cls_layer(feats), rpn.rpn_reg_layer(feats)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        got_cls, got_reg = rpn._head("rpn_cls_layer", feats), rpn._head("rpn_reg_layer", feats)
+    assert got_cls.shape == want_cls.shape == (2, 1, 4096) and got_reg.shape == want_reg.shape == (2, 40, 4096)
+    for got, want in ((got_cls, want_cls), (got_reg, want_reg)):
+        assert float((got - want).abs().max()) <= TOL * (float(want.abs().max()) + 1e-6) + 1e-4

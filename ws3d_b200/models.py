@@ -13,6 +13,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import fused_mlp
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
@@ -149,10 +150,21 @@ class RPN(nn.Module):
             nn.init.constant_(self.rpn_cls_layer[2].conv.bias, -np.log((1 - pi) / pi))
         nn.init.normal_(self.rpn_reg_layer[-1].conv.weight, mean=0, std=0.001)
 
+    def _head(self, name: str, x: torch.Tensor) -> torch.Tensor:
+        """A per-point head (Conv1d + BN + ReLU, Dropout, Conv1d).  Inference: the tensor-core layer kernel
+        (dropout is the identity in eval mode); otherwise the PyTorch modules."""
+        seq = getattr(self, name)
+        if fused_mlp.enabled_for(self) and x.is_cuda and fused_mlp.supported(x.shape[2], 0) and x.is_contiguous():
+            cache = self.__dict__.setdefault("_folded_heads", {})
+            if name not in cache:
+                cache[name] = fused_mlp.FoldedMLP(nn.Sequential(*[m for m in seq if not isinstance(m, nn.Dropout)]))
+            return cache[name](x)
+        return seq(x)
+
     def forward(self, input_data):
         pts_input = input_data['pts_input'] if isinstance(input_data, dict) else input_data
         backbone_xyz, backbone_features = self.backbone_net(pts_input)
-        rpn_cls = self.rpn_cls_layer(backbone_features).transpose(1, 2).contiguous()
-        rpn_reg = self.rpn_reg_layer(backbone_features).transpose(1, 2).contiguous()
+        rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
+        rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()
         return {'rpn_cls': rpn_cls, 'rpn_reg': rpn_reg, 'backbone_xyz': backbone_xyz,
                 'backbone_features': backbone_features}
