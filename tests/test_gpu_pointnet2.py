@@ -35,8 +35,10 @@ FPS_CASES = [
     (1, 1, 1, "uniform"), (2, 5000, 100, "uniform"), (2, 2048, 512, "grid"), (1, 300, 300, "grid"),
     (1, 64, 100, "uniform"),  # m > n: the sampler keeps re-selecting (all distances 0)
     (200, 512, 128, "uniform"), (1, 20000, 64, "uniform"), (20, 16384, 16, "uniform"),
-    # batches that leave < 4 SMs per cloud take the spatially bucketed single-CTA kernel (csrc/fps_bucket.cu)
-    (40, 2048, 128, "uniform"), (38, 4096, 64, "grid"), (40, 5000, 300, "scene"), (38, 16384, 256, "scene"),
+    # batches that leave < 2 SMs per cloud take the spatially bucketed single-CTA kernel (csrc/fps_bucket.cu)
+    (80, 2048, 128, "uniform"), (76, 4096, 64, "grid"), (80, 5000, 300, "scene"), (76, 16384, 256, "scene"),
+    # clusters of 2 / 4 CTAs with the one-level exchange (fps_flat_kernel): n > 4096
+    (40, 5000, 300, "scene"), (3, 8192, 2048, "uniform"), (2, 6000, 700, "grid"), (30, 16384, 128, "scene"),
 ]
 
 

@@ -36,20 +36,21 @@ print(json.dumps(out))
 
 def main():
     res = {}
-    for name, env in [("auto", {}), ("cluster", {"WS3D_FPS_BUCKET": "0"}), ("bucket", {"WS3D_FPS_BUCKET": "1"})]:
+    for name, env in [("auto", {}), ("flat", {"WS3D_FPS_BUCKET": "0", "WS3D_FPS_FLAT": "1"}),
+                      ("cluster", {"WS3D_FPS_BUCKET": "0", "WS3D_FPS_FLAT": "0"}), ("bucket", {"WS3D_FPS_BUCKET": "1"})]:
         e = dict(os.environ); e.update(env)
         p = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
         if p.returncode:
             print(name, "FAILED", p.stderr[-2000:])
             continue
         res[name] = json.loads(p.stdout.strip().splitlines()[-1])
-    names = [k for k in ("auto", "cluster", "bucket") if k in res]
+    names = [k for k in ("auto", "flat", "cluster", "bucket") if k in res]
     for i in range(len(res[names[0]])):
         a = res[names[0]][i]
         line = f"b={a['b']:3d} n={a['n']:6d} m={a['m']:5d} "
         for k in names:
             r = res[k][i]
-            line += f" | {k} {r['ms']:.3f} ms ({r['us_per_iter']:.3f} us/sample)"
+            line += f" | {k} {r['ms']:.3f}"
         line += "  same_idx=" + str(len({res[k][i]['checksum'] for k in names}) == 1)
         print(line)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "fps_bench.json"), "w"))

@@ -49,6 +49,26 @@ __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
   return __fmaf_rn(dz, dz, t);
 }
 
+// Two squared distances at once with the packed FP32 pipe (FADD2 / FMUL2 / FFMA2 on sm_100): every lane of a
+// packed operation is an IEEE round-to-nearest operation, so each result is bit-identical to sqdist_ref.
+__device__ __forceinline__ void sqdist_ref_x2(float x0, float x1, float y0, float y1, float z0, float z1, float cx, float cy,
+                                              float cz, float &d0, float &d1) {
+  unsigned long long X, Y, Z, CX, CY, CZ, T;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(X) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(Y) : "f"(y0), "f"(y1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(Z) : "f"(z0), "f"(z1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(CX) : "f"(cx));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(CY) : "f"(cy));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(CZ) : "f"(cz));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(X) : "l"(X), "l"(CX));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(Y) : "l"(Y), "l"(CY));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(Z) : "l"(Z), "l"(CZ));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(T) : "l"(Y));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(T) : "l"(X), "l"(T));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(T) : "l"(Z), "l"(T));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(T));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -209,6 +209,142 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
   if (CLUSTER) cluster_sync_all();  // nobody leaves while a peer could still post to it
 }
 
+// One-level exchange: every WARP posts its candidate {value, key} straight to every CTA of the cluster and every
+// warp then reduces the C * nwarps candidates itself.  Compared with fps_cluster_kernel this removes the CTA
+// barrier and warp 0's intermediate arg-max from the serial chain of an iteration (warp arg-max -> DSMEM post ->
+// final arg-max instead of warp arg-max -> barrier -> CTA arg-max -> DSMEM post -> final arg-max).  The winner's
+// coordinates are not shipped: every CTA keeps the whole cloud in shared memory (3 n floats <= 192 KB).
+constexpr int kFlatMaxRecs = 128;   // C * warps per CTA: four candidates per lane in the final reduction
+
+template <int P>
+__global__ void __launch_bounds__(512, 1) fps_flat_kernel(FpsParams prm) {
+  extern __shared__ __align__(16) float s_cloud[];     // x[n], y[n], z[n]
+  __shared__ __align__(8) uint2 s_rec[2][kFlatMaxRecs];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = blockDim.x, nwarps = T >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t C = cluster_nctarank();
+  const int CT = (int)C * T;
+  const int g = (int)rank * T + tid;
+  const int R = (int)C * nwarps;
+  const int n = prm.n, m = prm.m, L = prm.L;
+  const size_t cloud = blockIdx.y;
+  const float *xyz = prm.xyz + cloud * (size_t)n * 3;
+  float *temp = prm.temp ? prm.temp + cloud * (size_t)n : nullptr;
+  int *idx = prm.idx + cloud * (size_t)m;
+  float *new_xyz = prm.new_xyz ? prm.new_xyz + cloud * (size_t)m * 3 : nullptr;
+  float *s_x = s_cloud, *s_y = s_cloud + n, *s_z = s_cloud + 2 * n;
+
+  const uint32_t bar_base = smem_u32(&s_bar[0]);
+  if (tid == 0) {
+    mbar_init(bar_base, 1);
+    mbar_init(bar_base + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = tid; e < n * 3; e += T) {   // coalesced read of the packed cloud, de-interleaved into x / y / z
+    const float v = __ldg(xyz + e);
+    const int k = e / 3, a = e - k * 3;
+    s_cloud[a * n + k] = v;
+  }
+
+  float x[P], y[P], z[P], t[P];
+  uint32_t key[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int k = p * CT + g;
+    if (k < n) {
+      x[p] = __ldg(xyz + (size_t)k * 3 + 0);
+      y[p] = __ldg(xyz + (size_t)k * 3 + 1);
+      z[p] = __ldg(xyz + (size_t)k * 3 + 2);
+      t[p] = temp ? temp[k] : 1e10f;
+      key[p] = fps_key((uint32_t)k, L);
+    } else {
+      x[p] = y[p] = z[p] = 0.f;
+      t[p] = -1.f;  // never beats a real point (real running distances are >= 0)
+      key[p] = kNoKey;
+    }
+  }
+  sort_by_key<P>(key, x, y, z, t);  // strict '>' below must meet a thread's points in ascending key order
+
+  float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);  // idx[0] = 0
+  if (g == 0 && m > 0) {
+    idx[0] = 0;
+    if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
+  }
+  // remote address of this warp's record slot and of the barrier in CTA `lane`, per parity
+  uint32_t rdst[2] = {0u, 0u}, rbars[2] = {0u, 0u};
+  if (lane < (int)C) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      rdst[q] = mapa(smem_u32(&s_rec[q][rank * nwarps + warp]), (uint32_t)lane);
+      rbars[q] = mapa(bar_base + 8u * (uint32_t)q, (uint32_t)lane);
+    }
+  }
+  cluster_sync_all();  // barriers and cloud copies are ready everywhere
+
+  for (int it = 0; it + 1 < m; ++it) {
+    const int par = it & 1;
+    const uint32_t bar = bar_base + 8u * (uint32_t)par;
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)R * 8u);
+    // distance update, two points per packed instruction; running arg-max in ascending key order (strict '>').
+    // (Measured: replacing the running scan by a max tree + key tree is slower -- more instructions to issue.)
+    float best = -1.f;
+    uint32_t bkey = kNoKey;
+    if (P >= 2) {
+#pragma unroll
+      for (int p = 0; p + 1 < P; p += 2) {
+        float d0, d1;
+        sqdist_ref_x2(x[p], x[p + 1], y[p], y[p + 1], z[p], z[p + 1], cx, cy, cz, d0, d1);
+        t[p] = fminf(d0, t[p]);
+        t[p + 1] = fminf(d1, t[p + 1]);
+        if (t[p] > best) { best = t[p]; bkey = key[p]; }
+        if (t[p + 1] > best) { best = t[p + 1]; bkey = key[p + 1]; }
+      }
+    } else {
+      t[0] = fminf(sqdist_ref(x[0] - cx, y[0] - cy, z[0] - cz), t[0]);
+      if (t[0] > best) { best = t[0]; bkey = key[0]; }
+    }
+    const int vb = __float_as_int(best);
+    const int wv = __reduce_max_sync(0xFFFFFFFFu, vb);
+    const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, vb == wv ? bkey : kNoKey);
+    if (lane < (int)C) st_async_v2(par ? rdst[1] : rdst[0], (uint32_t)wv, wk, par ? rbars[1] : rbars[0]);
+
+    mbar_wait(bar, (uint32_t)(it >> 1) & 1u);
+    int bv = INT_MIN;
+    uint32_t bk = kNoKey;
+#pragma unroll
+    for (int s = 0; s < kFlatMaxRecs / 32; ++s) {
+      const int ri = s * 32 + lane;
+      if (ri < R) {
+        const uint2 rc = s_rec[par][ri];
+        const int v = (int)rc.x;
+        if (v > bv || (v == bv && rc.y < bk)) { bv = v; bk = rc.y; }
+      }
+    }
+    const int gv = __reduce_max_sync(0xFFFFFFFFu, bv);
+    const uint32_t win_key = __reduce_min_sync(0xFFFFFFFFu, bv == gv ? bk : kNoKey);
+    const int wi = (int)fps_unkey(win_key, L);
+    cx = s_x[wi]; cy = s_y[wi]; cz = s_z[wi];
+    if (g == 0) {
+      idx[it + 1] = wi;
+      if (new_xyz) {
+        new_xyz[(size_t)(it + 1) * 3 + 0] = cx;
+        new_xyz[(size_t)(it + 1) * 3 + 1] = cy;
+        new_xyz[(size_t)(it + 1) * 3 + 2] = cz;
+      }
+    }
+  }
+
+  if (temp) {
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+      if (key[p] != kNoKey) temp[fps_unkey(key[p], L)] = t[p];
+  }
+  cluster_sync_all();  // nobody leaves while a peer could still post to it
+}
+
 // Any-size fallback: one CTA per cloud, running distances in global memory (L2-resident).
 __global__ void __launch_bounds__(1024, 1) fps_generic_kernel(FpsParams prm) {
   __shared__ int2 s_wrec[32];
@@ -302,6 +438,30 @@ int launch_cluster(const FpsParams &prm, int b, int C, int T, cudaStream_t strea
   return check_launch("furthest_point_sampling");
 }
 
+template <int P>
+int launch_flat(const FpsParams &prm, int b, int C, int T, cudaStream_t stream) {
+  auto kern = fps_flat_kernel<P>;
+  const size_t smem = (size_t)prm.n * 3 * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && C > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) { set_error("fps: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C, (unsigned)b, 1);
+  cfg.blockDim = dim3((unsigned)T, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, prm);
+  if (e != cudaSuccess) { set_error("fps: launch (flat P=%d C=%d T=%d): %s", P, C, T, cudaGetErrorString(e)); return (int)e; }
+  return check_launch("furthest_point_sampling");
+}
+
 int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, float *new_xyz, cudaStream_t stream) {
   if (b < 0 || n < 0 || m < 0 || (b > 0 && n > 0 && m > 0 && (!xyz || !idx))) return fail_arg("furthest_point_sampling");
   if (b == 0 || m == 0) return 0;
@@ -342,6 +502,32 @@ int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, f
 
   const bool ok = (C >= 1 && C <= kMaxCluster && (C & (C - 1)) == 0 && T >= 32 && T <= 1024 && (T & (T - 1)) == 0 &&
                    P <= 8 && (long long)P * T * C >= n);
+  {
+    // Clouds of 2048+ points that fit every CTA's shared memory: one-level exchange (fps_flat_kernel) on a
+    // cluster of 4 CTAs x 16 (n > 8192) or 8 points per thread (n = 4096: 0.40 ms against 0.50 ms on one CTA).  Measured at b = 16, n = 16384 (profiles/r1_fps_bench_v4.json):
+    // 2.09 ms against 2.76 ms for the two-level kernel on 8 CTAs; more CTAs or more warps per cluster lose to
+    // the DSMEM traffic of the all-to-all post (C = 8, T = 512: 5.2 ms), fewer to the per-thread update.
+    static const int flat = env_int("WS3D_FPS_FLAT", 1);
+    static const int flat_min = env_int("WS3D_FPS_FLAT_MIN", 2048);
+    if (flat && n >= flat_min && (size_t)n * 12 <= 200 * 1024 && cmax >= 2) {
+      int Cf = env_int("WS3D_FPS_C", cmax >= 4 ? 4 : 2);
+      int Tf = pow2_ceil(ceil_div(ceil_div(n, Cf), env_int("WS3D_FPS_PPT", n > 8192 ? 16 : 8)));
+      if (Tf < 32) Tf = 32;
+      if (Tf > 512) Tf = 512;
+      const int Pf = pow2_ceil(ceil_div(ceil_div(n, Cf), Tf));
+      if (Cf > 1 && Cf <= kMaxCluster && (Cf & (Cf - 1)) == 0 && Pf <= 16 && Cf * (Tf / 32) <= kFlatMaxRecs &&
+          (long long)Pf * Tf * Cf >= n) {
+        prm.log2T = ilog2(Tf);
+        switch (Pf) {
+          case 1: return launch_flat<1>(prm, b, Cf, Tf, stream);
+          case 2: return launch_flat<2>(prm, b, Cf, Tf, stream);
+          case 4: return launch_flat<4>(prm, b, Cf, Tf, stream);
+          case 8: return launch_flat<8>(prm, b, Cf, Tf, stream);
+          case 16: return launch_flat<16>(prm, b, Cf, Tf, stream);
+        }
+      }
+    }
+  }
   if (!ok) {
     // generic path needs the scratch array
     float *tp = temp;

@@ -352,12 +352,13 @@ int launch_bucket(const FpsParams &prm, int b, cudaStream_t stream) {
 
 // Large clouds only: below 2048 points the whole cloud is a few buckets and the register kernels win;
 // 16384 points is what fits one SM's shared memory (coordinates + 16-bit indices = 224 KB).
-// It needs ONE SM per cloud, so it is the choice when the batch leaves fewer than ~4 SMs per cloud for the
-// cluster kernels (measured on B200, b = 64 x 16384 points: 3.6 ms against 4.9 ms); WS3D_FPS_BUCKET=1/0 forces it.
+// It needs ONE SM per cloud, so it is the choice when the batch leaves fewer than 2 SMs per cloud for the
+// cluster kernels (b > 74; measured on B200 at b = 64 x 16384 points: 3.55 ms against 4.39 ms for the two-level
+// cluster kernel, 3.06 ms for the flat one on 2 SMs per cloud); WS3D_FPS_BUCKET=1/0 forces it.
 bool fps_bucket_applicable(int b, int n, int m) {
   static const int mode = env_int2("WS3D_FPS_BUCKET", -1);
   if (mode == 0 || n < 2048 || n > 16384 || m < 64 || b < 1 || b > 65535) return false;
-  return mode == 1 || b * 4 > kNumSMs;
+  return mode == 1 || b * 2 > kNumSMs;
 }
 
 int fps_bucket_launch(const FpsParams &prm, int b, cudaStream_t stream) {
