@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(1024, 1) fps_cluster_kernel(FpsParams prm) {
 // coordinates are not shipped: every CTA keeps the whole cloud in shared memory (3 n floats <= 192 KB).
 constexpr int kFlatMaxRecs = 128;   // C * warps per CTA: four candidates per lane in the final reduction
 
-template <int P>
-__global__ void __launch_bounds__(512, 1) fps_flat_kernel(FpsParams prm) {
+template <int P, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) fps_flat_kernel(FpsParams prm) {
   extern __shared__ __align__(16) float s_cloud[];     // x[n], y[n], z[n]
   __shared__ __align__(8) uint2 s_rec[2][kFlatMaxRecs];
   __shared__ __align__(8) unsigned long long s_bar[2];
@@ -438,9 +438,9 @@ int launch_cluster(const FpsParams &prm, int b, int C, int T, cudaStream_t strea
   return check_launch("furthest_point_sampling");
 }
 
-template <int P>
+template <int P, int MAXT = 512>
 int launch_flat(const FpsParams &prm, int b, int C, int T, cudaStream_t stream) {
-  auto kern = fps_flat_kernel<P>;
+  auto kern = fps_flat_kernel<P, MAXT>;
   const size_t smem = (size_t)prm.n * 3 * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess && C > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
