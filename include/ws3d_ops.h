@@ -132,7 +132,7 @@ int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_ou
  * pointnet2_modules.py:40-44,154 + pytorch_utils.py:5-32 in inference.
  *   w (c_out_pad, 32*(ceil(c1/32)+ceil(c2/32))) row-major, zero padded, c_out_pad % 128 == 0;
  *   x1 (B, c1, cols), x2 (B, c2, cols) or NULL (second K range, e.g. skip features); shift (c_out_pad);
- *   out (B, c_out, cols) or, when pool > 0, (B, c_out, cols / pool).  cols % 4 == 0; pool is a power of two <= 32 dividing cols.
+ *   out (B, c_out, cols) or, when pool > 0, (B, c_out, cols / pool).  cols % 4 == 0; pool is a power of two <= 128 dividing cols (and 128 / r, see relu bits 4-5).
  *   relu: bit 0 = apply ReLU; bit 1 = round the stored output to the nearest TF32 value (use for every layer
  *   whose output feeds another ws3d_mlp_layer: the tensor core truncates FP32 operands to TF32);
  *   bits 4-5 = log2(r), r in {1, 2, 4}: rows [k*128/r, (k+1)*128/r) of w (and shift) each hold a copy of the

@@ -41,7 +41,8 @@ def _ref(mlp, x, pool):
 
 
 @pytest.mark.parametrize("spec,B,M,K", [((4, 16, 16, 32), 2, 512, 16), ((4, 32, 32, 64), 1, 1024, 32), ((99, 64, 96, 128), 2, 256, 32),
-                                        ((259, 128, 196, 256), 2, 64, 16), ((515, 256, 384, 512), 1, 64, 32), ((35, 40), 3, 100, 4)])
+                                        ((259, 128, 196, 256), 2, 64, 16), ((515, 256, 384, 512), 1, 64, 32), ((35, 40), 3, 100, 4),
+                                        ((131, 128, 128, 256), 3, 32, 64), ((20, 24), 2, 8, 128), ((20, 70), 2, 6, 64)])
 def test_folded_mlp_with_pool_matches_torch(spec, B, M, K):
     from ws3d_b200 import fused_mlp
     mlp = _mlp(spec, seed=sum(spec))

@@ -94,4 +94,4 @@ def test_folded_mlp_weights_equal_conv_bn_eval_on_cpu():
     r = fused_mlp._round_tf32(t)
     assert r.tolist() == [1.0 + 2 ** -10, 1.0, -(1.0 + 2 ** -10), 3.0]
     assert fused_mlp.supported(4096, 32) and fused_mlp.supported(4096, 0) and not fused_mlp.supported(4098, 0) \
-        and not fused_mlp.supported(4096, 64) and not fused_mlp.supported(4096, 24)
+        and fused_mlp.supported(4096, 64) and not fused_mlp.supported(4096, 256) and not fused_mlp.supported(4096, 24)

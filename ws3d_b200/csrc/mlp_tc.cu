@@ -98,13 +98,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 
 // Max-pool epilogue of one warp: 32 channels (one per lane) x the columns [cbeg, cend) of the accumulator.
-// NS = nsample when it is 16 or 32 (the backbone's values: everything folds at compile time, one 4-byte store per
-// pooled value), NS = 0 takes any power of two `ns_rt` <= 32.  cols % ns == 0, so a started group is complete.
+// NS = nsample when it is 16 or 32 (the backbone's values: everything folds at compile time), NS = 0 takes any
+// power of two `ns_rt` <= 128 that divides the warp's column share.  cols % ns == 0, so a started group is complete.
 template <int NS>
 __device__ __forceinline__ void pooled_chunks(uint32_t trow, int cbeg, int cend, int col0, int cols, bool live, float shift,
                                               bool relu, float *dst, int ns_rt = 0) {
   const int ns = NS ? NS : ns_rt;
   const int lg = __ffs(ns) - 1;
+  float run = -INFINITY;
   for (int c = cbeg; c < cend && col0 + c < cols; c += 32) {
     uint32_t r[32];
     tmem_ld_32x32(trow + (uint32_t)c, r);
@@ -129,6 +130,12 @@ __device__ __forceinline__ void pooled_chunks(uint32_t trow, int cbeg, int cend,
       const bool second = col0 + c + 16 < cols;   // the row may end in the middle of this 32-column chunk
       if (second && (reinterpret_cast<uintptr_t>(o) & 7u) == 0) *reinterpret_cast<float2 *>(o) = make_float2(v[0], v[16]);
       else { o[0] = v[0]; if (second) o[1] = v[16]; }
+    } else if (ns > 32) {   // a group spans several 32-column chunks (cbeg % ns == 0: the share starts on a group)
+      run = fmaxf(run, v[0]);
+      if (((c + 32) & (ns - 1)) == 0) {
+        dst[(c + 32 - ns) >> lg] = run;
+        run = -INFINITY;
+      }
     } else {
 #pragma unroll
       for (int g = 0; g < 32; ++g)
@@ -366,7 +373,7 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
     const int rep_log2 = (relu >> 4) & 3;
     if (rep_log2 > 2 || (rep_log2 > 0 && (c_out_pad != kTileM || c_out > (kTileM >> rep_log2))))
       return fail_arg("mlp_layer (row replication needs c_out_pad == 128 and c_out <= 128 / copies)");
-    if (pool > 32 || (pool > 0 && ((128 >> rep_log2) % pool) != 0)) return fail_arg("mlp_layer (pool must be <= 32 and divide the per-warp column share)");
+    if (pool > 128 || (pool > 0 && ((128 >> rep_log2) % pool) != 0)) return fail_arg("mlp_layer (pool must be <= 128 and divide the per-warp column share)");
   }
   // tile configuration: (columns per tile, smem stages, CTAs per SM).  Several small CTAs per SM overlap one
   // CTA's TMA / MMA phase with another's epilogue; WS3D_MLP_CFG overrides for experiments.

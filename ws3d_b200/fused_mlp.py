@@ -104,13 +104,16 @@ class FoldedMLP:
             c1 = cur1.shape[1]
             c2 = cur2.shape[1] if cur2 is not None else 0
             assert (c1, c2) == tuple(lay.splits), ((c1, c2), lay.splits)
-            flags = int(lay.relu) | (0 if last else 2) | (lay.rep_log2 << 4)  # intermediates are stored TF32-rounded
+            rep = lay.rep_log2
+            while p and (_TILE_M >> rep) % p:   # a pooling group must fit the column share of one epilogue warp
+                rep -= 1                        # (fewer copies are used; the extra replicated rows are simply masked)
+            flags = int(lay.relu) | (0 if last else 2) | (rep << 4)  # intermediates are stored TF32-rounded
             native.mlp_layer(B, lay.c_out, lay.c_out_pad, c1, c2, cols, lay.w, lay.shift, cur1, cur2, out, flags, p)
             cur1, cur2 = out, None
         return cur1
 
 
 def supported(cols: int, pool: int) -> bool:
-    """Shapes the kernel accepts: 16-byte aligned rows; pooling groups (nsample) that are a power of two <= 32, so
+    """Shapes the kernel accepts: 16-byte aligned rows; pooling groups (nsample) that are a power of two <= 128, so
     that a group never straddles the column share of one epilogue warp."""
-    return cols % 4 == 0 and (pool == 0 or (pool & (pool - 1) == 0 and pool <= 32 and cols % pool == 0))
+    return cols % 4 == 0 and (pool == 0 or (pool & (pool - 1) == 0 and pool <= 128 and cols % pool == 0))
