@@ -267,6 +267,22 @@ def run_gpu(args):
                 feats = model(x)[1]
                 return feats.sum(dim=(1, 2)).cpu()  # D2H read of the per-cloud checksum (synchronises)
 
+    # Software pipeline (ws3d_b200.graphs.PipelinedBackboneRunner): one replay = level-1 FPS of batch i+1 beside the
+    # rest of the forward pass of batch i.  A step still completes exactly one batch of 16 clouds.
+    pipelined = use_graph and args.inflight >= 2
+    if pipelined:
+        from ws3d_b200.graphs import PipelinedBackboneRunner
+        native.set_sm_budget(args.sm_budget)
+        host_b = torch.from_numpy(synth.make_batch(BATCH, NPTS, first_scene=(world + rank) * BATCH)).pin_memory()
+        hosts = [host, host_b]
+        pr = PipelinedBackboneRunner(model, resident)
+        pr.stage[0].copy_(host)
+        pr.stage[1].copy_(host_b)
+        pr.prefetch(pr.stage[0])
+
+        def step_pipe():
+            return pr.step()
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -302,10 +318,51 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches, prof, wall
 
+    def timed_stream_e2e(steps):
+        """K pipelined steps from pinned HOST batches, one event pair round all of them: per step an H2D copy of the
+        batch after next (copy stream, overlapping the running step), one replay, a checksum kernel and an async
+        D2H read of it; the host only ever waits for the PREVIOUS step's result.  L2 is flushed in-stream."""
+        pinned = [torch.empty(BATCH, dtype=torch.float32).pin_memory() for _ in range(2)]
+        read_ev = [None, None]
+        results = []
+        pr.prefetch(hosts[0])
+        pr.stage_next(hosts[1])
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for j in range(steps):
+            flush_small.fill_(0)
+            out = pr.step()                       # completes batch j (samples batch j+1 meanwhile)
+            pr.stage_next(hosts[j % 2])           # H2D of batch j+2, waits only for the replay that read that buffer
+            if read_ev[j % 2] is not None:        # result of step j-2 must have been consumed before its buffer is reused
+                read_ev[j % 2].synchronize()
+                results.append(float(pinned[j % 2][0]))
+            pinned[j % 2].copy_(out.sum(dim=(1, 2)), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            read_ev[j % 2] = ev
+        for k in ((steps) % 2, (steps + 1) % 2):
+            if read_ev[k] is not None:
+                read_ev[k].synchronize()
+                results.append(float(pinned[k][0]))
+        e.record()
+        e.synchronize()
+        sync_all()
+        t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert len(results) == steps
+        return float(t.item())
+
+    flush_small = torch.empty(160 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     for _ in range(max(args.warmup, 3)):
         step_resident()
         step_e2e()
         step_eager()
+        if pipelined:
+            step_pipe()
+    if pipelined:
+        timed_stream_e2e(max(args.warmup, 3))
     sync_all()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -318,6 +375,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
         launches = (_C.launch_count() - l0) * args.steps
     ms_e2e, _, _, _ = timed_region(step_e2e, args.steps, profile=False)
+    ms_single, ms_single_e2e = ms_total, ms_e2e
+    if pipelined:
+        pr.prefetch(pr.stage[0])
+        ms_total, _, _, _ = timed_region(step_pipe, args.steps, profile=False)
+        ms_e2e = timed_stream_e2e(args.steps)
     # the same K steps once more with a CUDA-event pair round every launch of this library (per-kernel durations
     # for the roofline entries; kept out of `value` because ~600 extra event records per step cost host time)
     ms_prof, _, prof, _ = timed_region(step_eager, args.steps, profile=True)
@@ -375,12 +437,22 @@ def run_gpu(args):
                        "mlp": ("tcgen05 TF32 shared-MLP layers (conv1x1+BN+ReLU[+max-pool] per launch, FP32 accumulate)"
                                if torch.backends.cudnn.allow_tf32 else "PyTorch/cuDNN fp32 (TF32 off)"),
                        "launch": "one CUDA graph replay per step" if use_graph else "eager launches",
+                       "pipeline": ("2 batches in flight: each replay runs level-1 FPS of batch i+1 (high-priority stream) beside "
+                                    "the rest of the forward pass of batch i; one batch of 16 clouds completes per step"
+                                    if pipelined else "none (one batch in flight)"),
+                       "sm_budget_persistent_kernels": args.sm_budget if pipelined else 0,
                        "streams": "two CUDA streams (FPS chain + interpolation stencils run ahead of grouping / MLPs)"
                                   if os.environ.get("WS3D_TWO_STREAMS", "1") != "0" else "single stream",
                        "sharding": "scenes per rank, no data-path collective"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4) * world,
                     "d2h_bytes_per_step": BATCH * 4 * world, "ms_per_step": round(ms_e2e / args.steps, 4),
-                    "note": "pinned host cloud -> H2D -> backbone forward -> per-cloud feature checksum -> D2H"},
+                    "note": ("pinned host clouds -> H2D (copy stream) -> pipelined forward -> per-cloud feature checksum -> async D2H, "
+                             "K steps streamed under one event pair, L2 flushed in-stream every step" if pipelined else
+                             "pinned host cloud -> H2D -> backbone forward -> per-cloud feature checksum -> D2H")},
+            "single_batch_latency": {"ms": round(ms_single / args.steps, 4),
+                                     "Mpoints_per_s": round(world * BATCH * NPTS / (ms_single / args.steps / 1e3) / 1e6, 3),
+                                     "e2e_ms": round(ms_single_e2e / args.steps, 4),
+                                     "note": "one batch in flight (graph replay of the two-stream forward), same timing method"},
             "gpu_launches": int(launches),
             "rpn": {"scenes_per_s": round(world * BATCH / (ms_rpn / args.steps / 1e3), 1), "ms_per_step": round(ms_rpn / args.steps, 4),
                     "note": "Stage-1 RPN forward (backbone + cls/reg heads, lib/net/rpn.py:67-81), same batch, inputs resident"},
@@ -406,6 +478,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "2")),
+                    help="2: software-pipelined forward (level-1 FPS of the next batch beside the current batch); 1: off")
+    ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "0")),
+                    help="SMs the persistent MLP kernel spreads over in pipelined mode (0 = all)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_cpu(args)

@@ -43,6 +43,15 @@ int ws3d_abi_version(void);
 const char *ws3d_last_error(void);
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t ws3d_launch_count(void);
+/* Scratch arena (0..7) used by the calling thread's subsequent launches; returns the previous one.
+ * The cached scratch buffers (cell grids, NMS masks) are per (device, arena): forward passes that are
+ * in flight at the same time -- e.g. two CUDA graphs replayed on different streams -- must be issued
+ * (or captured) under different arenas.  The reference has no counterpart (it cudaMallocs per call,
+ * iou3d.cpp:87, roipool3d_kernel.cu:214). */
+int ws3d_set_workspace_arena(int arena);
+/* Upper bound on the SMs a persistent kernel (ws3d_mlp_layer) spreads over; 0 = all 148.  Used when a
+ * latency-bound kernel of another batch (FPS) is meant to run beside it.  Returns the previous value. */
+int ws3d_set_sm_budget(int sms);
 
 /* ---- pointnet2_cuda -------------------------------------------------------- */
 
@@ -174,6 +183,28 @@ int ws3d_nms_host(const float *boxes, int boxes_num, float nms_overlap_thresh,
                   int64_t *keep_host, ws3d_stream_t stream);
 int ws3d_nms_normal_host(const float *boxes, int boxes_num, float nms_overlap_thresh,
                          int64_t *keep_host, ws3d_stream_t stream);
+
+/* Extension: the DIAGONAL of boxes_iou3d_gpu
+ * (lib/utils/iou3d/iou3d_utils.py:21-56) for n aligned pairs -- all that the Stage-2 losses keep of
+ * their fg x fg matrices (lib/net/train_functions.py:258-260, :287-289).  boxes_a, boxes_b (n,7)
+ * [x,y,z,h,w,l,ry]; iou2d, iou3d (n) (either may be NULL).  BEV conversion (kitti_utils.py:134-147),
+ * rotated overlap and the height / volume arithmetic in one launch; bit-identical to the diagonal. */
+int ws3d_boxes_iou3d_aligned(int n, const float *boxes_a, const float *boxes_b, float *iou2d,
+                             float *iou3d, ws3d_stream_t stream);
+
+/* Extension (row f3): greedy "radius NMS" of tools/eval_auto.py:263-279.  centers (n,2) BEV (x,z)
+ * ALREADY sorted by descending score; candidate i is kept iff its distance (lib/utils/distance.py:3,
+ * float32) to every centre kept before it is > radius.  keep (n) int64 device indices into the sorted
+ * order, num_keep (1) int32 device.  workspace: ws3d_nms_workspace_bytes(n) bytes or NULL. */
+int ws3d_radius_nms(const float *centers, int n, float radius, int64_t *keep, int *num_keep,
+                    void *workspace, ws3d_stream_t stream);
+
+/* Extension (row f3): cylinder crop of tools/eval_auto.py:289-291,:327-343.  pts (n,3), centers (m,2)
+ * BEV (x,z).  Point i belongs to centre c iff distance_2(centre, (x_i,z_i)) < radius.  idx (m,cap)
+ * gets the first `cap` members of every centre in index order (other slots untouched), cnt (m) the
+ * full member count, any (n) bytes (caller-zeroed; may be NULL) is set to 1 for members of any centre. */
+int ws3d_cylinder_query(int n, int m, int cap, float radius, const float *pts, const float *centers,
+                        int *idx, int *cnt, unsigned char *any, ws3d_stream_t stream);
 
 /* ---- roipool3d_cuda -------------------------------------------------------- */
 

@@ -213,3 +213,33 @@ def roipool3d_cpu(pts, boxes3d, pts_feature, sampled_pt_num):
     lib().oracle_roipool3d_cpu(_p(pts), _p(boxes3d), _p(pts_feature), _p(pooled_pts), _p(pooled_feat),
                                _p(flag), m, pts.shape[0], c, int(sampled_pt_num))
     return pooled_pts, pooled_feat, flag
+
+
+# ---- SURVEY.md section 8 "next" rows f2 / f3 ---------------------------------------------------
+def boxes_iou3d_aligned(boxes_a, boxes_b):
+    """Diagonal of boxes_iou3d_gpu (iou3d_utils.py:21-56): (n,7),(n,7) -> iou2d (n), iou3d (n)."""
+    a, b = _f(boxes_a), _f(boxes_b)
+    assert a.shape == b.shape and a.shape[1] == 7
+    i2, i3 = np.zeros(a.shape[0], dtype=np.float32), np.zeros(a.shape[0], dtype=np.float32)
+    lib().oracle_boxes_iou3d_aligned(a.shape[0], _p(a), _p(b), _p(i2), _p(i3))
+    return i2, i3
+
+
+def radius_nms(centers_sorted, radius):
+    """tools/eval_auto.py:263-279: centres (n,2) sorted by descending score -> int64 keep indices."""
+    c = _f(centers_sorted)
+    keep = np.zeros(c.shape[0], dtype=np.int64)
+    lib().oracle_radius_nms.restype = ctypes.c_int
+    n = lib().oracle_radius_nms(_p(c), c.shape[0], ctypes.c_float(radius), _p(keep))
+    return keep[:n]
+
+
+def cylinder_query(pts, centers, radius, cap):
+    """tools/eval_auto.py:289-291,:327-343: pts (n,3), centres (m,2) -> idx (m,cap) (-1 padded), cnt (m), any (n)."""
+    p, c = _f(pts), _f(centers)
+    idx = np.full((c.shape[0], cap), -1, dtype=np.int32)
+    cnt = np.zeros(c.shape[0], dtype=np.int32)
+    any_ = np.zeros(p.shape[0], dtype=np.uint8)
+    lib().oracle_cylinder_query(p.shape[0], c.shape[0], int(cap), ctypes.c_float(radius), _p(p), _p(c), _p(idx), _p(cnt),
+                                _p(any_))
+    return idx, cnt, any_

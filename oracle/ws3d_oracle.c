@@ -588,3 +588,97 @@ ORACLE_API void oracle_roipool3d_cpu(const float *pts, const float *boxes3d,
     }
   }
 }
+
+/* ------------------------------------------------------------------------ */
+/* SURVEY.md section 8 "next" rows f2 / f3 (host-side PyTorch code in the      */
+/* reference; restated with one IEEE operation per torch elementwise kernel).  */
+
+/* lib/utils/kitti_utils.py:134-147 boxes3d_to_bev_torch: [x,y,z,h,w,l,ry] -> [x1,y1,x2,y2,ry];
+ * half extents are l/2, w/2 (exact), the corners one rounded add / subtract each. */
+static void box3d_to_bev(const float *b, float *o) {
+  const float half_l = b[5] / 2.0f, half_w = b[4] / 2.0f;
+  o[0] = b[0] - half_l; o[1] = b[2] - half_w;
+  o[2] = b[0] + half_l; o[3] = b[2] + half_w;
+  o[4] = b[6];
+}
+
+static inline float clamp_min(float v, float lo) { return v < lo ? lo : v; } /* torch.clamp(min=): NaN stays NaN */
+
+/* The DIAGONAL of lib/utils/iou3d/iou3d_utils.py:21-56 boxes_iou3d_gpu(a, b): what the live Stage-2 training
+ * keeps of the fg x fg matrix (lib/net/train_functions.py:258-260, :287-289).  boxes (n,7) each. */
+ORACLE_API void oracle_boxes_iou3d_aligned(int n, const float *boxes_a, const float *boxes_b, float *iou2d,
+                                           float *iou3d) {
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int i = 0; i < n; ++i) {
+    const float *a = boxes_a + (size_t)i * 7, *b = boxes_b + (size_t)i * 7;
+    float abev[5], bbev[5];
+    box3d_to_bev(a, abev);
+    box3d_to_bev(b, bbev);
+    const float ov = box_overlap(abev, bbev);                       /* :31-32 */
+    const float a_hmin = a[1] - a[3], b_hmin = b[1] - b[3];         /* :35-38 */
+    const float max_of_min = a_hmin > b_hmin ? a_hmin : b_hmin;     /* :40 */
+    const float min_of_max = a[1] < b[1] ? a[1] : b[1];             /* :41 */
+    const float ov_h = clamp_min(min_of_max - max_of_min, 0.0f);    /* :42 */
+    const float s_a = a[4] * a[5], s_b = b[4] * b[5];               /* :44-45 */
+    const float ssum = s_a + s_b;
+    iou2d[i] = ov / clamp_min(ssum - ov, 1e-7f);                    /* :46 */
+    const float ov3 = ov * ov_h;                                    /* :48 */
+    const float ha = a[3] * a[4], hb = b[3] * b[4];
+    const float vol_a = ha * a[5], vol_b = hb * b[5];               /* :50-51 */
+    const float vsum = vol_a + vol_b;
+    iou3d[i] = ov3 / clamp_min(vsum - ov3, 1e-7f);                  /* :53 */
+  }
+}
+
+/* lib/utils/distance.py:3 distance_2 on (x, z) pairs: sqrt(sum((a - b) ** 2)) in float32, one rounding per
+ * torch kernel (subtract, square, two-term sum, sqrt). */
+static inline float bev_dist(float ax, float az, float bx, float bz) {
+  const float dx = ax - bx, dz = az - bz;
+  const float sx = dx * dx, sz = dz * dz;
+  return sqrtf(sx + sz);
+}
+
+/* tools/eval_auto.py:263-279 "radius NMS": centres already sorted by descending score; candidate i is kept when
+ * its distance to every centre kept so far is > radius (min(...) > 0.3 in the script; a NaN distance fails the
+ * comparison, so the candidate is dropped).  The first candidate is always kept.  Returns the number kept. */
+ORACLE_API int oracle_radius_nms(const float *centers, int n, float radius, int64_t *keep) {
+  int num = 0;
+  for (int i = 0; i < n; ++i) {
+    int ok = 1;
+    if (i > 0) {
+      float mn = INFINITY;
+      int nan = 0;
+      for (int k = 0; k < num; ++k) {
+        const int j = (int)keep[k];
+        /* prop_prop_distance[keep_id, i] = distance_2(rois, rois)[j, i] = |rois[i] - rois[j]| */
+        const float d = bev_dist(centers[2 * i], centers[2 * i + 1], centers[2 * j], centers[2 * j + 1]);
+        if (d != d) nan = 1;
+        if (d < mn) mn = d;
+      }
+      ok = !nan && (mn > radius);   /* torch.min propagates NaN; NaN > r is False */
+    }
+    if (ok) keep[num++] = i;
+  }
+  return num;
+}
+
+/* tools/eval_auto.py:289-291 and :327-343: point_center_distance = distance_2(rpn_center, inputs[:, [0, 2]]),
+ * a point belongs to proposal c when that distance is < radius (4.0 in the script); the per-proposal crops keep
+ * the points in index order.  idx (m, cap) receives the first `cap` members of every proposal (rest untouched),
+ * cnt (m) the full member count, any (n) = 1 where the point is in at least one cylinder (:291). */
+ORACLE_API void oracle_cylinder_query(int n, int m, int cap, float radius, const float *pts, const float *centers,
+                                      int *idx, int *cnt, unsigned char *any) {
+  for (int i = 0; i < n; ++i) any[i] = 0;
+  for (int c = 0; c < m; ++c) {
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+      const float d = bev_dist(centers[2 * c], centers[2 * c + 1], pts[3 * i], pts[3 * i + 2]);
+      if (d < radius) {
+        if (k < cap) idx[(size_t)c * cap + k] = i;
+        ++k;
+        any[i] = 1;
+      }
+    }
+    cnt[c] = k;
+  }
+}

@@ -123,3 +123,36 @@ def test_cuda_graph_replay_equals_eager_two_stream_forward():
     assert torch.equal(runner(a), want_a)
     assert torch.equal(runner(b), want_b)
     assert torch.equal(runner(a), want_a)
+
+
+def test_pipelined_runner_equals_unpipelined_forward():
+    """graphs.PipelinedBackboneRunner (level-1 FPS of batch i+1 beside the rest of batch i, two alternating CUDA
+    graphs) returns, for every batch of a stream of batches, exactly what the plain forward returns."""
+    from ws3d_b200 import models, synth
+    from ws3d_b200.graphs import PipelinedBackboneRunner
+    torch.manual_seed(0)
+    cfg = {"NPOINTS": [512, 128, 32, 8], "RADIUS": models.RPN_SA_CONFIG["RADIUS"], "NSAMPLE": models.RPN_SA_CONFIG["NSAMPLE"],
+           "MLPS": [[[8, 8, 16], [8, 8, 16]], [[16, 16, 32], [16, 24, 32]], [[32, 32, 64], [32, 48, 64]], [[64, 64, 96], [64, 64, 96]]]}
+    fp = [[32, 32], [48, 48], [64, 64], [64, 64]]
+    model = models.Pointnet2MSG(input_channels=1, sa_config=cfg, fp_mlps=fp).to(dev).eval()
+    _randomize_bn(model, 2)
+    batches = [torch.from_numpy(synth.make_batch(2, 2048, first_scene=10 * k)) for k in range(5)]
+    with torch.no_grad():
+        want = [model(b.to(dev))[1].clone() for b in batches]
+    runner = PipelinedBackboneRunner(model, batches[0].to(dev))
+    pinned = [b.pin_memory() for b in batches]
+    runner.prefetch(pinned[0])                       # host batches: H2D on the runner's copy stream
+    got = []
+    for k in range(len(batches)):
+        out = runner.step(pinned[k + 1] if k + 1 < len(batches) else None)
+        got.append(out.clone())
+    torch.cuda.synchronize()
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert torch.equal(g, w), f"batch {k} differs"
+    # a second pass over device-resident batches through stage_next(), issued while the previous step is in flight
+    runner.prefetch(batches[4].to(dev))
+    runner.stage_next(batches[3].to(dev))
+    a = runner.step().clone()
+    b = runner.step().clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, want[4]) and torch.equal(b, want[3])

@@ -56,3 +56,22 @@ def test_roipool3d_golden():
     pooled, flag = oracle.roipool3d(g["xyz"], g["feat"], g["boxes"], g["pooled"].shape[2])
     np.testing.assert_array_equal(flag, g["flag"])
     np.testing.assert_array_equal(pooled, g["pooled"])
+
+
+def test_next_rows_f2_f3_match_reference_python():
+    """the oracle restatements against vectors produced by executing the reference's
+    own Python (tools/make_golden_next.py: boxes_iou3d_gpu diagonal, distance_2-driven radius NMS + cylinder crop)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "next_rows.npz"))
+    i2, i3 = oracle.boxes_iou3d_aligned(g["f2_boxes_a"], g["f2_boxes_b"])
+    np.testing.assert_array_equal(i2, g["f2_iou2d_diag"])
+    np.testing.assert_array_equal(i3, g["f2_iou3d_diag"])
+    assert (g["f2_iou3d_diag"][:40] > 0.999).all() and (g["f2_iou3d_diag"][40:100] == 0).all()
+    centres_sorted = g["f3_centres"][g["f3_sort"]]
+    keep = oracle.radius_nms(centres_sorted, 0.3)
+    np.testing.assert_array_equal(keep, g["f3_keep_id"])
+    assert 1 < len(keep) < len(centres_sorted)
+    idx, cnt, any_ = oracle.cylinder_query(g["f3_points"], centres_sorted[keep], 4.0, g["f3_idx"].shape[1])
+    np.testing.assert_array_equal(cnt, g["f3_cnt"])
+    np.testing.assert_array_equal(idx, g["f3_idx"])
+    np.testing.assert_array_equal(any_, g["f3_any"])

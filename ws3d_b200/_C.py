@@ -20,6 +20,8 @@ _SIGNATURES = {
     "ws3d_abi_version": [],
     "ws3d_last_error": [],
     "ws3d_launch_count": [],
+    "ws3d_set_workspace_arena": [_i],
+    "ws3d_set_sm_budget": [_i],
     "ws3d_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_furthest_point_sampling_gather": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -41,6 +43,9 @@ _SIGNATURES = {
     "ws3d_nms_normal": [_vp, _i, _f, _vp, _vp, _vp, _vp],
     "ws3d_nms_host": [_vp, _i, _f, _vp, _vp],
     "ws3d_nms_normal_host": [_vp, _i, _f, _vp, _vp],
+    "ws3d_boxes_iou3d_aligned": [_i, _vp, _vp, _vp, _vp, _vp],
+    "ws3d_radius_nms": [_vp, _i, _f, _vp, _vp, _vp, _vp],
+    "ws3d_cylinder_query": [_i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_roipool3d": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_pts_in_boxes3d_cpu": [_vp, _vp, _vp, _i, _i],
     "ws3d_roipool3d_cpu": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],

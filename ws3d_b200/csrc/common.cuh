@@ -18,6 +18,8 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 // cached per-device scratch (grown on demand, never shrunk); nullptr + error on failure
 void *scratch(size_t bytes, int slot);
+// grid size of a persistent kernel with `per_sm` CTAs per SM, honouring ws3d_set_sm_budget()
+int persistent_ctas(int per_sm);
 
 inline cudaStream_t to_stream(ws3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -233,7 +233,16 @@ __global__ void __launch_bounds__(256) pair_matrix_kernel(int num_a, const float
 
 // ---------------------------------------------------------------------------------------------
 // NMS mask: upper-triangle 64x64 tiles only; 64 threads per tile, thread = row box.
-template <bool ROTATED>
+// BEV centre distance exactly as lib/utils/distance.py:3 evaluates it in float32 torch kernels
+// (subtract, square, two-term sum, sqrt: one rounding each).
+__device__ __forceinline__ float bev_dist(float ax, float az, float bx, float bz) {
+  const float dx = __fsub_rn(ax, bx), dz = __fsub_rn(az, bz);
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz)));
+}
+
+constexpr int kModeNormal = 0, kModeRotated = 1, kModeRadius = 2;
+
+template <int MODE>
 __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
                                                       unsigned long long *__restrict__ mask) {
   const int col_blocks = ceil_div(n, 64);
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const
     const int cbk = rb + (int)t;
     const int row_size = min(64, n - rb * 64), col_size = min(64, n - cbk * 64);
     const int tid = threadIdx.x;
-    if (ROTATED) {
+    if (MODE == kModeRotated) {
       __shared__ BoxPre scol[64], srow[64];
       __shared__ unsigned short s_queue[64 * 64];
       __shared__ unsigned int s_bits[64][2];
@@ -287,6 +296,20 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const
       if (tid < row_size)
         mask[(size_t)(rb * 64 + tid) * col_blocks + cbk] =
             (unsigned long long)s_bits[tid][0] | ((unsigned long long)s_bits[tid][1] << 32);
+    } else if (MODE == kModeRadius) {
+      // "radius NMS" of tools/eval_auto.py:272-279: `boxes` = (n, 2) BEV centres, thresh = radius; a kept centre
+      // suppresses every later one that is NOT farther than the radius (a NaN distance suppresses, as there)
+      __shared__ float2 scol[64];
+      if (tid < col_size) scol[tid] = reinterpret_cast<const float2 *>(boxes)[cbk * 64 + tid];
+      __syncthreads();
+      if (tid < row_size) {
+        const float2 me = reinterpret_cast<const float2 *>(boxes)[rb * 64 + tid];
+        unsigned long long bits = 0;
+        const int start = (rb == cbk) ? tid + 1 : 0;
+        for (int j = start; j < col_size; ++j)
+          if (!(bev_dist(scol[j].x, scol[j].y, me.x, me.y) > thresh)) bits |= 1ULL << j;
+        mask[(size_t)(rb * 64 + tid) * col_blocks + cbk] = bits;
+      }
     } else {
       __shared__ float scol[64 * 5];
       if (tid < col_size)
@@ -361,6 +384,45 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, const uns
   if (threadIdx.x == 0) *num_keep = s_total;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Aligned pairs: the DIAGONAL of boxes_iou3d_gpu (lib/utils/iou3d/iou3d_utils.py:21-56),
+// which is all that the Stage-2 losses keep of their fg x fg matrices (lib/net/train_functions.py:258-260,:287-289).
+// One thread per pair: BEV conversion (kitti_utils.py:134-147), the exact rotated overlap above, then the height /
+// area / volume arithmetic of :35-53 with one IEEE operation per torch elementwise kernel.
+__device__ __forceinline__ float clamp_min(float v, float lo) { return v < lo ? lo : v; }  // torch.clamp(min=): NaN stays NaN
+
+__device__ __forceinline__ void box3d_to_bev(const float *__restrict__ b, float *o) {
+  const float half_l = __fmul_rn(b[5], 0.5f), half_w = __fmul_rn(b[4], 0.5f);   // x / 2 is exact
+  o[0] = __fsub_rn(b[0], half_l); o[1] = __fsub_rn(b[2], half_w);
+  o[2] = __fadd_rn(b[0], half_l); o[3] = __fadd_rn(b[2], half_w);
+  o[4] = b[6];
+}
+
+__global__ void __launch_bounds__(128) iou3d_aligned_kernel(int n, const float *__restrict__ boxes_a,
+                                                             const float *__restrict__ boxes_b, float *__restrict__ iou2d,
+                                                             float *__restrict__ iou3d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a[7], b[7], abev[5], bbev[5];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) { a[q] = boxes_a[(size_t)i * 7 + q]; b[q] = boxes_b[(size_t)i * 7 + q]; }
+  box3d_to_bev(a, abev);
+  box3d_to_bev(b, bbev);
+  BoxPre pa, pb;
+  precompute(abev, pa);
+  precompute(bbev, pb);
+  const float ov = overlap_pair(pa, pb);
+  const float a_hmin = __fsub_rn(a[1], a[3]), b_hmin = __fsub_rn(b[1], b[3]);
+  const float max_of_min = (a_hmin != a_hmin || b_hmin != b_hmin) ? __fadd_rn(a_hmin, b_hmin) : fmaxf(a_hmin, b_hmin);
+  const float min_of_max = (a[1] != a[1] || b[1] != b[1]) ? __fadd_rn(a[1], b[1]) : fminf(a[1], b[1]);  // torch.max/min propagate NaN
+  const float ov_h = clamp_min(__fsub_rn(min_of_max, max_of_min), 0.f);
+  const float s_a = __fmul_rn(a[4], a[5]), s_b = __fmul_rn(b[4], b[5]);
+  if (iou2d) iou2d[i] = __fdiv_rn(ov, clamp_min(__fsub_rn(__fadd_rn(s_a, s_b), ov), 1e-7f));
+  const float ov3 = __fmul_rn(ov, ov_h);
+  const float vol_a = __fmul_rn(__fmul_rn(a[3], a[4]), a[5]), vol_b = __fmul_rn(__fmul_rn(b[3], b[4]), b[5]);
+  if (iou3d) iou3d[i] = __fdiv_rn(ov3, clamp_min(__fsub_rn(__fadd_rn(vol_a, vol_b), ov3), 1e-7f));
+}
+
 int matrix_dispatch(bool iou, int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *ans,
                     cudaStream_t stream) {
   const char *what = iou ? "boxes_iou_bev" : "boxes_overlap_bev";
@@ -379,9 +441,9 @@ size_t nms_ws_bytes(int n) {
   return (size_t)n * cb * 8 + cb * 8 + 256;
 }
 
-int nms_dispatch(bool rotated, const float *boxes, int n, float thresh, int64_t *keep, int *num_keep, void *workspace,
+int nms_dispatch(int mode, const float *boxes, int n, float thresh, int64_t *keep, int *num_keep, void *workspace,
                  cudaStream_t stream) {
-  const char *what = rotated ? "nms" : "nms_normal";
+  const char *what = mode == kModeRotated ? "nms" : mode == kModeRadius ? "radius_nms" : "nms_normal";
   if (n < 0) return fail_arg(what);
   if (!num_keep) return fail_arg(what);
   if (n == 0) {
@@ -397,8 +459,9 @@ int nms_dispatch(bool rotated, const float *boxes, int n, float thresh, int64_t 
   unsigned long long *remv_g = mask + (size_t)n * cb;
   const long long tiles = (long long)cb * (cb + 1) / 2;
   if (tiles > 2147483647LL) return fail_arg(what);
-  if (rotated) nms_mask_kernel<true><<<(unsigned)tiles, 64, 0, stream>>>(n, thresh, boxes, mask);
-  else nms_mask_kernel<false><<<(unsigned)tiles, 64, 0, stream>>>(n, thresh, boxes, mask);
+  if (mode == kModeRotated) nms_mask_kernel<kModeRotated><<<(unsigned)tiles, 64, 0, stream>>>(n, thresh, boxes, mask);
+  else if (mode == kModeRadius) nms_mask_kernel<kModeRadius><<<(unsigned)tiles, 64, 0, stream>>>(n, thresh, boxes, mask);
+  else nms_mask_kernel<kModeNormal><<<(unsigned)tiles, 64, 0, stream>>>(n, thresh, boxes, mask);
   int rc = check_launch(what);
   if (rc) return rc;
   const size_t smem = (size_t)cb * 8;
@@ -416,7 +479,7 @@ int nms_host(bool rotated, const float *boxes, int n, float thresh, int64_t *kee
   if (!dev) return -(int)cudaErrorMemoryAllocation;
   int64_t *keep_dev = reinterpret_cast<int64_t *>(dev + 64);
   int *num_dev = reinterpret_cast<int *>(dev);
-  int rc = nms_dispatch(rotated, boxes, n, thresh, keep_dev, num_dev, nullptr, stream);
+  int rc = nms_dispatch(rotated ? kModeRotated : kModeNormal, boxes, n, thresh, keep_dev, num_dev, nullptr, stream);
   if (rc) return -rc;
   int num = 0;
   cudaError_t e = cudaMemcpyAsync(&num, num_dev, sizeof(int), cudaMemcpyDeviceToHost, stream);
@@ -445,11 +508,11 @@ WS3D_API int ws3d_boxes_iou_bev(int num_a, const float *boxes_a, int num_b, cons
 WS3D_API size_t ws3d_nms_workspace_bytes(int boxes_num) { return boxes_num > 0 ? nms_ws_bytes(boxes_num) : 0; }
 WS3D_API int ws3d_nms(const float *boxes, int boxes_num, float thresh, int64_t *keep, int *num_keep, void *workspace,
                       ws3d_stream_t stream) {
-  return nms_dispatch(true, boxes, boxes_num, thresh, keep, num_keep, workspace, to_stream(stream));
+  return nms_dispatch(kModeRotated, boxes, boxes_num, thresh, keep, num_keep, workspace, to_stream(stream));
 }
 WS3D_API int ws3d_nms_normal(const float *boxes, int boxes_num, float thresh, int64_t *keep, int *num_keep,
                              void *workspace, ws3d_stream_t stream) {
-  return nms_dispatch(false, boxes, boxes_num, thresh, keep, num_keep, workspace, to_stream(stream));
+  return nms_dispatch(kModeNormal, boxes, boxes_num, thresh, keep, num_keep, workspace, to_stream(stream));
 }
 WS3D_API int ws3d_nms_host(const float *boxes, int boxes_num, float thresh, int64_t *keep_host, ws3d_stream_t stream) {
   return nms_host(true, boxes, boxes_num, thresh, keep_host, to_stream(stream));
@@ -457,4 +520,18 @@ WS3D_API int ws3d_nms_host(const float *boxes, int boxes_num, float thresh, int6
 WS3D_API int ws3d_nms_normal_host(const float *boxes, int boxes_num, float thresh, int64_t *keep_host,
                                   ws3d_stream_t stream) {
   return nms_host(false, boxes, boxes_num, thresh, keep_host, to_stream(stream));
+}
+
+WS3D_API int ws3d_boxes_iou3d_aligned(int n, const float *boxes_a, const float *boxes_b, float *iou2d, float *iou3d,
+                                      ws3d_stream_t stream) {
+  const char *what = "boxes_iou3d_aligned";
+  if (n < 0) return fail_arg(what);
+  if (n == 0) return 0;
+  if (!boxes_a || !boxes_b || (!iou2d && !iou3d)) return fail_arg(what);
+  iou3d_aligned_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, to_stream(stream)>>>(n, boxes_a, boxes_b, iou2d, iou3d);
+  return check_launch(what);
+}
+WS3D_API int ws3d_radius_nms(const float *centers, int n, float radius, int64_t *keep, int *num_keep, void *workspace,
+                             ws3d_stream_t stream) {
+  return nms_dispatch(kModeRadius, centers, n, radius, keep, num_keep, workspace, to_stream(stream));
 }

@@ -422,7 +422,8 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
     const long long tiles = (long long)prm.n_col_tiles * prm.n_m_tiles * b;                                         \
     if (tiles > 0x7FFFFFFFLL) return fail_arg("mlp_layer (too many tiles)");                                        \
     prm.n_tiles = (int)tiles;                                                                                       \
-    const int ctas = (int)(tiles < (long long)kNumSMs * (MB_) ? tiles : (long long)kNumSMs * (MB_));                \
+    const int pc = persistent_ctas(MB_);                                                                            \
+    const int ctas = (int)(tiles < (long long)pc ? tiles : (long long)pc);                                                          \
     kern<<<ctas, kThreads, smem, to_stream(stream)>>>(mw, m1, m2, prm);                                             \
   }
   switch (cfg) {

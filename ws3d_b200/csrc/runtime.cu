@@ -21,11 +21,20 @@ void set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 namespace {
-constexpr int kMaxDev = 16, kSlots = 8;
+constexpr int kMaxDev = 16, kSlots = 8, kArenas = 8;
 struct Slot { void *p = nullptr; size_t cap = 0; };
-Slot g_slots[kMaxDev][kSlots];
+Slot g_slots[kMaxDev][kArenas][kSlots];
 std::mutex g_mu;
+// Which set of cached scratch buffers the calling thread's launches use.  Two forward passes that are in
+// flight at the same time (two CUDA graphs replayed on different streams) must not share cell grids.
+thread_local int g_arena = 0;
+std::atomic<int> g_sm_budget{0};
 }  // namespace
+
+int persistent_ctas(int per_sm) {
+  const int b = g_sm_budget.load(std::memory_order_relaxed);
+  return (b > 0 && b < kNumSMs ? b : kNumSMs) * per_sm;
+}
 
 void *scratch(size_t bytes, int slot) {
   int dev = 0;
@@ -34,7 +43,7 @@ void *scratch(size_t bytes, int slot) {
     return nullptr;
   }
   std::lock_guard<std::mutex> lk(g_mu);
-  Slot &s = g_slots[dev][slot];
+  Slot &s = g_slots[dev][g_arena][slot];
   if (s.cap < bytes) {
     if (s.p) {
       cudaDeviceSynchronize();  // earlier work may still be using the old buffer
@@ -59,3 +68,10 @@ void *scratch(size_t bytes, int slot) {
 WS3D_API int ws3d_abi_version(void) { return WS3D_ABI_VERSION; }
 WS3D_API const char *ws3d_last_error(void) { return ws3d::g_err; }
 WS3D_API uint64_t ws3d_launch_count(void) { return ws3d::g_launches.load(); }
+
+WS3D_API int ws3d_set_workspace_arena(int arena) {
+  const int prev = ws3d::g_arena;
+  if (arena >= 0 && arena < ws3d::kArenas) ws3d::g_arena = arena;
+  return prev;
+}
+WS3D_API int ws3d_set_sm_budget(int sms) { return ws3d::g_sm_budget.exchange(sms < 0 ? 0 : sms); }

@@ -34,6 +34,17 @@ def boxes_iou3d_gpu(boxes_a: torch.Tensor, boxes_b: torch.Tensor):
     return iou2d, iou3d
 
 
+def boxes_iou3d_aligned(boxes_a: torch.Tensor, boxes_b: torch.Tensor):
+    """(n,7), (n,7) -> (iou2d (n), iou3d (n)) of box i of `a` with box i of `b`: the diagonal of boxes_iou3d_gpu in one
+    launch and O(n) work.  Drop-in for the `torch.gather(iou3d, 1, eye)` idiom of lib/net/train_functions.py:258-260
+    and :287-289, which builds the whole fg x fg matrix (twice per step) to keep n numbers; bit-identical to it."""
+    a, b = boxes_a.contiguous().float(), boxes_b.contiguous().float()
+    iou2d = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+    iou3d = torch.empty_like(iou2d)
+    native.boxes_iou3d_aligned(a, b, iou2d, iou3d)
+    return iou2d, iou3d
+
+
 def _nms(boxes, scores, thresh, rotated):
     order = scores.sort(0, descending=True)[1]
     sorted_boxes = boxes[order].contiguous()

@@ -8,6 +8,7 @@ tools/cfgs/weaklyRPN.yaml:43-56 (= lib/config.py:57-70), restated here as RPN_SA
 """
 import copy
 import os
+from typing import Optional
 
 import numpy as np
 import torch
@@ -65,7 +66,15 @@ class Pointnet2MSG(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
-    def _forward_two_streams(self, xyz, features):
+    def sample_first_level(self, pointcloud: torch.Tensor) -> torch.Tensor:
+        """Level-1 sampling alone: (B,N,3+C) -> new_xyz (B, npoint_1, 3).  It depends on coordinates only and is the
+        head of every dependency chain of the forward pass, so a caller that knows the NEXT batch can compute it
+        while the current batch is still in its grouping / MLP layers (graphs.PipelinedBackboneRunner) and hand it
+        to forward(..., first_samples=)."""
+        xyz = pointcloud[..., 0:3].contiguous()
+        return pointnet2_utils.sample_and_gather(xyz, self.SA_modules[0].npoint)[1]
+
+    def _forward_two_streams(self, xyz, features, first_samples=None):
         """Same computation as forward(), scheduled on two CUDA streams.
 
         Sampling (FPS) and the interpolation stencils (three_nn + weights) depend on coordinates only, and FPS is a
@@ -76,14 +85,18 @@ class Pointnet2MSG(nn.Module):
         main = torch.cuda.current_stream(xyz.device)
         side = self.__dict__.get("_side_stream")
         if side is None or side.device != xyz.device:
-            side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=xyz.device)
+            # high priority: the sampling chain is latency-bound and narrow; it must not queue behind wide kernels
+            side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=xyz.device, priority=-1)
         start = torch.cuda.Event()
         start.record(main)
         l_xyz, fps_done, stencil, stencil_done = [xyz], [], {}, {}
         with torch.cuda.stream(side):
             side.wait_event(start)
-            for sa in self.SA_modules:
-                _, nx = pointnet2_utils.sample_and_gather(l_xyz[-1], sa.npoint)
+            for k, sa in enumerate(self.SA_modules):
+                if k == 0 and first_samples is not None:
+                    nx = first_samples
+                else:
+                    _, nx = pointnet2_utils.sample_and_gather(l_xyz[-1], sa.npoint)
                 nx.record_stream(main)
                 l_xyz.append(nx)
                 ev = torch.cuda.Event()
@@ -108,15 +121,16 @@ class Pointnet2MSG(nn.Module):
         xyz.record_stream(side)
         return l_xyz[0], l_features[0]
 
-    def forward(self, pointcloud: torch.Tensor):
-        """pointcloud (B,N,3+C) -> (xyz (B,N,3), per-point features (B,128,N))."""
+    def forward(self, pointcloud: torch.Tensor, first_samples: Optional[torch.Tensor] = None):
+        """pointcloud (B,N,3+C) -> (xyz (B,N,3), per-point features (B,128,N)).
+        `first_samples`: level-1 FPS output for this batch if the caller already has it (sample_first_level)."""
         xyz, features = self._break_up_pc(pointcloud)
         if (xyz.is_cuda and os.environ.get("WS3D_TWO_STREAMS", "1") != "0" and len(self.FP_modules) == len(self.SA_modules)
                 and all(sa.npoint is not None for sa in self.SA_modules)):
-            return self._forward_two_streams(xyz, features)
+            return self._forward_two_streams(xyz, features, first_samples)
         l_xyz, l_features = [xyz], [features]
-        for sa in self.SA_modules:
-            nx, nf = sa(l_xyz[-1], l_features[-1])
+        for k, sa in enumerate(self.SA_modules):
+            nx, nf = sa(l_xyz[-1], l_features[-1], new_xyz=first_samples if k == 0 else None)
             l_xyz.append(nx)
             l_features.append(nf)
         for i in range(-1, -(len(self.FP_modules) + 1), -1):
@@ -161,9 +175,9 @@ class RPN(nn.Module):
             return cache[name](x)
         return seq(x)
 
-    def forward(self, input_data):
+    def forward(self, input_data, first_samples: Optional[torch.Tensor] = None):
         pts_input = input_data['pts_input'] if isinstance(input_data, dict) else input_data
-        backbone_xyz, backbone_features = self.backbone_net(pts_input)
+        backbone_xyz, backbone_features = self.backbone_net(pts_input, first_samples=first_samples)
         rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
         rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()
         return {'rpn_cls': rpn_cls, 'rpn_reg': rpn_reg, 'backbone_xyz': backbone_xyz,

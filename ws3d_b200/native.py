@@ -126,6 +126,8 @@ def mlp_layer(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, po
 # ---- iou3d_cuda -------------------------------------------------------------------------------
 def _check_boxes(*ts):
     for t in ts:
+        if t is None:
+            continue
         if not t.is_cuda:
             raise RuntimeError("boxes must be a CUDAtensor ")
         if not t.is_contiguous():
@@ -180,6 +182,40 @@ def nms_device(boxes, thresh, rotated=True):
     return keep, num
 
 
+def boxes_iou3d_aligned(boxes_a, boxes_b, iou2d, iou3d):
+    """Extension: diagonal of boxes_iou3d_gpu for aligned (n,7) box pairs; outputs (n) each."""
+    _check_boxes(boxes_a, boxes_b, iou2d, iou3d)
+    if boxes_a.shape != boxes_b.shape or boxes_a.dim() != 2 or boxes_a.size(1) != 7:
+        raise RuntimeError("boxes_iou3d_aligned: boxes must both be (n, 7)")
+    with device_of(boxes_a):
+        check(lib().ws3d_boxes_iou3d_aligned(boxes_a.size(0), ptr(boxes_a), ptr(boxes_b), ptr(iou2d), ptr(iou3d), stream()),
+              "boxes_iou3d_aligned")
+
+
+def radius_nms_device(centers, radius):
+    """Extension: greedy radius NMS over (n,2) BEV centres sorted by descending score.
+    Returns (keep int64 CUDA (n), num_keep int32 CUDA (1)); no sync."""
+    _check_boxes(centers)
+    if centers.dim() != 2 or centers.size(1) != 2:
+        raise RuntimeError("radius_nms: centers must be (n, 2)")
+    n = centers.size(0)
+    keep = torch.empty(n, dtype=torch.int64, device=centers.device)
+    num = torch.zeros(1, dtype=torch.int32, device=centers.device)
+    with device_of(centers):
+        check(lib().ws3d_radius_nms(ptr(centers), n, float(radius), ptr(keep), ptr(num), None, stream()), "radius_nms")
+    return keep, num
+
+
+def cylinder_query(pts, centers, radius, idx, cnt, any_flag=None):
+    """Extension: pts (n,3), centers (m,2) -> idx (m,cap) int32, cnt (m) int32, any_flag (n) uint8."""
+    _check_boxes(pts, centers, idx, cnt, any_flag)
+    if pts.dim() != 2 or pts.size(1) != 3 or centers.dim() != 2 or centers.size(1) != 2:
+        raise RuntimeError("cylinder_query: pts must be (n, 3) and centers (m, 2)")
+    with device_of(pts):
+        check(lib().ws3d_cylinder_query(pts.size(0), centers.size(0), idx.size(1), float(radius), ptr(pts), ptr(centers),
+                                        ptr(idx), ptr(cnt), ptr(any_flag), stream()), "cylinder_query")
+
+
 # ---- roipool3d_cuda ---------------------------------------------------------------------------
 def roipool3d_forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
     """Reference `forward` (roipool3d.cpp:48): xyz (B,N,3), boxes3d (B,M,7), pts_feature (B,N,C),
@@ -209,3 +245,13 @@ def roipool3d_cpu(pts, boxes3d, pts_feature, pooled_pts, pooled_features, pooled
                                    ptr(pooled_empty_flag), boxes3d.size(0), pts.size(0), pts_feature.size(1),
                                    pooled_pts.size(1)), "roipool3d_cpu")
     return 1
+
+
+def set_workspace_arena(arena: int) -> int:
+    """Scratch arena (0..7) for this thread's subsequent launches; returns the previous one (ws3d_ops.h)."""
+    return int(lib().ws3d_set_workspace_arena(int(arena)))
+
+
+def set_sm_budget(sms: int) -> int:
+    """Upper bound on the SMs a persistent kernel (mlp_layer) spreads over; 0 = all.  Returns the previous value."""
+    return int(lib().ws3d_set_sm_budget(int(sms)))
