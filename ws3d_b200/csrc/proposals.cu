@@ -20,32 +20,49 @@ __device__ __forceinline__ float bev_dist(float ax, float az, float bx, float bz
   return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz)));
 }
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;        // centres per CTA
+constexpr int kChunk = 4096;     // points staged in shared memory at a time (x, z: 32 KB)
 
+// The CTA's warps share every chunk of points (one coalesced pass over pts per 4 centres instead of one per centre,
+// and the scan itself reads shared memory); members are appended in index order because chunks and the 32-point
+// steps inside them are visited in order and ballot / popc orders the lanes.
 __global__ void __launch_bounds__(kWarps * 32) cylinder_query_kernel(int n, int m, int cap, float radius,
                                                                      const float *__restrict__ pts,
                                                                      const float *__restrict__ centers,
                                                                      int *__restrict__ idx, int *__restrict__ cnt,
                                                                      unsigned char *__restrict__ any) {
+  __shared__ float2 s_xz[kChunk];
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * kWarps + (threadIdx.x >> 5);
-  if (c >= m) return;
-  const float cx = __ldg(centers + 2 * (size_t)c), cz = __ldg(centers + 2 * (size_t)c + 1);
-  int *row = idx + (size_t)c * cap;
+  const bool live = c < m;
+  const float cx = live ? __ldg(centers + 2 * (size_t)c) : 0.f, cz = live ? __ldg(centers + 2 * (size_t)c + 1) : 0.f;
+  int *row = idx + (size_t)(live ? c : 0) * cap;
   int found = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    bool hit = false;
-    if (i < n) hit = bev_dist(cx, cz, __ldg(pts + 3 * (size_t)i), __ldg(pts + 3 * (size_t)i + 2)) < radius;
-    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, hit);
-    if (hit) {
-      const int slot = found + __popc(ballot & ((1u << lane) - 1u));
-      if (slot < cap) row[slot] = i;
-      if (any) any[i] = 1;   // benign race: every writer stores 1
+  for (int base = 0; base < n; base += kChunk) {
+    const int len = min(kChunk, n - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < len; k += kWarps * 32)
+      s_xz[k] = make_float2(__ldg(pts + 3 * (size_t)(base + k)), __ldg(pts + 3 * (size_t)(base + k) + 2));
+    __syncthreads();
+    if (!live) continue;
+#pragma unroll 4
+    for (int k0 = 0; k0 < len; k0 += 32) {
+      const int k = k0 + lane;
+      bool hit = false;
+      if (k < len) {
+        const float2 p = s_xz[k];
+        hit = bev_dist(cx, cz, p.x, p.y) < radius;
+      }
+      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, hit);
+      if (hit) {
+        const int slot = found + __popc(ballot & ((1u << lane) - 1u));
+        if (slot < cap) row[slot] = base + k;
+        if (any) any[base + k] = 1;   // benign race: every writer stores 1
+      }
+      found += __popc(ballot);
     }
-    found += __popc(ballot);
   }
-  if (lane == 0) cnt[c] = found;
+  if (live && lane == 0) cnt[c] = found;
 }
 
 }  // namespace
