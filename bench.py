@@ -159,6 +159,8 @@ ALG_BYTES = {
     "group_concat": lambda b, n, m, c, k, **kw: b * (4 * m * k + 12 * n + 4 * c * n + 12 * m + 4 * (3 + c) * m * k),
     "three_nn": lambda b, n, m, **k: b * (12 * n + 12 * m + 24 * n),
     "three_interpolate": lambda b, c, m, n, **k: b * (4 * c * m + 24 * n + 4 * c * n),
+    # one fused set-abstraction scale: indices + coordinates + features in, pooled features out (weights are L2-resident)
+    "sa_mlp_fused": lambda b, n, m, k, c, c3, **kw: b * (4 * m * k + 12 * n + 12 * m + 4 * c * n + 4 * c3 * m),
     # one shared-MLP layer: read (c1+c2) x cols, write c_out x cols (or cols/pool), read the folded weights once
     "mlp_layer": lambda b, c_out, c_in, cols, pool, **k: 4 * (b * c_in * cols + b * c_out * (cols // pool if pool else cols)
                                                               + c_out * c_in),
@@ -193,6 +195,8 @@ class OpProfiler:
             "group_concat": ("group_concat", lambda b, n, m, c, k, *r: dict(b=b, n=n, m=m, c=c, k=k)),
             "three_nn_wrapper": ("three_nn", lambda b, n, m, *r: dict(b=b, n=n, m=m)),
             "three_interpolate_wrapper": ("three_interpolate", lambda b, c, m, n, *r: dict(b=b, c=c, m=m, n=n)),
+            "sa_mlp_fused": ("sa_mlp_fused", lambda b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, *r:
+                             dict(b=b, n=n, m=m, k=nsample, c=c_feat, c3=widths[2])),
             "mlp_layer": ("mlp_layer", lambda b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool:
                           dict(b=b, c_out=c_out, c_in=c1 + c2, cols=cols, pool=pool)),
         }

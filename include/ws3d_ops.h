@@ -150,6 +150,26 @@ int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int cols, co
                    const float *shift, const float *x1, const float *x2, float *out, int relu, int pool,
                    ws3d_stream_t stream);
 
+/* Extension (complete form): ONE set-abstraction scale in one kernel --
+ * QueryAndGroup's grouping (pointnet2_utils.py:241-264, use_xyz = True), the three SharedMLP layers
+ * (pytorch_utils.py:5-32: conv1x1 + BatchNorm(eval, folded) + ReLU) and the max-pool over nsample
+ * (pointnet2_modules.py:40-44), without materialising the grouped tensor or the intermediate
+ * activations (they stay in tensor memory).  TF32 inputs, FP32 accumulation.
+ *   xyz (B,n,3), new_xyz (B,m,3), features (B,c_feat,n) or NULL when c_feat == 0, idx (B,m,nsample);
+ *   k0 = roundup(3 + c_feat, 8), n_l = roundup(c_l, 16);
+ *   w1 (n1, 32*ceil(k0/32)) with columns [dx,dy,dz,features...], w2 (n2, 32*ceil(n1/32)),
+ *   w3 (n3, 32*ceil(n2/32)): row-major, zero padded, rounded to TF32; shift_l (n_l) zero padded;
+ *   out (B, out_ctot, m): channels [out_coff, out_coff + c3) are written (the scale's slot of the
+ *   concatenated multi-scale output, pointnet2_modules.py:55).
+ * ws3d_sa_mlp_fused_supported: 1 when the shape fits (nsample a power of two <= 128, weights resident
+ * in shared memory, <= 512 tensor-memory columns), else 0 -- callers then use ws3d_mlp_layer. */
+int ws3d_sa_mlp_fused_supported(int c_feat, int nsample, int c1, int c2, int c3);
+int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float *xyz,
+                      const float *new_xyz, const float *features, const int *idx, int c1, int c2,
+                      int c3, const float *w1, const float *shift1, const float *w2,
+                      const float *shift2, const float *w3, const float *shift3, float *out,
+                      int out_ctot, int out_coff, ws3d_stream_t stream);
+
 /* ---- iou3d_cuda ------------------------------------------------------------ */
 
 /* Replaces boxesoverlapLauncher (lib/utils/iou3d/src/iou3d.cpp:26, iou3d_kernel.cu:354-363).

@@ -107,3 +107,56 @@ def test_rpn_heads_on_the_layer_kernel_match_pytorch():
     assert got_cls.shape == want_cls.shape == (2, 1, 4096) and got_reg.shape == want_reg.shape == (2, 40, 4096)
     for got, want in ((got_cls, want_cls), (got_reg, want_reg)):
         assert float((got - want).abs().max()) <= TOL * (float(want.abs().max()) + 1e-6) + 1e-4
+
+
+def _sa_reference(sa, xyz, feat, new_xyz):
+    """The module's own FP32 PyTorch path (grouping kernels + cuDNN convs with TF32 off + max_pool2d)."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return sa(xyz, feat, new_xyz=new_xyz)[1]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("n,m,c,radii,nsamples,mlps", [
+    (4096, 1024, 1, [0.5, 1.0], [16, 32], [[1, 16, 16, 32], [1, 32, 32, 64]]),          # SA1 widths
+    (2048, 512, 96, [1.0, 2.0], [16, 32], [[96, 64, 64, 128], [96, 64, 96, 128]]),      # SA2 widths
+    (1500, 100, 5, [1.0, 2.0], [16, 64], [[5, 24, 40, 40], [5, 16, 16, 72]]),           # ragged tiles, odd widths, cross-warp pooling
+    (1024, 33, 0, [2.0], [128], [[0, 16, 32, 48]]),                                       # no features, one centre per tile
+    (600, 64, 128, [3.0], [16], [[128, 128, 128, 128]]),                                  # Stage-2 widths: 512 TMEM columns, 208 KB of weights
+])
+def test_fused_sa_scale_matches_module_fp32_path(n, m, c, radii, nsamples, mlps, monkeypatch):
+    """csrc/sa_fused.cu (grouping + 3 layers + max-pool in one kernel, activations in tensor memory) against the same
+    module on its FP32 PyTorch path; and against the per-layer tcgen05 path, which rounds identically except for
+    the first-layer input (truncated there, rounded to nearest here)."""
+    from ws3d_b200 import _C, pointnet2_modules, pointnet2_utils, synth
+    torch.manual_seed(n + m)
+    sa = pointnet2_modules.PointnetSAModuleMSG(npoint=m, radii=radii, nsamples=nsamples, mlps=[list(s) for s in mlps],
+                                              use_xyz=True).to(dev).eval()
+    g = torch.Generator(device="cpu").manual_seed(m)
+    for mod in sa.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.2)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.bias.shape, generator=g) * 0.2)
+    pts = torch.from_numpy(synth.make_batch(2, n)).to(dev)
+    xyz = pts[..., :3].contiguous()
+    feat = torch.randn(2, c, n, device=dev) if c else None
+    _, new_xyz = pointnet2_utils.sample_and_gather(xyz, m)
+    want = _sa_reference(sa, xyz, feat, new_xyz)
+    before = _C.launch_count()
+    with torch.no_grad():
+        got = sa(xyz, feat, new_xyz=new_xyz)[1]
+    launched = _C.launch_count() - before
+    assert len(sa.__dict__.get("_fused_scales", {})) == len(radii)            # the fused path was taken ...
+    assert launched <= 2 * ((len(radii) + 1) // 2) + len(radii), launched    # ... ball queries (grid build + query) + ONE kernel per scale
+    assert got.shape == want.shape
+    scale = float(want.abs().max()) + 1e-6
+    assert float((got - want).abs().max()) <= TOL * scale + 1e-4, float((got - want).abs().max()) / scale
+    monkeypatch.setenv("WS3D_SA_FUSED", "0")
+    with torch.no_grad():
+        layered = sa(xyz, feat, new_xyz=new_xyz)[1]
+    assert float((got - layered).abs().max()) <= TOL * scale + 1e-4

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "ws3d_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_mlp_layer": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "ws3d_sa_mlp_fused_supported": [_i, _i, _i, _i, _i],
+    "ws3d_sa_mlp_fused": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ws3d_boxes_overlap_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "ws3d_boxes_iou_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "ws3d_nms_workspace_bytes": [_i],

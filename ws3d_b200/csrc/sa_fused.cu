@@ -1,0 +1,411 @@
+// One set-abstraction scale in ONE kernel:
+//
+//     ball-query indices -> gather [xyz - centre ; features] -> (conv1x1 + BN + ReLU) x 3 -> max over nsample
+//
+// i.e. QueryAndGroup's grouping (pointnet2_utils.py:241-264), the three SharedMLP layers (pytorch_utils.py:5-32) and
+// the max-pool of pointnet2_modules.py:40-44, without ever materialising the (B, 3+C, npoint, nsample) grouped tensor
+// or the two intermediate activations in HBM.  The per-layer path (mlp_tc.cu) moves them through HBM five times;
+// at the Stage-1 shapes that is 80-95 % of the traffic of SA1 and SA2.
+//
+// Orientation (transposed with respect to mlp_tc.cu): the 128 grouped points of a tile sit on the MMA M dimension
+// = the 128 TMEM lanes, channels run along TMEM columns.
+//   * The gathered input tile is written straight into TMEM (tcgen05.st) by the thread that owns the row: thread r
+//     fetches idx, the centre, xyz[idx] - centre and features[:, idx] and stores them along lane r.
+//   * Every layer is  D[128 x N] = A[128 x K] * W^T  with A READ FROM TMEM (tcgen05.mma, A in tensor memory) and
+//     W (N x K, K-major, BN folded, TF32-rounded) resident in shared memory for the whole kernel (TMA, 128B swizzle).
+//   * The accumulator of layer l has exactly the layout layer l+1 wants for its A operand, so the epilogue is
+//     tcgen05.ld -> + shift, ReLU, round to TF32 -> tcgen05.st in place.  Activations never leave TMEM.
+//   * The last epilogue max-pools over nsample consecutive rows = lanes: the values are >= 0 after the ReLU, so their
+//     bit patterns order like unsigned integers and one redux.sync.max.u32 per channel pools a whole warp.
+// TMEM columns are reused: layer 2's accumulator overlays the (dead) input tile, layer 3's overlays layer 1's.
+//
+// Warp roles (160 threads): warps 0-3 own TMEM lanes 32w..32w+31 (gather + the three epilogues), warp 4 issues the
+// MMAs.  Persistent CTAs, two per SM when TMEM and shared memory allow, so one CTA's gather overlaps the other's
+// epilogues.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace ws3d {
+namespace {
+
+constexpr int kRows = 128;          // grouped points per tile (UMMA M)
+constexpr int kThreads = 160;
+constexpr int kMaxPool = 256 * 8;   // floats of pooled staging: c3 (<= 256) x centres per tile (<= 8)
+
+struct SaFusedParams {
+  int n, m, ns, c_feat;          // points per cloud, centres per cloud, nsample, feature channels
+  int k0;                        // 3 + c_feat rounded up to 8: K of layer 1
+  int n1, n2, n3;                // layer widths rounded up to 16 (UMMA N; K of the next layer)
+  int c3;                        // real output channels
+  int nk1, nk2, nk3;             // 32-deep K chunks of the resident weights
+  int tm_a0, tm_r1, tm_r2, tm_r3, tmem_cols;
+  int tiles_per_cloud, n_tiles;
+  const float *xyz, *new_xyz, *feat;
+  const int *idx;
+  const float *shift1, *shift2, *shift3;   // padded to n1 / n2 / n3
+  float *out;
+  int out_ctot, out_coff;        // out is (B, out_ctot, m); this scale writes channels [out_coff, out_coff + c3)
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows 128 B apart, 8-row groups 1 KB apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)(16u >> 4) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: TF32 inputs, FP32 accumulate, M = 128
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t round_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
+
+// the four row warps only (threads 0..127)
+__device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
+                                                                   const __grid_constant__ CUtensorMap map_w2,
+                                                                   const __grid_constant__ CUtensorMap map_w3,
+                                                                   const SaFusedParams prm) {
+  extern __shared__ uint8_t s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar_w, s_bar_a, s_bar_d;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_shift[3 * 256];
+  __shared__ unsigned int s_pool[kMaxPool];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_base = (smem_u32(s_raw) + 1023u) & ~1023u;      // 128B-swizzle atoms need 1 KB alignment
+  const uint32_t w1 = w_base, w2 = w1 + (uint32_t)prm.nk1 * prm.n1 * 128u, w3 = w2 + (uint32_t)prm.nk2 * prm.n2 * 128u;
+  const uint32_t bar_w = smem_u32(&s_bar_w), bar_a = smem_u32(&s_bar_a), bar_d = smem_u32(&s_bar_d);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a, 4);    // one arrival per row warp
+    mbar_init(bar_d, 1);    // tcgen05.commit
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < prm.n1; i += kThreads) s_shift[i] = __ldg(prm.shift1 + i);
+  for (int i = threadIdx.x; i < prm.n2; i += kThreads) s_shift[256 + i] = __ldg(prm.shift2 + i);
+  for (int i = threadIdx.x; i < prm.n3; i += kThreads) s_shift[512 + i] = __ldg(prm.shift3 + i);
+  for (int i = threadIdx.x; i < kMaxPool; i += kThreads) s_pool[i] = 0u;
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(prm.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- resident weights: every 32-deep K chunk of the three layers, once per CTA
+      const uint32_t bytes = ((uint32_t)prm.nk1 * prm.n1 + (uint32_t)prm.nk2 * prm.n2 + (uint32_t)prm.nk3 * prm.n3) * 128u;
+      mbar_expect_tx(bar_w, bytes);
+      for (int i = 0; i < prm.nk1; ++i) tma_load_2d(w1 + (uint32_t)i * prm.n1 * 128u, &map_w1, i * 32, 0, bar_w);
+      for (int i = 0; i < prm.nk2; ++i) tma_load_2d(w2 + (uint32_t)i * prm.n2 * 128u, &map_w2, i * 32, 0, bar_w);
+      for (int i = 0; i < prm.nk3; ++i) tma_load_2d(w3 + (uint32_t)i * prm.n3 * 128u, &map_w3, i * 32, 0, bar_w);
+      mbar_wait(bar_w, 0);
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N per layer
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
+      const uint32_t wl[3] = {w1, w2, w3};
+      const int nl[3] = {prm.n1, prm.n2, prm.n3};
+      const int kl[3] = {prm.k0, prm.n1, prm.n2};
+      const uint32_t al[3] = {(uint32_t)prm.tm_a0, (uint32_t)prm.tm_r1, (uint32_t)prm.tm_r2};
+      const uint32_t dl[3] = {(uint32_t)prm.tm_r1, (uint32_t)prm.tm_r2, (uint32_t)prm.tm_r3};
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int l = 0; l < 3; ++l) {
+          mbar_wait(bar_a, phase & 1u);   // the A operand of this layer is in TMEM
+          ++phase;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t idesc = idesc0 | ((uint32_t)(nl[l] >> 3) << 17);
+          const int ksteps = kl[l] >> 3;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // weights: chunk ks/4 (N rows x 128 B), 32 B further per K = 8 step inside the swizzled row
+            const uint64_t db = smem_desc_k128(wl[l] + (uint32_t)(ks >> 2) * (uint32_t)nl[l] * 128u + (uint32_t)(ks & 3) * 32u);
+            umma_tf32_ts(tmem_base + dl[l], tmem_base + al[l] + (uint32_t)ks * 8u, db, idesc, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_d);
+        }
+      }
+    }
+  } else {
+    // ---- row warps: thread = one grouped point (TMEM lane)
+    const int row = threadIdx.x;                      // 0..127
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int ns = prm.ns, lg_ns = __ffs(ns) - 1;
+    const int cpt = kRows >> lg_ns;                   // centres per tile (>= 1)
+    const int cols = prm.m * ns;                      // grouped points per cloud
+    const unsigned gmask = ns >= 32 ? 0xFFFFFFFFu : (((1u << ns) - 1u) << (lane & ~(ns - 1)));
+    uint32_t phase_d = 0;
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+      const int cloud = tile / prm.tiles_per_cloud, t_in = tile - cloud * prm.tiles_per_cloud;
+      const int flat = t_in * kRows + row;
+      const bool valid = flat < cols;
+      // ---- gather: [xyz[idx] - centre ; features[:, idx]] along this thread's TMEM lane
+      {
+        const int j = valid ? flat >> lg_ns : 0;
+        const int p = valid ? __ldg(prm.idx + (size_t)cloud * cols + flat) : 0;
+        const float *px = prm.xyz + ((size_t)cloud * prm.n + p) * 3;
+        const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
+        const float *pf = prm.feat ? prm.feat + (size_t)cloud * prm.c_feat * prm.n + p : nullptr;
+        const float dx = __fsub_rn(__ldg(px), __ldg(pc)), dy = __fsub_rn(__ldg(px + 1), __ldg(pc + 1)),
+                    dz = __fsub_rn(__ldg(px + 2), __ldg(pc + 2));
+        const int c_feat = prm.c_feat;
+        for (int q = 0; q < prm.k0; q += 32) {
+          float v[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const int ch = q + t - 3;                 // feature channel
+            v[t] = (valid && ch >= 0 && ch < c_feat) ? __ldg(pf + (size_t)ch * prm.n) : 0.f;
+          }
+          if (q == 0) { v[0] = valid ? dx : 0.f; v[1] = valid ? dy : 0.f; v[2] = valid ? dz : 0.f; }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (q + g * 8 < prm.k0) {                 // warp-uniform
+              uint32_t r[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) r[t] = round_tf32(v[g * 8 + t]);
+              tmem_st8(lane_addr + (uint32_t)(prm.tm_a0 + q + g * 8), r);
+            }
+          }
+        }
+        tmem_st_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
+      }
+      // ---- layers 1 and 2: accumulator -> + shift, ReLU, TF32 -> A operand of the next layer, in place
+#pragma unroll 1
+      for (int l = 0; l < 2; ++l) {
+        const int nl = l == 0 ? prm.n1 : prm.n2;
+        const uint32_t acc = lane_addr + (uint32_t)(l == 0 ? prm.tm_r1 : prm.tm_r2);
+        const float *sh = s_shift + 256 * l;
+        mbar_wait(bar_d, phase_d & 1u);
+        ++phase_d;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c0 = 0; c0 < nl; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 16; ++t) r[t] = round_tf32(fmaxf(__uint_as_float(r[t]) + sh[c0 + t], 0.f));
+          tmem_st16(acc + (uint32_t)c0, r);
+        }
+        tmem_st_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
+      }
+      // ---- layer 3: + shift, ReLU, max over the nsample rows of every centre
+      {
+        const uint32_t acc = lane_addr + (uint32_t)prm.tm_r3;
+        const float *sh = s_shift + 512;
+        mbar_wait(bar_d, phase_d & 1u);
+        ++phase_d;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int centre_local = row >> lg_ns;        // centre of this row inside the tile
+        const bool leader = (lane & (min(ns, 32) - 1)) == 0;
+        for (int c0 = 0; c0 < prm.n3; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc + (uint32_t)c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            // rows beyond the cloud hold relu(shift): they must not reach a real centre (they never do: a tile's
+            // invalid rows belong to centres >= m), values are >= 0 so unsigned order == float order
+            const unsigned u = __float_as_uint(fmaxf(__uint_as_float(r[t]) + sh[c0 + t], 0.f));
+            const unsigned mx = __reduce_max_sync(gmask, u);
+            if (leader && c0 + t < prm.c3) atomicMax(&s_pool[(c0 + t) * cpt + centre_local], mx);
+          }
+        }
+        // the accumulator has been read: the next tile's gather may overwrite TMEM (tm_a0 overlays tm_r2, which
+        // layer 3 read as its A operand -- complete, because bar_d fired)
+        row_warps_sync();
+        const int centre0 = t_in * cpt;
+        for (int c = row; c < prm.c3; c += 128) {
+          float *dst = prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + c) * prm.m + centre0;
+          unsigned int *src = s_pool + c * cpt;
+          if (cpt % 4 == 0 && centre0 + cpt <= prm.m && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+            for (int k = 0; k < cpt; k += 4) {
+              *reinterpret_cast<uint4 *>(dst + k) = make_uint4(src[k], src[k + 1], src[k + 2], src[k + 3]);
+              src[k] = 0u; src[k + 1] = 0u; src[k + 2] = 0u; src[k + 3] = 0u;
+            }
+          } else {
+            for (int k = 0; k < cpt; ++k) {
+              if (centre0 + k < prm.m) dst[k] = __uint_as_float(src[k]);
+              src[k] = 0u;
+            }
+          }
+        }
+        row_warps_sync();
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prm.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// weights (rows x k_pad) row-major, box = 32 k x `rows`
+bool weight_map(CUtensorMap *m, const float *w, int rows, int k_pad) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("sa_mlp_fused: cuTensorMapEncodeTiled unavailable"); return false; }
+  const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)k_pad * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(w), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("sa_mlp_fused: cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+  return true;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Plan { int k0, n1, n2, n3, nk1, nk2, nk3, a0, r1, r2, r3, tmem_cols; size_t smem; int ctas_per_sm; bool ok; };
+
+Plan make_plan(int c_feat, int c1, int c2, int c3) {
+  Plan p = {};
+  p.k0 = round_up(3 + c_feat, 8);
+  p.n1 = round_up(c1, 16); p.n2 = round_up(c2, 16); p.n3 = round_up(c3, 16);
+  p.nk1 = ceil_div(p.k0, 32); p.nk2 = ceil_div(p.n1, 32); p.nk3 = ceil_div(p.n2, 32);
+  int total;
+  if (p.n2 <= p.k0) {            // layer 2's accumulator overlays the input tile, layer 3's overlays layer 1's
+    p.a0 = 0; p.r1 = p.k0; p.r2 = 0; p.r3 = p.k0;
+    total = p.k0 + (p.n1 > p.n3 ? p.n1 : p.n3);
+  } else {
+    p.a0 = 0; p.r1 = p.k0; p.r2 = p.k0 + p.n1; p.r3 = p.r2 + p.n2;
+    total = p.r3 + p.n3;
+  }
+  p.tmem_cols = total <= 32 ? 32 : total <= 64 ? 64 : total <= 128 ? 128 : total <= 256 ? 256 : 512;
+  p.smem = ((size_t)p.nk1 * p.n1 + (size_t)p.nk2 * p.n2 + (size_t)p.nk3 * p.n3) * 128 + 1024;
+  p.ok = total <= 512 && p.n1 <= 256 && p.n2 <= 256 && p.n3 <= 256 && p.smem <= 232448 - 12 * 1024;   // 227 KB per CTA minus the kernel's static shared memory
+  const int by_tmem = 512 / p.tmem_cols;
+  const int by_smem = (int)((228 * 1024) / (p.smem + 13 * 1024));   // + static shared memory of the kernel
+  p.ctas_per_sm = by_tmem < by_smem ? by_tmem : by_smem;
+  if (p.ctas_per_sm > 2) p.ctas_per_sm = 2;
+  if (p.ctas_per_sm < 1) p.ok = false;
+  return p;
+}
+
+}  // namespace
+}  // namespace ws3d
+
+using namespace ws3d;
+
+WS3D_API int ws3d_sa_mlp_fused_supported(int c_feat, int nsample, int c1, int c2, int c3) {
+  if (c_feat < 0 || c1 <= 0 || c2 <= 0 || c3 <= 0 || nsample <= 0 || nsample > kRows || (nsample & (nsample - 1))) return 0;
+  return make_plan(c_feat, c1, c2, c3).ok ? 1 : 0;
+}
+
+// One set-abstraction scale: grouping + 3 x (conv1x1 + BN(eval, folded) + ReLU) + max over nsample.
+//   xyz (B,n,3), new_xyz (B,m,3), features (B,c_feat,n) or NULL (c_feat = 0), idx (B,m,nsample) from ball_query;
+//   w1 (n1 x 32*ceil(k0/32)), w2 (n2 x 32*ceil(n1/32)), w3 (n3 x 32*ceil(n2/32)): BN-folded, zero padded, TF32-rounded,
+//     row-major; k0 = roundup(3 + c_feat, 8), n_l = roundup(c_l, 16); w1's columns are [dx,dy,dz, features...];
+//   shift_l (n_l) zero padded;  out (B, out_ctot, m): channels [out_coff, out_coff + c3) are written.
+WS3D_API int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
+                               const float *features, const int *idx, int c1, int c2, int c3, const float *w1,
+                               const float *shift1, const float *w2, const float *shift2, const float *w3,
+                               const float *shift3, float *out, int out_ctot, int out_coff, ws3d_stream_t stream) {
+  const char *what = "sa_mlp_fused";
+  if (b < 0 || n <= 0 || m < 0 || out_coff < 0 || out_coff + c3 > out_ctot) return fail_arg(what);
+  if (!ws3d_sa_mlp_fused_supported(c_feat, nsample, c1, c2, c3)) return fail_arg("sa_mlp_fused (unsupported shape)");
+  if (b == 0 || m == 0) return 0;
+  if (!xyz || !new_xyz || !idx || !w1 || !w2 || !w3 || !shift1 || !shift2 || !shift3 || !out || (c_feat > 0 && !features))
+    return fail_arg(what);
+  const Plan pl = make_plan(c_feat, c1, c2, c3);
+  SaFusedParams prm;
+  prm.n = n; prm.m = m; prm.ns = nsample; prm.c_feat = c_feat;
+  prm.k0 = pl.k0; prm.n1 = pl.n1; prm.n2 = pl.n2; prm.n3 = pl.n3; prm.c3 = c3;
+  prm.nk1 = pl.nk1; prm.nk2 = pl.nk2; prm.nk3 = pl.nk3;
+  prm.tm_a0 = pl.a0; prm.tm_r1 = pl.r1; prm.tm_r2 = pl.r2; prm.tm_r3 = pl.r3; prm.tmem_cols = pl.tmem_cols;
+  const long long cols = (long long)m * nsample;
+  prm.tiles_per_cloud = (int)((cols + kRows - 1) / kRows);
+  const long long tiles = (long long)prm.tiles_per_cloud * b;
+  if (tiles > 0x7FFFFFFFLL || cols > 0x7FFFFFFFLL) return fail_arg("sa_mlp_fused (too many tiles)");
+  prm.n_tiles = (int)tiles;
+  prm.xyz = xyz; prm.new_xyz = new_xyz; prm.feat = c_feat > 0 ? features : nullptr; prm.idx = idx;
+  prm.shift1 = shift1; prm.shift2 = shift2; prm.shift3 = shift3;
+  prm.out = out; prm.out_ctot = out_ctot; prm.out_coff = out_coff;
+  CUtensorMap m1, m2, m3;
+  if (!weight_map(&m1, w1, pl.n1, pl.nk1 * 32) || !weight_map(&m2, w2, pl.n2, pl.nk2 * 32) ||
+      !weight_map(&m3, w3, pl.n3, pl.nk3 * 32))
+    return (int)cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(sa_mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) { set_error("sa_mlp_fused: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  const int pc = persistent_ctas(pl.ctas_per_sm);
+  const int ctas = (int)(tiles < (long long)pc ? tiles : (long long)pc);
+  sa_mlp_fused_kernel<<<ctas, kThreads, pl.smem, to_stream(stream)>>>(m1, m2, m3, prm);
+  return check_launch(what);
+}

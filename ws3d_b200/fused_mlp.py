@@ -117,3 +117,66 @@ def supported(cols: int, pool: int) -> bool:
     """Shapes the kernel accepts: 16-byte aligned rows; pooling groups (nsample) that are a power of two <= 128, so
     that a group never straddles the column share of one epilogue warp."""
     return cols % 4 == 0 and (pool == 0 or (pool & (pool - 1) == 0 and pool <= 128 and cols % pool == 0))
+
+
+class FusedSAScale:
+    """Folded weights of a 3-layer SharedMLP in the layout of `ws3d_sa_mlp_fused` (csrc/sa_fused.cu): one kernel per
+    set-abstraction scale does grouping + the three layers + the max-pool with every activation kept in TMEM.
+    Layer l's weight is (roundup(c_l, 16), 32 * ceil(K_l / 32)) with K_1 = roundup(3 + C, 8), K_{l+1} = roundup(c_l, 16)."""
+
+    def __init__(self, mlp: nn.Sequential):
+        self._mlp = mlp
+        self._versions = None
+        self._build()
+
+    @staticmethod
+    def eligible(mlp: nn.Sequential, c_feat: int, nsample: int) -> bool:
+        blocks = list(mlp)
+        if len(blocks) != 3 or not all(hasattr(b, "conv") and hasattr(b, "activation") for b in blocks):
+            return False
+        if any(not isinstance(b.activation, nn.ReLU) for b in blocks):
+            return False   # the pooled epilogue orders non-negative floats as unsigned integers
+        if any(hasattr(b, "bn") and not hasattr(b.bn, "bn") for b in blocks):
+            return False
+        if blocks[0].conv.in_channels != 3 + c_feat:
+            return False
+        widths = [b.conv.out_channels for b in blocks]
+        return bool(native.sa_mlp_fused_supported(c_feat, nsample, *widths))
+
+    def _stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self._mlp.parameters()) + list(self._mlp.buffers()))
+
+    def _build(self):
+        self.w, self.shift, self.widths = [], [], []
+        k_in = None
+        for block in self._mlp:
+            conv = block.conv
+            w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
+            shift = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+            if hasattr(block, "bn"):
+                bn = block.bn.bn
+                scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+                w = w * scale[:, None]
+                shift = (shift - bn.running_mean) * scale + bn.bias.detach()
+            c_out, c_in = w.shape
+            n_pad = _ceil(c_out, 16)
+            k_pad = _ceil(_ceil(c_in, 8) if k_in is None else k_in, _CHUNK_K)
+            wp = torch.zeros((n_pad, k_pad), dtype=torch.float32, device=w.device)
+            wp[:c_out, :c_in] = _round_tf32(w)
+            sp = torch.zeros(n_pad, dtype=torch.float32, device=w.device)
+            sp[:c_out] = shift
+            self.w.append(wp.contiguous())
+            self.shift.append(sp)
+            self.widths.append(c_out)
+            k_in = n_pad
+        self._versions = self._stamp()
+
+    def __call__(self, xyz, new_xyz, features, idx, out, c_off):
+        """xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or None, idx (B,M,K) int32; writes out[:, c_off:c_off+c3, :]."""
+        if self._versions != self._stamp():
+            self._build()
+        B, N, _ = xyz.shape
+        M, K = idx.shape[1], idx.shape[2]
+        c_feat = 0 if features is None else features.shape[1]
+        native.sa_mlp_fused(B, N, M, K, c_feat, xyz, new_xyz, features, idx, self.widths, self.w, self.shift, out,
+                            out.shape[1], c_off)

@@ -247,6 +247,19 @@ def roipool3d_cpu(pts, boxes3d, pts_feature, pooled_pts, pooled_features, pooled
     return 1
 
 
+def sa_mlp_fused_supported(c_feat, nsample, c1, c2, c3) -> bool:
+    return bool(lib().ws3d_sa_mlp_fused_supported(int(c_feat), int(nsample), int(c1), int(c2), int(c3)))
+
+
+def sa_mlp_fused(b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, w, shift, out, out_ctot, out_coff):
+    """Extension: grouping + 3 x (conv1x1 + BN + ReLU) + max-pool of one set-abstraction scale."""
+    require_cuda(xyz, new_xyz, features, idx, out, *w, *shift)
+    with device_of(xyz):
+        check(lib().ws3d_sa_mlp_fused(b, n, m, nsample, c_feat, ptr(xyz), ptr(new_xyz), ptr(features), ptr(idx),
+                                      widths[0], widths[1], widths[2], ptr(w[0]), ptr(shift[0]), ptr(w[1]), ptr(shift[1]),
+                                      ptr(w[2]), ptr(shift[2]), ptr(out), out_ctot, out_coff, stream()), "sa_mlp_fused")
+
+
 def set_workspace_arena(arena: int) -> int:
     """Scratch arena (0..7) for this thread's subsequent launches; returns the previous one (ws3d_ops.h)."""
     return int(lib().ws3d_set_workspace_arena(int(arena)))

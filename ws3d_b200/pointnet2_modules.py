@@ -11,6 +11,7 @@ and therefore the same state_dict keys.  The forward passes sequence the B200 op
              features, cat                    (3+C, npoint, nsample) tensor once
   SharedMLP + max-pool                        unchanged (PyTorch / cuDNN)
 """
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -60,6 +61,23 @@ class _PointnetSAModuleBase(nn.Module):
             indices = [None] * len(self.groupers)  # GroupAll
         pooled = []
         fused = fused_mlp.enabled_for(self) and self.pool_method == 'max_pool'
+        if fused and self.npoint is not None and os.environ.get("WS3D_SA_FUSED", "1") != "0":
+            # inference: one kernel per scale (grouping + 3 layers + max-pool, activations stay in tensor memory),
+            # each writing its slot of the concatenated output
+            c_feat = 0 if features is None else features.shape[1]
+            if (all(getattr(g, "use_xyz", False) for g in self.groupers) and xyz.is_contiguous()
+                    and (features is None or features.is_contiguous())
+                    and all(fused_mlp.FusedSAScale.eligible(mlp, c_feat, g.nsample) for g, mlp in zip(self.groupers, self.mlps))):
+                cache = self.__dict__.setdefault("_fused_scales", {})
+                widths = [mlp[-1].conv.out_channels for mlp in self.mlps]
+                out = torch.empty((xyz.shape[0], sum(widths), new_xyz.shape[1]), dtype=torch.float32, device=xyz.device)
+                off = 0
+                for k, (mlp, idx) in enumerate(zip(self.mlps, indices)):
+                    if k not in cache:
+                        cache[k] = fused_mlp.FusedSAScale(mlp)
+                    cache[k](xyz, new_xyz, features, idx, out, off)
+                    off += widths[k]
+                return new_xyz, out
         for k, (grouper, mlp, idx) in enumerate(zip(self.groupers, self.mlps, indices)):
             grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
             B, C, M, K = grouped.shape
