@@ -19,9 +19,9 @@
 //     bit patterns order like unsigned integers and one redux.sync.max.u32 per channel pools a whole warp.
 // TMEM columns are reused: layer 2's accumulator overlays the (dead) input tile, layer 3's overlays layer 1's.
 //
-// Warp roles (160 threads): warps 0-3 own TMEM lanes 32w..32w+31 (gather + the three epilogues), warp 4 issues the
-// MMAs.  Persistent CTAs, two per SM when TMEM and shared memory allow, so one CTA's gather overlaps the other's
-// epilogues.
+// 128 threads: warp w owns TMEM lanes 32w..32w+31 (gather + the three epilogues); after a CTA barrier thread 0 issues
+// the layer's MMAs and everybody waits for the tcgen05.commit.  Persistent CTAs, up to four per SM (TMEM columns,
+// shared memory), so one CTA's gather latency and MMA hand-offs are covered by the others' epilogues.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,8 +31,7 @@ namespace ws3d {
 namespace {
 
 constexpr int kRows = 128;          // grouped points per tile (UMMA M)
-constexpr int kThreads = 160;
-constexpr int kMaxPool = 256 * 8;   // floats of pooled staging: c3 (<= 256) x centres per tile (<= 8)
+constexpr int kThreads = 128;
 
 struct SaFusedParams {
   int n, m, ns, c_feat;          // points per cloud, centres per cloud, nsample, feature channels
@@ -105,35 +104,53 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __device__ __forceinline__ uint32_t round_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
 
-// the four row warps only (threads 0..127)
-__device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Butterfly max-reduction over the G lanes of a pooling group: every lane enters with G channel values of its own
+// row and leaves with ONE channel (index = lane % G) maximised over the G rows -- a reduce-scatter, G - 1 shuffles
+// for G channels instead of G full-warp reductions.
+template <int G>
+__device__ __forceinline__ float pool_scatter(float (&v)[G], int lane) {
+#pragma unroll
+  for (int h = G / 2; h >= 1; h >>= 1) {
+    const bool upper = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = upper ? v[i] : v[i + h];
+      const float keep = upper ? v[i + h] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, send, h));
+    }
+  }
+  return v[0];
+}
 
-__global__ void __launch_bounds__(kThreads, 1) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
+__global__ void __launch_bounds__(kThreads, 4) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
                                                                    const __grid_constant__ CUtensorMap map_w2,
                                                                    const __grid_constant__ CUtensorMap map_w3,
                                                                    const SaFusedParams prm) {
   extern __shared__ uint8_t s_raw[];
-  __shared__ __align__(8) unsigned long long s_bar_w, s_bar_a, s_bar_d;
+  __shared__ __align__(8) unsigned long long s_bar_w, s_bar_d;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_shift[3 * 256];
-  __shared__ unsigned int s_pool[kMaxPool];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_base = (smem_u32(s_raw) + 1023u) & ~1023u;      // 128B-swizzle atoms need 1 KB alignment
   const uint32_t w1 = w_base, w2 = w1 + (uint32_t)prm.nk1 * prm.n1 * 128u, w3 = w2 + (uint32_t)prm.nk2 * prm.n2 * 128u;
-  const uint32_t bar_w = smem_u32(&s_bar_w), bar_a = smem_u32(&s_bar_a), bar_d = smem_u32(&s_bar_d);
+  const uint32_t w_end = w3 + (uint32_t)prm.nk3 * prm.n3 * 128u;
+  // behind the weights: the three shift vectors (n1 + n2 + n3 floats), then the pooled staging (c3 x centres per tile)
+  float *s_shift = reinterpret_cast<float *>(s_raw + (w_end - smem_u32(s_raw)));
+  unsigned int *s_pool = reinterpret_cast<unsigned int *>(s_shift + prm.n1 + prm.n2 + prm.n3);
+  const uint32_t bar_w = smem_u32(&s_bar_w), bar_d = smem_u32(&s_bar_d);
+  const int lg_ns = __ffs(prm.ns) - 1;
+  const int cpt = kRows >> lg_ns;                     // centres per tile (>= 1)
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_a, 4);    // one arrival per row warp
     mbar_init(bar_d, 1);    // tcgen05.commit
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < prm.n1; i += kThreads) s_shift[i] = __ldg(prm.shift1 + i);
-  for (int i = threadIdx.x; i < prm.n2; i += kThreads) s_shift[256 + i] = __ldg(prm.shift2 + i);
-  for (int i = threadIdx.x; i < prm.n3; i += kThreads) s_shift[512 + i] = __ldg(prm.shift3 + i);
-  for (int i = threadIdx.x; i < kMaxPool; i += kThreads) s_pool[i] = 0u;
-  if (warp == 4) {
+  for (int i = threadIdx.x; i < prm.n2; i += kThreads) s_shift[prm.n1 + i] = __ldg(prm.shift2 + i);
+  for (int i = threadIdx.x; i < prm.n3; i += kThreads) s_shift[prm.n1 + prm.n2 + i] = __ldg(prm.shift3 + i);
+  for (int i = threadIdx.x; i < prm.c3 * cpt; i += kThreads) s_pool[i] = 0u;
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(prm.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -143,157 +160,202 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_fused_kernel(const __grid_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      // ---- resident weights: every 32-deep K chunk of the three layers, once per CTA
-      const uint32_t bytes = ((uint32_t)prm.nk1 * prm.n1 + (uint32_t)prm.nk2 * prm.n2 + (uint32_t)prm.nk3 * prm.n3) * 128u;
-      mbar_expect_tx(bar_w, bytes);
-      for (int i = 0; i < prm.nk1; ++i) tma_load_2d(w1 + (uint32_t)i * prm.n1 * 128u, &map_w1, i * 32, 0, bar_w);
-      for (int i = 0; i < prm.nk2; ++i) tma_load_2d(w2 + (uint32_t)i * prm.n2 * 128u, &map_w2, i * 32, 0, bar_w);
-      for (int i = 0; i < prm.nk3; ++i) tma_load_2d(w3 + (uint32_t)i * prm.n3 * 128u, &map_w3, i * 32, 0, bar_w);
-      mbar_wait(bar_w, 0);
-      // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N per layer
-      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
-      const uint32_t wl[3] = {w1, w2, w3};
-      const int nl[3] = {prm.n1, prm.n2, prm.n3};
-      const int kl[3] = {prm.k0, prm.n1, prm.n2};
-      const uint32_t al[3] = {(uint32_t)prm.tm_a0, (uint32_t)prm.tm_r1, (uint32_t)prm.tm_r2};
-      const uint32_t dl[3] = {(uint32_t)prm.tm_r1, (uint32_t)prm.tm_r2, (uint32_t)prm.tm_r3};
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-#pragma unroll 1
-        for (int l = 0; l < 3; ++l) {
-          mbar_wait(bar_a, phase & 1u);   // the A operand of this layer is in TMEM
-          ++phase;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t idesc = idesc0 | ((uint32_t)(nl[l] >> 3) << 17);
-          const int ksteps = kl[l] >> 3;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            // weights: chunk ks/4 (N rows x 128 B), 32 B further per K = 8 step inside the swizzled row
-            const uint64_t db = smem_desc_k128(wl[l] + (uint32_t)(ks >> 2) * (uint32_t)nl[l] * 128u + (uint32_t)(ks & 3) * 32u);
-            umma_tf32_ts(tmem_base + dl[l], tmem_base + al[l] + (uint32_t)ks * 8u, db, idesc, ks != 0 ? 1u : 0u);
+  if (threadIdx.x == 0) {
+    // ---- resident weights: every 32-deep K chunk of the three layers, once per CTA
+    const uint32_t bytes = ((uint32_t)prm.nk1 * prm.n1 + (uint32_t)prm.nk2 * prm.n2 + (uint32_t)prm.nk3 * prm.n3) * 128u;
+    mbar_expect_tx(bar_w, bytes);
+    for (int i = 0; i < prm.nk1; ++i) tma_load_2d(w1 + (uint32_t)i * prm.n1 * 128u, &map_w1, i * 32, 0, bar_w);
+    for (int i = 0; i < prm.nk2; ++i) tma_load_2d(w2 + (uint32_t)i * prm.n2 * 128u, &map_w2, i * 32, 0, bar_w);
+    for (int i = 0; i < prm.nk3; ++i) tma_load_2d(w3 + (uint32_t)i * prm.n3 * 128u, &map_w3, i * 32, 0, bar_w);
+    mbar_wait(bar_w, 0);
+  }
+
+  // One layer's MMAs, issued by thread 0 once all 128 threads have written their rows of the A operand:
+  // D[128 x N] = A[128 x K] (TMEM) * W^T (shared memory), K = 8 per instruction.
+  auto issue_layer = [&](uint32_t wl, int nl, int kl, uint32_t a_col, uint32_t d_col) {
+    tmem_st_wait();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = nl
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24) | ((uint32_t)(nl >> 3) << 17);
+      const int ksteps = kl >> 3;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        // weights: chunk ks/4 (N rows x 128 B), 32 B further per K = 8 step inside the swizzled row
+        const uint64_t db = smem_desc_k128(wl + (uint32_t)(ks >> 2) * (uint32_t)nl * 128u + (uint32_t)(ks & 3) * 32u);
+        umma_tf32_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)ks * 8u, db, idesc, ks != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_d);
+    }
+  };
+
+  // ---- thread = one grouped point (TMEM lane)
+  const int row = threadIdx.x;                        // 0..127
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int ns = prm.ns;
+  const int cols = prm.m * ns;                        // grouped points per cloud
+  const int n = prm.n, c_feat = prm.c_feat;
+  uint32_t phase_d = 0;
+  for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+    const int cloud = tile / prm.tiles_per_cloud, t_in = tile - cloud * prm.tiles_per_cloud;
+    const int flat = t_in * kRows + row;
+    const bool valid = flat < cols;
+    // ---- gather: [xyz[idx] - centre ; features[:, idx]] along this thread's TMEM lane.  Rows beyond the cloud
+    // (last tile only) recompute point 0 against centre 0: finite values that never reach an output.
+    {
+      const int j = valid ? flat >> lg_ns : 0;
+      const int p = valid ? __ldg(prm.idx + (size_t)cloud * cols + flat) : 0;
+      const float *px = prm.xyz + ((size_t)cloud * n + p) * 3;
+      const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
+      const float *pf = prm.feat + (size_t)cloud * c_feat * n;     // not dereferenced when c_feat == 0
+      uint32_t r[8];
+      unsigned off = (unsigned)p;                     // index of (channel, point p) in this cloud's features
+      // first group: 3 coordinates + channels 0..4 (raw FP32 features: the tensor core truncates to TF32)
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        r[3 + t] = t < c_feat ? __float_as_uint(__ldg(pf + off)) : 0u;
+        off += (unsigned)n;
+      }
+      r[0] = round_tf32(__fsub_rn(__ldg(px), __ldg(pc)));
+      r[1] = round_tf32(__fsub_rn(__ldg(px + 1), __ldg(pc + 1)));
+      r[2] = round_tf32(__fsub_rn(__ldg(px + 2), __ldg(pc + 2)));
+      tmem_st8(lane_addr + (uint32_t)prm.tm_a0, r);
+      // then 32 channels (32 independent loads) at a time; the last batch is predicated / zero padded
+      for (int ch = 5; ch + 3 < prm.k0; ch += 32) {
+        uint32_t v[32];
+        if (ch + 32 <= c_feat) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) { v[t] = __float_as_uint(__ldg(pf + off)); off += (unsigned)n; }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) { v[t] = ch + t < c_feat ? __float_as_uint(__ldg(pf + off)) : 0u; off += (unsigned)n; }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (ch + 3 + g * 8 < prm.k0) {              // CTA-uniform
+            uint32_t q[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) q[t] = v[g * 8 + t];
+            tmem_st8(lane_addr + (uint32_t)(prm.tm_a0 + ch + 3 + g * 8), q);
           }
-          umma_commit(bar_d);
         }
       }
     }
-  } else {
-    // ---- row warps: thread = one grouped point (TMEM lane)
-    const int row = threadIdx.x;                      // 0..127
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int ns = prm.ns, lg_ns = __ffs(ns) - 1;
-    const int cpt = kRows >> lg_ns;                   // centres per tile (>= 1)
-    const int cols = prm.m * ns;                      // grouped points per cloud
-    const unsigned gmask = ns >= 32 ? 0xFFFFFFFFu : (((1u << ns) - 1u) << (lane & ~(ns - 1)));
-    uint32_t phase_d = 0;
-    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-      const int cloud = tile / prm.tiles_per_cloud, t_in = tile - cloud * prm.tiles_per_cloud;
-      const int flat = t_in * kRows + row;
-      const bool valid = flat < cols;
-      // ---- gather: [xyz[idx] - centre ; features[:, idx]] along this thread's TMEM lane
-      {
-        const int j = valid ? flat >> lg_ns : 0;
-        const int p = valid ? __ldg(prm.idx + (size_t)cloud * cols + flat) : 0;
-        const float *px = prm.xyz + ((size_t)cloud * prm.n + p) * 3;
-        const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
-        const float *pf = prm.feat ? prm.feat + (size_t)cloud * prm.c_feat * prm.n + p : nullptr;
-        const float dx = __fsub_rn(__ldg(px), __ldg(pc)), dy = __fsub_rn(__ldg(px + 1), __ldg(pc + 1)),
-                    dz = __fsub_rn(__ldg(px + 2), __ldg(pc + 2));
-        const int c_feat = prm.c_feat;
-        for (int q = 0; q < prm.k0; q += 32) {
+    issue_layer(w1, prm.n1, prm.k0, (uint32_t)prm.tm_a0, (uint32_t)prm.tm_r1);
+    // ---- layers 1 and 2: accumulator -> + shift, ReLU, round to TF32 -> A operand of the next layer, in place.
+    // (Adding half a TF32 ulp is the rounding: the tensor core ignores the low 13 bits.)
+#pragma unroll 1
+    for (int l = 0; l < 2; ++l) {
+      const int nl = l == 0 ? prm.n1 : prm.n2;
+      const uint32_t acc = lane_addr + (uint32_t)(l == 0 ? prm.tm_r1 : prm.tm_r2);
+      const float4 *sh = reinterpret_cast<const float4 *>(s_shift + (l == 0 ? 0 : prm.n1));
+      mbar_wait(bar_d, phase_d & 1u);
+      ++phase_d;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t ra[16], rb[16];
+      tmem_ld16(acc, ra);
+      for (int c0 = 0; c0 < nl; c0 += 32) {
+        tmem_ld_wait();
+        if (c0 + 16 < nl) tmem_ld16(acc + (uint32_t)(c0 + 16), rb);      // in flight while ra is processed
+#pragma unroll
+        for (int t = 0; t < 16; t += 4) {
+          const float4 s4 = sh[(c0 + t) >> 2];
+          ra[t] = __float_as_uint(fmaxf(__uint_as_float(ra[t]) + s4.x, 0.f)) + 0x1000u;
+          ra[t + 1] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 1]) + s4.y, 0.f)) + 0x1000u;
+          ra[t + 2] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 2]) + s4.z, 0.f)) + 0x1000u;
+          ra[t + 3] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 3]) + s4.w, 0.f)) + 0x1000u;
+        }
+        tmem_st16(acc + (uint32_t)c0, ra);
+        if (c0 + 16 < nl) {
+          tmem_ld_wait();
+          if (c0 + 32 < nl) tmem_ld16(acc + (uint32_t)(c0 + 32), ra);
+#pragma unroll
+          for (int t = 0; t < 16; t += 4) {
+            const float4 s4 = sh[(c0 + 16 + t) >> 2];
+            rb[t] = __float_as_uint(fmaxf(__uint_as_float(rb[t]) + s4.x, 0.f)) + 0x1000u;
+            rb[t + 1] = __float_as_uint(fmaxf(__uint_as_float(rb[t + 1]) + s4.y, 0.f)) + 0x1000u;
+            rb[t + 2] = __float_as_uint(fmaxf(__uint_as_float(rb[t + 2]) + s4.z, 0.f)) + 0x1000u;
+            rb[t + 3] = __float_as_uint(fmaxf(__uint_as_float(rb[t + 3]) + s4.w, 0.f)) + 0x1000u;
+          }
+          tmem_st16(acc + (uint32_t)(c0 + 16), rb);
+        }
+      }
+      if (l == 0) issue_layer(w2, prm.n2, prm.n1, (uint32_t)prm.tm_r1, (uint32_t)prm.tm_r2);
+      else issue_layer(w3, prm.n3, prm.n2, (uint32_t)prm.tm_r2, (uint32_t)prm.tm_r3);
+    }
+    // ---- layer 3: max over the nsample rows of every centre, then + shift and ReLU on the pooled value (the shift
+    // is per channel and ReLU is monotone, so they commute with the max).  A butterfly reduce-scatter leaves lane t
+    // of a pooling group with channel c0 + t.
+    {
+      const uint32_t acc = lane_addr + (uint32_t)prm.tm_r3;
+      const float *sh = s_shift + prm.n1 + prm.n2;
+      mbar_wait(bar_d, phase_d & 1u);
+      ++phase_d;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int centre_local = row >> lg_ns;          // centre of this row inside the tile
+      int c0 = 0;
+      if (ns >= 32) {
+        for (; c0 + 32 <= prm.n3; c0 += 32) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(acc + (uint32_t)c0, ra);
+          tmem_ld16(acc + (uint32_t)(c0 + 16), rb);
+          tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const int ch = q + t - 3;                 // feature channel
-            v[t] = (valid && ch >= 0 && ch < c_feat) ? __ldg(pf + (size_t)ch * prm.n) : 0.f;
-          }
-          if (q == 0) { v[0] = valid ? dx : 0.f; v[1] = valid ? dy : 0.f; v[2] = valid ? dz : 0.f; }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (q + g * 8 < prm.k0) {                 // warp-uniform
-              uint32_t r[8];
-#pragma unroll
-              for (int t = 0; t < 8; ++t) r[t] = round_tf32(v[g * 8 + t]);
-              tmem_st8(lane_addr + (uint32_t)(prm.tm_a0 + q + g * 8), r);
-            }
+          for (int t = 0; t < 16; ++t) { v[t] = __uint_as_float(ra[t]); v[16 + t] = __uint_as_float(rb[t]); }
+          const float mx = pool_scatter<32>(v, lane);
+          const int c = c0 + lane;
+          if (c < prm.c3) {
+            const unsigned u = __float_as_uint(fmaxf(mx + sh[c], 0.f));
+            if (ns == 32) s_pool[c * cpt + centre_local] = u;
+            else atomicMax(&s_pool[c * cpt + centre_local], u);   // >= 0: unsigned order == float order
           }
         }
-        tmem_st_wait();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
       }
-      // ---- layers 1 and 2: accumulator -> + shift, ReLU, TF32 -> A operand of the next layer, in place
-#pragma unroll 1
-      for (int l = 0; l < 2; ++l) {
-        const int nl = l == 0 ? prm.n1 : prm.n2;
-        const uint32_t acc = lane_addr + (uint32_t)(l == 0 ? prm.tm_r1 : prm.tm_r2);
-        const float *sh = s_shift + 256 * l;
-        mbar_wait(bar_d, phase_d & 1u);
-        ++phase_d;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int c0 = 0; c0 < nl; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(acc + (uint32_t)c0, r);
-          tmem_ld_wait();
+      for (; c0 < prm.n3; c0 += 16) {
+        uint32_t ra[16];
+        tmem_ld16(acc + (uint32_t)c0, ra);
+        tmem_ld_wait();
+        float v[16];
 #pragma unroll
-          for (int t = 0; t < 16; ++t) r[t] = round_tf32(fmaxf(__uint_as_float(r[t]) + sh[c0 + t], 0.f));
-          tmem_st16(acc + (uint32_t)c0, r);
+        for (int t = 0; t < 16; ++t) {
+          v[t] = __uint_as_float(ra[t]);
+          if (ns >= 32) v[t] = fmaxf(v[t], __shfl_xor_sync(0xFFFFFFFFu, v[t], 16));   // both half-warps belong to one centre
         }
-        tmem_st_wait();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
+        const float mx = pool_scatter<16>(v, lane);
+        const int c = c0 + (lane & 15);
+        if (c < prm.c3 && (ns < 32 || lane < 16)) {
+          const unsigned u = __float_as_uint(fmaxf(mx + sh[c], 0.f));
+          if (ns <= 32) s_pool[c * cpt + centre_local] = u;
+          else atomicMax(&s_pool[c * cpt + centre_local], u);
+        }
       }
-      // ---- layer 3: + shift, ReLU, max over the nsample rows of every centre
-      {
-        const uint32_t acc = lane_addr + (uint32_t)prm.tm_r3;
-        const float *sh = s_shift + 512;
-        mbar_wait(bar_d, phase_d & 1u);
-        ++phase_d;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int centre_local = row >> lg_ns;        // centre of this row inside the tile
-        const bool leader = (lane & (min(ns, 32) - 1)) == 0;
-        for (int c0 = 0; c0 < prm.n3; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(acc + (uint32_t)c0, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            // rows beyond the cloud hold relu(shift): they must not reach a real centre (they never do: a tile's
-            // invalid rows belong to centres >= m), values are >= 0 so unsigned order == float order
-            const unsigned u = __float_as_uint(fmaxf(__uint_as_float(r[t]) + sh[c0 + t], 0.f));
-            const unsigned mx = __reduce_max_sync(gmask, u);
-            if (leader && c0 + t < prm.c3) atomicMax(&s_pool[(c0 + t) * cpt + centre_local], mx);
+      // the accumulator has been read: the next tile's gather may overwrite TMEM
+      __syncthreads();
+      const int centre0 = t_in * cpt;
+      for (int c = row; c < prm.c3; c += kThreads) {
+        float *dst = prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + c) * prm.m + centre0;
+        unsigned int *src = s_pool + c * cpt;
+        if (cpt % 4 == 0 && centre0 + cpt <= prm.m && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+          for (int k = 0; k < cpt; k += 4) {
+            *reinterpret_cast<uint4 *>(dst + k) = *reinterpret_cast<const uint4 *>(src + k);
+            if (ns > 32) *reinterpret_cast<uint4 *>(src + k) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
+          for (int k = 0; k < cpt; ++k) {
+            if (centre0 + k < prm.m) dst[k] = __uint_as_float(src[k]);
+            if (ns > 32) src[k] = 0u;
           }
         }
-        // the accumulator has been read: the next tile's gather may overwrite TMEM (tm_a0 overlays tm_r2, which
-        // layer 3 read as its A operand -- complete, because bar_d fired)
-        row_warps_sync();
-        const int centre0 = t_in * cpt;
-        for (int c = row; c < prm.c3; c += 128) {
-          float *dst = prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + c) * prm.m + centre0;
-          unsigned int *src = s_pool + c * cpt;
-          if (cpt % 4 == 0 && centre0 + cpt <= prm.m && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-            for (int k = 0; k < cpt; k += 4) {
-              *reinterpret_cast<uint4 *>(dst + k) = make_uint4(src[k], src[k + 1], src[k + 2], src[k + 3]);
-              src[k] = 0u; src[k + 1] = 0u; src[k + 2] = 0u; src[k + 3] = 0u;
-            }
-          } else {
-            for (int k = 0; k < cpt; ++k) {
-              if (centre0 + k < prm.m) dst[k] = __uint_as_float(src[k]);
-              src[k] = 0u;
-            }
-          }
-        }
-        row_warps_sync();
       }
+      // (the next write to s_pool comes after three more __syncthreads)
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prm.tmem_cols) : "memory");
   }
 }
@@ -335,26 +397,36 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct Plan { int k0, n1, n2, n3, nk1, nk2, nk3, a0, r1, r2, r3, tmem_cols; size_t smem; int ctas_per_sm; bool ok; };
 
-Plan make_plan(int c_feat, int c1, int c2, int c3) {
+Plan make_plan(int c_feat, int nsample, int c1, int c2, int c3) {
   Plan p = {};
   p.k0 = round_up(3 + c_feat, 8);
   p.n1 = round_up(c1, 16); p.n2 = round_up(c2, 16); p.n3 = round_up(c3, 16);
   p.nk1 = ceil_div(p.k0, 32); p.nk2 = ceil_div(p.n1, 32); p.nk3 = ceil_div(p.n2, 32);
-  int total;
-  if (p.n2 <= p.k0) {            // layer 2's accumulator overlays the input tile, layer 3's overlays layer 1's
-    p.a0 = 0; p.r1 = p.k0; p.r2 = 0; p.r3 = p.k0;
-    total = p.k0 + (p.n1 > p.n3 ? p.n1 : p.n3);
-  } else {
-    p.a0 = 0; p.r1 = p.k0; p.r2 = p.k0 + p.n1; p.r3 = p.r2 + p.n2;
-    total = p.r3 + p.n3;
+  // TMEM layouts (a region may overlay one that is dead by the time it is written; an accumulator must never
+  // overlap the A operand of its own layer):
+  //   sequential : a0 | r1 | r2 | r3
+  //   A          : r2 over a0, r3 over r1            (needs n2 <= k0)
+  //   C          : r3 over a0, then r1, r2           (the input tile is dead long before layer 3)
+  int total = p.k0 + p.n1 + p.n2 + p.n3;
+  p.a0 = 0; p.r1 = p.k0; p.r2 = p.k0 + p.n1; p.r3 = p.r2 + p.n2;
+  if (p.n2 <= p.k0) {
+    const int t = p.k0 + (p.n1 > p.n3 ? p.n1 : p.n3);
+    if (t < total) { total = t; p.a0 = 0; p.r1 = p.k0; p.r2 = 0; p.r3 = p.k0; }
+  }
+  {
+    const int head = p.n3 > p.k0 ? p.n3 : p.k0;
+    const int t = head + p.n1 + p.n2;
+    if (t < total) { total = t; p.a0 = 0; p.r3 = 0; p.r1 = head; p.r2 = head + p.n1; }
   }
   p.tmem_cols = total <= 32 ? 32 : total <= 64 ? 64 : total <= 128 ? 128 : total <= 256 ? 256 : 512;
-  p.smem = ((size_t)p.nk1 * p.n1 + (size_t)p.nk2 * p.n2 + (size_t)p.nk3 * p.n3) * 128 + 1024;
-  p.ok = total <= 512 && p.n1 <= 256 && p.n2 <= 256 && p.n3 <= 256 && p.smem <= 232448 - 12 * 1024;   // 227 KB per CTA minus the kernel's static shared memory
+  const int cpt = nsample > 0 && nsample <= 128 ? 128 / nsample : 1;
+  p.smem = ((size_t)p.nk1 * p.n1 + (size_t)p.nk2 * p.n2 + (size_t)p.nk3 * p.n3) * 128 + 1024   // weights + alignment slack
+           + (size_t)(p.n1 + p.n2 + p.n3) * 4 + (size_t)c3 * cpt * 4 + 16;
+  p.ok = total <= 512 && p.n1 <= 256 && p.n2 <= 256 && p.n3 <= 256 && p.smem <= 232448 - 1024;
   const int by_tmem = 512 / p.tmem_cols;
-  const int by_smem = (int)((228 * 1024) / (p.smem + 13 * 1024));   // + static shared memory of the kernel
+  const int by_smem = (int)((233472 - 2048) / (p.smem + 1024 + 256));   // 228 KB per SM, 1 KB reserved per CTA
   p.ctas_per_sm = by_tmem < by_smem ? by_tmem : by_smem;
-  if (p.ctas_per_sm > 2) p.ctas_per_sm = 2;
+  if (p.ctas_per_sm > 4) p.ctas_per_sm = 4;   // registers: 4 x 128 threads x <= 128
   if (p.ctas_per_sm < 1) p.ok = false;
   return p;
 }
@@ -365,8 +437,8 @@ Plan make_plan(int c_feat, int c1, int c2, int c3) {
 using namespace ws3d;
 
 WS3D_API int ws3d_sa_mlp_fused_supported(int c_feat, int nsample, int c1, int c2, int c3) {
-  if (c_feat < 0 || c1 <= 0 || c2 <= 0 || c3 <= 0 || nsample <= 0 || nsample > kRows || (nsample & (nsample - 1))) return 0;
-  return make_plan(c_feat, c1, c2, c3).ok ? 1 : 0;
+  if (c_feat < 0 || c1 <= 0 || c2 <= 0 || c3 <= 0 || nsample < 16 || nsample > kRows || (nsample & (nsample - 1))) return 0;
+  return make_plan(c_feat, nsample, c1, c2, c3).ok ? 1 : 0;
 }
 
 // One set-abstraction scale: grouping + 3 x (conv1x1 + BN(eval, folded) + ReLU) + max over nsample.
@@ -384,7 +456,7 @@ WS3D_API int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, con
   if (b == 0 || m == 0) return 0;
   if (!xyz || !new_xyz || !idx || !w1 || !w2 || !w3 || !shift1 || !shift2 || !shift3 || !out || (c_feat > 0 && !features))
     return fail_arg(what);
-  const Plan pl = make_plan(c_feat, c1, c2, c3);
+  const Plan pl = make_plan(c_feat, nsample, c1, c2, c3);
   SaFusedParams prm;
   prm.n = n; prm.m = m; prm.ns = nsample; prm.c_feat = c_feat;
   prm.k0 = pl.k0; prm.n1 = pl.n1; prm.n2 = pl.n2; prm.n3 = pl.n3; prm.c3 = c3;
