@@ -122,7 +122,10 @@ __device__ __forceinline__ float pool_scatter(float (&v)[G], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(kThreads, 4) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
+// kBatch feature channels are fetched per thread before they are stored to TMEM (independent loads in flight);
+// the wide variant (64) is for the scales whose TMEM / shared-memory footprint allows two CTAs per SM anyway.
+template <int kBatch, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
                                                                    const __grid_constant__ CUtensorMap map_w2,
                                                                    const __grid_constant__ CUtensorMap map_w3,
                                                                    const SaFusedParams prm) {
@@ -197,15 +200,23 @@ __global__ void __launch_bounds__(kThreads, 4) sa_mlp_fused_kernel(const __grid_
   const int cols = prm.m * ns;                        // grouped points per cloud
   const int n = prm.n, c_feat = prm.c_feat;
   uint32_t phase_d = 0;
+  // the neighbour index of this thread's row is fetched one tile ahead (it heads the gather's dependency chain)
+  auto load_idx = [&](int t) -> int {
+    const int cl = t / prm.tiles_per_cloud;
+    const int fl = (t - cl * prm.tiles_per_cloud) * kRows + row;
+    return fl < cols ? __ldg(prm.idx + (size_t)cl * cols + fl) : 0;
+  };
+  int p_next = blockIdx.x < prm.n_tiles ? load_idx(blockIdx.x) : 0;
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
     const int cloud = tile / prm.tiles_per_cloud, t_in = tile - cloud * prm.tiles_per_cloud;
     const int flat = t_in * kRows + row;
     const bool valid = flat < cols;
+    const int p = p_next;
+    if (tile + (int)gridDim.x < prm.n_tiles) p_next = load_idx(tile + (int)gridDim.x);
     // ---- gather: [xyz[idx] - centre ; features[:, idx]] along this thread's TMEM lane.  Rows beyond the cloud
     // (last tile only) recompute point 0 against centre 0: finite values that never reach an output.
     {
       const int j = valid ? flat >> lg_ns : 0;
-      const int p = valid ? __ldg(prm.idx + (size_t)cloud * cols + flat) : 0;
       const float *px = prm.xyz + ((size_t)cloud * n + p) * 3;
       const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
       const float *pf = prm.feat + (size_t)cloud * c_feat * n;     // not dereferenced when c_feat == 0
@@ -221,18 +232,18 @@ __global__ void __launch_bounds__(kThreads, 4) sa_mlp_fused_kernel(const __grid_
       r[1] = round_tf32(__fsub_rn(__ldg(px + 1), __ldg(pc + 1)));
       r[2] = round_tf32(__fsub_rn(__ldg(px + 2), __ldg(pc + 2)));
       tmem_st8(lane_addr + (uint32_t)prm.tm_a0, r);
-      // then 32 channels (32 independent loads) at a time; the last batch is predicated / zero padded
-      for (int ch = 5; ch + 3 < prm.k0; ch += 32) {
-        uint32_t v[32];
-        if (ch + 32 <= c_feat) {
+      // then kBatch channels (independent loads) at a time; the last batch is predicated / zero padded
+      for (int ch = 5; ch + 3 < prm.k0; ch += kBatch) {
+        uint32_t v[kBatch];
+        if (ch + kBatch <= c_feat) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) { v[t] = __float_as_uint(__ldg(pf + off)); off += (unsigned)n; }
+          for (int t = 0; t < kBatch; ++t) { v[t] = __float_as_uint(__ldg(pf + off)); off += (unsigned)n; }
         } else {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) { v[t] = ch + t < c_feat ? __float_as_uint(__ldg(pf + off)) : 0u; off += (unsigned)n; }
+          for (int t = 0; t < kBatch; ++t) { v[t] = ch + t < c_feat ? __float_as_uint(__ldg(pf + off)) : 0u; off += (unsigned)n; }
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < kBatch / 8; ++g) {
           if (ch + 3 + g * 8 < prm.k0) {              // CTA-uniform
             uint32_t q[8];
 #pragma unroll
@@ -474,10 +485,12 @@ WS3D_API int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, con
   if (!weight_map(&m1, w1, pl.n1, pl.nk1 * 32) || !weight_map(&m2, w2, pl.n2, pl.nk2 * 32) ||
       !weight_map(&m3, w3, pl.n3, pl.nk3 * 32))
     return (int)cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(sa_mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  const bool wide = pl.ctas_per_sm <= 2 && c_feat > 37;
+  auto kern = wide ? sa_mlp_fused_kernel<64, 2> : sa_mlp_fused_kernel<32, 4>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) { set_error("sa_mlp_fused: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   const int pc = persistent_ctas(pl.ctas_per_sm);
   const int ctas = (int)(tiles < (long long)pc ? tiles : (long long)pc);
-  sa_mlp_fused_kernel<<<ctas, kThreads, pl.smem, to_stream(stream)>>>(m1, m2, m3, prm);
+  kern<<<ctas, kThreads, pl.smem, to_stream(stream)>>>(m1, m2, m3, prm);
   return check_launch(what);
 }
