@@ -384,9 +384,65 @@ def run_gpu(args):
         pr.prefetch(pr.stage[0])
         ms_total, _, _, _ = timed_region(step_pipe, args.steps, profile=False)
         ms_e2e = timed_stream_e2e(args.steps)
+    ms_two, ms_two_e2e = ms_total, ms_e2e
+    deep = pipelined and args.inflight >= 3
+    if deep:
+        # The coordinate phase (FPS levels in throughput mode, ball queries, stencils) runs `inflight - 1` batches ahead
+        # on its own streams beside the feature phase (ws3d_b200.graphs.StreamedBackboneRunner).  K steps, one event pair.
+        from ws3d_b200.graphs import StreamedBackboneRunner
+        look = args.inflight - 1
+        sr = StreamedBackboneRunner(model, resident, lookahead=look)
+        residents = [resident, host_b.to(dev)]
+
+        def timed_streamed(sr, steps, from_host):
+            src = hosts if from_host else residents
+            pinned = [torch.empty(BATCH, dtype=torch.float32).pin_memory() for _ in range(2)]
+            read_ev = [None, None]
+            for j in range(look):
+                sr.submit(src[j % 2])
+            sync_all()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for j in range(steps):
+                flush_small.fill_(0)                      # in-stream L2 flush, inside the timed region
+                out = sr.complete()                       # rest of the forward pass of batch j
+                sr.submit(src[(j + look) % 2])            # staging copy + level-1 FPS of batch j + look (own stream)
+                if from_host:
+                    if read_ev[j % 2] is not None:
+                        read_ev[j % 2].synchronize()
+                    pinned[j % 2].copy_(out.sum(dim=(1, 2)), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    read_ev[j % 2] = ev
+            e.record()
+            e.synchronize()
+            for _ in range(look):                         # drain the batches sampled ahead
+                sr.complete()
+            sync_all()
+            t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        timed_streamed(sr, max(args.warmup, 3), False)
+        timed_streamed(sr, max(args.warmup, 3), True)
+        ms_total = timed_streamed(sr, args.steps, False)
+        ms_e2e = timed_streamed(sr, args.steps, True)
     # the same K steps once more with a CUDA-event pair round every launch of this library (per-kernel durations
     # for the roofline entries; kept out of `value` because ~600 extra event records per step cost host time)
-    ms_prof, _, prof, _ = timed_region(step_eager, args.steps, profile=True)
+    def step_eager_two_phase():   # what the streamed pipeline runs, serially: coordinate phase (throughput FPS), feature phase
+        with torch.no_grad():
+            prev = native.set_fps_mode(1)
+            try:
+                plan = model.coordinate_phase(resident)
+            finally:
+                native.set_fps_mode(prev)
+            return model.feature_phase(resident, plan)[1]
+
+    if deep:
+        for _ in range(2):
+            step_eager_two_phase()
+    ms_prof, _, prof, _ = timed_region(step_eager_two_phase if deep else step_eager, args.steps, profile=True)
     # Stage-1 RPN = backbone + the two per-point heads (lib/net/rpn.py:67-81): scenes/s for the metric's second half
     rpn = models.RPN().to(dev).eval()
     rpn.backbone_net = model
@@ -416,6 +472,14 @@ def run_gpu(args):
     for _ in range(3):
         step_rpn()
     ms_rpn, _, _, _ = timed_region(step_rpn, args.steps, profile=False)
+    if deep:
+        def rpn_heads_plan(pc, plan):
+            o = rpn(pc, plan=plan)
+            return o["rpn_cls"], o["rpn_reg"]
+
+        rpn_sr = StreamedBackboneRunner(model, resident, fn=rpn_heads_plan, lookahead=look)
+        timed_streamed(rpn_sr, 3, False)
+        ms_rpn = timed_streamed(rpn_sr, args.steps, False)
     if sampler:
         sampler.__exit__(None, None, None)
 
@@ -433,8 +497,10 @@ def run_gpu(args):
                 "peak_source": peak_src, "alg_bytes": int(top["alg_bytes"]),
                 "avg_launch_ms": round(top["avg_ms"], 4), "share_of_step": round(top["ms_per_step"] / (ms_prof / args.steps), 4),
                 "profiled_ms_per_step": round(ms_prof / args.steps, 4),
-                "note": "FPS is a latency chain of m-1 dependent iterations (SURVEY.md 8d): its HBM fraction is "
-                        "reported for the record; us/iteration is the meaningful figure" if top["kernel"] == "fps" else ""}
+                "note": ("FPS is a latency chain of m-1 dependent iterations (SURVEY.md 8d): its HBM fraction is reported for the "
+                         "record; us/iteration is the meaningful figure.  In the pipelined modes it runs beside the feature "
+                         "phase of other batches (throughput mode: one SM per cloud), so its share of the SERIAL profile pass "
+                         "below is not its share of the timed step" if top["kernel"] == "fps" else "")}
         if top["kernel"] == "fps":
             roof["us_per_iteration"] = round(top["avg_ms"] * 1e3 / (top["dims"]["m"] - 1), 4)
 
@@ -454,8 +520,12 @@ def run_gpu(args):
                        "mlp": ("tcgen05 TF32 shared-MLP layers (conv1x1+BN+ReLU[+max-pool] per launch, FP32 accumulate)"
                                if torch.backends.cudnn.allow_tf32 else "PyTorch/cuDNN fp32 (TF32 off)"),
                        "launch": "one CUDA graph replay per step" if use_graph else "eager launches",
-                       "pipeline": ("2 batches in flight: each replay runs level-1 FPS of batch i+1 (high-priority stream) beside "
-                                    "the rest of the forward pass of batch i; one batch of 16 clouds completes per step"
+                       "pipeline": ((f"{args.inflight} batches in flight: the coordinate phase (4 FPS levels in throughput mode = one "
+                                     f"SM per cloud, ball queries, interpolation stencils) runs {args.inflight - 1} batches ahead on "
+                                     "its own streams beside the graph-replayed feature phase; one batch of 16 clouds completes "
+                                     "per step; K steps under one event pair, L2 flushed in-stream") if deep else
+                                    ("2 batches in flight: each replay runs level-1 FPS of batch i+1 (high-priority stream) beside "
+                                     "the rest of the forward pass of batch i; one batch of 16 clouds completes per step")
                                     if pipelined else "none (one batch in flight)"),
                        "sm_budget_persistent_kernels": args.sm_budget if pipelined else 0,
                        "streams": "two CUDA streams (FPS chain + interpolation stencils run ahead of grouping / MLPs)"
@@ -466,6 +536,11 @@ def run_gpu(args):
                     "note": ("pinned host clouds -> H2D (copy stream) -> pipelined forward -> per-cloud feature checksum -> async D2H, "
                              "K steps streamed under one event pair, L2 flushed in-stream every step" if pipelined else
                              "pinned host cloud -> H2D -> backbone forward -> per-cloud feature checksum -> D2H")},
+            "two_in_flight": ({"ms_per_step": round(ms_two / args.steps, 4),
+                               "Mpoints_per_s": round(world * BATCH * NPTS / (ms_two / args.steps / 1e3) / 1e6, 3),
+                               "e2e_Mpoints_per_s": round(world * BATCH * NPTS / (ms_two_e2e / args.steps / 1e3) / 1e6, 3),
+                               "note": "PipelinedBackboneRunner: FPS of batch i+1 inside the same replay as the rest of batch i"}
+                              if deep else None),
             "single_batch_latency": {"ms": round(ms_single / args.steps, 4),
                                      "Mpoints_per_s": round(world * BATCH * NPTS / (ms_single / args.steps / 1e3) / 1e6, 3),
                                      "e2e_ms": round(ms_single_e2e / args.steps, 4),
@@ -496,9 +571,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "2")),
-                    help="2: software-pipelined forward (level-1 FPS of the next batch beside the current batch); 1: off")
-    ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "84")),
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "5")),
+                    help=">= 3: coordinate phase (FPS, ball queries, stencils) N-1 batches ahead of the feature phase "
+                         "(StreamedBackboneRunner); 2: level-1 FPS of the next batch beside the current batch; 1: no pipeline")
+    ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "0")),
                     help="SMs the persistent MLP kernel spreads over in pipelined mode (0 = all; 84 = the SMs level-1 FPS leaves free)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -52,6 +52,13 @@ int ws3d_set_workspace_arena(int arena);
 /* Upper bound on the SMs a persistent kernel (ws3d_mlp_layer) spreads over; 0 = all 148.  Used when a
  * latency-bound kernel of another batch (FPS) is meant to run beside it.  Returns the previous value. */
 int ws3d_set_sm_budget(int sms);
+/* How the calling thread's subsequent furthest-point-sampling launches trade latency for SMs:
+ * 0 = automatic (default: thread-block clusters, 4 SMs per cloud, unless the batch leaves < 2 SMs per
+ * cloud), 1 = throughput (the spatially bucketed kernel, ONE SM per cloud, for 2048 <= n <= 16384:
+ * 1.7x the latency at a quarter of the SM time -- for samplers that run beside other work, see
+ * ws3d_b200.graphs.StreamedBackboneRunner), 2 = latency (never the one-SM kernel).  Results are
+ * bit-identical in every mode.  Returns the previous mode. */
+int ws3d_set_fps_mode(int mode);
 
 /* ---- pointnet2_cuda -------------------------------------------------------- */
 

@@ -156,3 +156,48 @@ def test_pipelined_runner_equals_unpipelined_forward():
     b = runner.step().clone()
     torch.cuda.synchronize()
     assert torch.equal(a, want[4]) and torch.equal(b, want[3])
+
+
+def test_streamed_runner_equals_plain_forward():
+    """graphs.StreamedBackboneRunner (coordinate phase -- FPS in throughput mode, ball queries, stencils -- two batches
+    ahead on its own streams, feature phase on the caller's) returns exactly the plain forward's output for every
+    batch of a stream of batches."""
+    from ws3d_b200 import models, native, synth
+    from ws3d_b200.graphs import StreamedBackboneRunner
+    torch.manual_seed(0)
+    cfg = {"NPOINTS": [512, 128, 32, 8], "RADIUS": models.RPN_SA_CONFIG["RADIUS"], "NSAMPLE": models.RPN_SA_CONFIG["NSAMPLE"],
+           "MLPS": [[[8, 8, 16], [8, 8, 16]], [[16, 16, 32], [16, 24, 32]], [[32, 32, 64], [32, 48, 64]], [[64, 64, 96], [64, 64, 96]]]}
+    fp = [[32, 32], [48, 48], [64, 64], [64, 64]]
+    model = models.Pointnet2MSG(input_channels=1, sa_config=cfg, fp_mlps=fp).to(dev).eval()
+    _randomize_bn(model, 3)
+    batches = [torch.from_numpy(synth.make_batch(2, 4096, first_scene=7 * k)) for k in range(6)]
+    with torch.no_grad():
+        want = [model(b.to(dev))[1].clone() for b in batches]
+    runner = StreamedBackboneRunner(model, batches[0].to(dev), lookahead=2)
+    pinned = [b.pin_memory() for b in batches]
+    runner.submit(pinned[0])
+    runner.submit(pinned[1])
+    got = []
+    for k in range(len(batches)):
+        got.append(runner.complete().clone())
+        if k + 2 < len(batches):
+            runner.submit(pinned[k + 2])
+    torch.cuda.synchronize()
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert torch.equal(g, w), f"batch {k} differs"
+    assert native.set_fps_mode(0) == 0          # the runner restores the calling thread's mode
+
+
+def test_fps_modes_are_bit_identical():
+    from ws3d_b200 import native, pointnet2_utils, synth
+    xyz = torch.from_numpy(np.ascontiguousarray(synth.make_batch(3, 8192)[..., :3])).to(dev)
+    outs = []
+    for mode in (0, 1, 2):
+        prev = native.set_fps_mode(mode)
+        try:
+            idx, nx = pointnet2_utils.sample_and_gather(xyz, 2048)
+        finally:
+            native.set_fps_mode(prev)
+        outs.append((idx.clone(), nx.clone()))
+    for idx, nx in outs[1:]:
+        assert torch.equal(idx, outs[0][0]) and torch.equal(nx, outs[0][1])

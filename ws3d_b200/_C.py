@@ -22,6 +22,7 @@ _SIGNATURES = {
     "ws3d_launch_count": [],
     "ws3d_set_workspace_arena": [_i],
     "ws3d_set_sm_budget": [_i],
+    "ws3d_set_fps_mode": [_i],
     "ws3d_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_furthest_point_sampling_gather": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],

@@ -20,6 +20,8 @@ void count_launch(int n = 1);
 void *scratch(size_t bytes, int slot);
 // grid size of a persistent kernel with `per_sm` CTAs per SM, honouring ws3d_set_sm_budget()
 int persistent_ctas(int per_sm);
+// ws3d_set_fps_mode() of the calling thread: 0 auto, 1 throughput (one SM per cloud), 2 latency (clusters)
+int fps_mode();
 
 inline cudaStream_t to_stream(ws3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

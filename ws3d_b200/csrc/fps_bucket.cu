@@ -356,7 +356,10 @@ int launch_bucket(const FpsParams &prm, int b, cudaStream_t stream) {
 // cluster kernels (b > 74; measured on B200 at b = 64 x 16384 points: 3.55 ms against 4.39 ms for the two-level
 // cluster kernel, 3.06 ms for the flat one on 2 SMs per cloud); WS3D_FPS_BUCKET=1/0 forces it.
 bool fps_bucket_applicable(int b, int n, int m) {
-  static const int mode = env_int2("WS3D_FPS_BUCKET", -1);
+  static const int env_mode = env_int2("WS3D_FPS_BUCKET", -1);
+  // ws3d_set_fps_mode(): 1 = throughput (one SM per cloud whenever this kernel applies), 2 = latency (never)
+  const int rt = fps_mode();
+  const int mode = rt == 1 ? 1 : rt == 2 ? 0 : env_mode;
   if (mode == 0 || n < 2048 || n > 16384 || m < 64 || b < 1 || b > 65535) return false;
   return mode == 1 || b * 2 > kNumSMs;
 }

@@ -29,7 +29,10 @@ std::mutex g_mu;
 // flight at the same time (two CUDA graphs replayed on different streams) must not share cell grids.
 thread_local int g_arena = 0;
 std::atomic<int> g_sm_budget{0};
+thread_local int g_fps_mode = 0;
 }  // namespace
+
+int fps_mode() { return g_fps_mode; }
 
 int persistent_ctas(int per_sm) {
   const int b = g_sm_budget.load(std::memory_order_relaxed);
@@ -75,3 +78,8 @@ WS3D_API int ws3d_set_workspace_arena(int arena) {
   return prev;
 }
 WS3D_API int ws3d_set_sm_budget(int sms) { return ws3d::g_sm_budget.exchange(sms < 0 ? 0 : sms); }
+WS3D_API int ws3d_set_fps_mode(int mode) {
+  const int prev = ws3d::g_fps_mode;
+  if (mode >= 0 && mode <= 2) ws3d::g_fps_mode = mode;
+  return prev;
+}

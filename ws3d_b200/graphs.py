@@ -149,3 +149,113 @@ class PipelinedBackboneRunner:
         self._done[1 - p] = ev     # this replay read stage[1-p]
         self.cur = 1 - p
         return self.outputs[p]
+
+
+class StreamedBackboneRunner:
+    """Deeper software pipeline for throughput: the COORDINATE phase of the forward pass (four FPS levels, ball
+    queries, interpolation stencils -- backbone.coordinate_phase) runs `lookahead` batches ahead of the FEATURE phase
+    (grouping + MLPs + interpolation -- backbone.feature_phase), each as its own CUDA graph on its own stream.
+
+    PipelinedBackboneRunner is bounded by the level-1 FPS latency (2.1 ms at the Stage-1 shapes, on 64 SMs).  Here
+    the samplers run in their throughput mode (native.set_fps_mode(1): the spatially bucketed kernel, ONE SM per
+    cloud, 1.7x the latency at a quarter of the SM time) and `lookahead` coordinate phases are in flight at any time
+    on a few SMs each, while the remaining SMs run the bandwidth-bound feature phase of the batch whose coordinates
+    are ready.  A batch then costs max(coordinate phase / lookahead, feature phase) of wall time; its own latency
+    grows to the sum of the two.
+
+        runner = StreamedBackboneRunner(backbone, example)
+        for b in the first `lookahead` batches: runner.submit(b)     # host (pinned) or device tensors
+        loop:  out = runner.complete(); runner.submit(next_batch)    # `out` is valid until `lookahead` more completes
+
+    `fn(pointcloud, plan)` is the consumer of the feature phase (default: backbone.feature_phase -> per-point
+    features).  Results are bit-identical to the plain forward: FPS is exact in every mode and the rest is the same
+    kernels on the same inputs.
+    """
+
+    def __init__(self, backbone, example: torch.Tensor, fn: Callable = None, lookahead: int = 3, fps_mode: int = 1,
+                 warmup: int = 2):
+        from . import native
+        assert example.is_cuda and lookahead >= 1
+        dev = example.device
+        self.device, self.backbone, self.lookahead = dev, backbone, lookahead
+        self.fn = fn or (lambda pc, plan: backbone.feature_phase(pc, plan)[1])
+        self.nbuf = lookahead + 1
+        self.inputs = [example.clone() for _ in range(self.nbuf)]
+        self.coord_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(lookahead)]
+        cur = torch.cuda.current_stream(dev)
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm), torch.no_grad():
+            for _ in range(warmup):   # lazily built state (folded weights, scratch) must exist before capture
+                self.fn(self.inputs[0], backbone.coordinate_phase(self.inputs[0]))
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.coord_graphs, self.feat_graphs, self.plans, self.outputs = [], [], [], []
+        prev_mode = native.set_fps_mode(fps_mode)
+        try:
+            for k in range(self.nbuf):   # the library's cached scratch of every arena must exist before capture
+                prev_arena = native.set_workspace_arena(1 + k % 7)
+                try:
+                    with torch.no_grad():
+                        backbone.coordinate_phase(self.inputs[k])
+                finally:
+                    native.set_workspace_arena(prev_arena)
+            torch.cuda.synchronize(dev)
+            for k in range(self.nbuf):
+                # every buffer set owns its scratch arena: coordinate phases of different batches overlap in time
+                prev_arena = native.set_workspace_arena(1 + k % 7)
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.no_grad(), torch.cuda.graph(g):
+                        plan = backbone.coordinate_phase(self.inputs[k])
+                finally:
+                    native.set_workspace_arena(prev_arena)
+                self.coord_graphs.append(g)
+                self.plans.append(plan)
+        finally:
+            native.set_fps_mode(prev_mode)
+        for k in range(self.nbuf):
+            g = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(g):
+                out = self.fn(self.inputs[k], self.plans[k])
+            self.feat_graphs.append(g)
+            self.outputs.append(out)
+        self.head = 0                        # batches submitted
+        self.tail = 0                        # batches completed
+        self._ready = [None] * self.nbuf     # coordinate-stream events: plan[k] is complete
+        self._done = [None] * self.nbuf      # main-stream events: the feature phase that read buffer set k has finished
+
+    def submit(self, batch: torch.Tensor, after: torch.cuda.Event = None):
+        """Stage `batch` (H2D / D2D copy on a coordinate stream) and start its coordinate phase; returns immediately.
+        `after`: event that marks a device-resident batch as produced (the coordinate streams do not otherwise wait
+        for the caller's stream, that is the point)."""
+        assert self.head - self.tail <= self.lookahead, "complete() a batch before submitting more"
+        k = self.head % self.nbuf
+        st = self.coord_streams[self.head % self.lookahead]
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            if self._done[k] is not None:
+                st.wait_event(self._done[k])
+            else:
+                st.wait_stream(main)
+            if after is not None:
+                st.wait_event(after)
+            self.inputs[k].copy_(batch, non_blocking=True)
+            self.coord_graphs[k].replay()
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._ready[k] = ev
+        self.head += 1
+
+    def complete(self):
+        """Runs the feature phase of the oldest submitted batch (graph replay on the current stream); returns its output."""
+        assert self.tail < self.head, "nothing submitted"
+        k = self.tail % self.nbuf
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self._ready[k])
+        self.feat_graphs[k].replay()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._done[k] = ev
+        self.tail += 1
+        return self.outputs[k]

@@ -74,6 +74,32 @@ class Pointnet2MSG(nn.Module):
         xyz = pointcloud[..., 0:3].contiguous()
         return pointnet2_utils.sample_and_gather(xyz, self.SA_modules[0].npoint)[1]
 
+    def coordinate_phase(self, pointcloud: torch.Tensor) -> dict:
+        """Everything of the forward pass that depends on coordinates only: the four FPS levels, the ball queries of
+        every scale and the three-nearest-neighbour interpolation stencils.  It is a chain of latency-bound kernels
+        that needs few SMs and no bandwidth, so a caller with a stream of batches runs it AHEAD of the feature phase,
+        beside the previous batches' feature phases (graphs.StreamedBackboneRunner)."""
+        xyz = pointcloud[..., 0:3].contiguous()
+        l_xyz, idx = [xyz], []
+        for sa in self.SA_modules:
+            _, nx = pointnet2_utils.sample_and_gather(l_xyz[-1], sa.npoint)
+            idx.append(sa._neighbour_indices(l_xyz[-1], nx))
+            l_xyz.append(nx)
+        nn_ = [PointnetFPModule.interpolation_weights(l_xyz[i], l_xyz[i + 1]) for i in range(len(self.FP_modules))]
+        return {"xyz": l_xyz[1:], "idx": idx, "nn": nn_}
+
+    def feature_phase(self, pointcloud: torch.Tensor, plan: dict):
+        """The rest: grouping + MLPs of the SA levels, interpolation + MLPs of the FP levels, on precomputed samples,
+        neighbour indices and stencils.  Same kernels and arithmetic as forward()."""
+        xyz, features = self._break_up_pc(pointcloud)
+        l_xyz, l_features = [xyz] + list(plan["xyz"]), [features]
+        for k, sa in enumerate(self.SA_modules):
+            _, nf = sa(l_xyz[k], l_features[k], new_xyz=l_xyz[k + 1], indices=plan["idx"][k])
+            l_features.append(nf)
+        for i in range(len(self.FP_modules) - 1, -1, -1):
+            l_features[i] = self.FP_modules[i](l_xyz[i], l_xyz[i + 1], l_features[i], l_features[i + 1], nn=plan["nn"][i])
+        return l_xyz[0], l_features[0]
+
     def _forward_two_streams(self, xyz, features, first_samples=None):
         """Same computation as forward(), scheduled on two CUDA streams.
 
@@ -175,9 +201,12 @@ class RPN(nn.Module):
             return cache[name](x)
         return seq(x)
 
-    def forward(self, input_data, first_samples: Optional[torch.Tensor] = None):
+    def forward(self, input_data, first_samples: Optional[torch.Tensor] = None, plan: Optional[dict] = None):
         pts_input = input_data['pts_input'] if isinstance(input_data, dict) else input_data
-        backbone_xyz, backbone_features = self.backbone_net(pts_input, first_samples=first_samples)
+        if plan is not None:
+            backbone_xyz, backbone_features = self.backbone_net.feature_phase(pts_input, plan)
+        else:
+            backbone_xyz, backbone_features = self.backbone_net(pts_input, first_samples=first_samples)
         rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
         rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()
         return {'rpn_cls': rpn_cls, 'rpn_reg': rpn_reg, 'backbone_xyz': backbone_xyz,

@@ -268,3 +268,8 @@ def set_workspace_arena(arena: int) -> int:
 def set_sm_budget(sms: int) -> int:
     """Upper bound on the SMs a persistent kernel (mlp_layer) spreads over; 0 = all.  Returns the previous value."""
     return int(lib().ws3d_set_sm_budget(int(sms)))
+
+
+def set_fps_mode(mode: int) -> int:
+    """0 auto, 1 throughput (one SM per cloud), 2 latency (clusters) for this thread's FPS launches; returns the previous mode."""
+    return int(lib().ws3d_set_fps_mode(int(mode)))

@@ -51,11 +51,15 @@ class _PointnetSAModuleBase(nn.Module):
         return out
 
     def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor] = None,
-                new_xyz: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B, sum_k mlps[k][-1], npoint)."""
+                new_xyz: Optional[torch.Tensor] = None, indices=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B, sum_k mlps[k][-1], npoint).
+        `new_xyz` / `indices` (one ball-query result per scale): the coordinate-only part of the layer if the caller
+        has already computed it (models.Pointnet2MSG.coordinate_phase)."""
         if new_xyz is None and self.npoint is not None:
             _, new_xyz = pointnet2_utils.sample_and_gather(xyz, self.npoint)
-        if self.npoint is not None:
+        if self.npoint is not None and indices is not None:
+            assert len(indices) == len(self.groupers)
+        elif self.npoint is not None:
             indices = self._neighbour_indices(xyz, new_xyz)
         else:
             indices = [None] * len(self.groupers)  # GroupAll
