@@ -38,8 +38,9 @@ def launches(src, dst, passes):
         a[1] += us
     tot = sum(a[1] for a in agg.values())
     with open(dst, "w") as f:
-        f.write(f"# ncu launch list summary: `ncu --metrics gpu__time_duration.sum --clock-control none python tools/prof_step.py {passes}`\n")
-        f.write(f"# {passes} backbone forward passes (B=16 clouds x 16384 points, single stream), {len(rows)} launches, {tot / 1e3:.3f} ms summed "
+        cmd = sys.argv[sys.argv.index("--cmd") + 1] if "--cmd" in sys.argv else f"python tools/prof_step.py {passes}"
+        f.write(f"# ncu launch list summary: `ncu --metrics gpu__time_duration.sum --clock-control none {cmd}`\n")
+        f.write(f"# {passes} passes (B=16 clouds x 16384 points), {len(rows)} launches, {tot / 1e3:.3f} ms summed "
                 f"= {tot / 1e3 / passes:.3f} ms per pass\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("kernel,launches_per_pass,us_per_pass,share\n")

@@ -82,7 +82,35 @@ class _PointnetSAModuleBase(nn.Module):
                     cache[k](xyz, new_xyz, features, idx, out, off)
                     off += widths[k]
                 return new_xyz, out
+        # inference, several scales: the scales are independent chains of small launches (group + three layers, each
+        # well under one wave at the deeper levels), so they run side by side on per-scale streams
+        side = None
+        if (fused and len(self.groupers) > 1 and xyz.is_cuda and self.npoint is not None
+                and all(fused_mlp.supported(new_xyz.shape[1] * g.nsample, g.nsample) for g in self.groupers)
+                and os.environ.get("WS3D_SCALE_STREAMS", "1") != "0"):
+            side = self.__dict__.get("_scale_streams")
+            if side is None or side[0].device != xyz.device:
+                side = self.__dict__["_scale_streams"] = [torch.cuda.Stream(device=xyz.device) for _ in self.groupers[1:]]
+            main = torch.cuda.current_stream(xyz.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
         for k, (grouper, mlp, idx) in enumerate(zip(self.groupers, self.mlps, indices)):
+            if side is not None and k > 0:
+                st = side[k - 1]
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    grouped = grouper(xyz, new_xyz, features, idx=idx)
+                    B, C, M, K = grouped.shape
+                    res = self._folded(k)(grouped.view(B, C, M * K), pool=K)
+                    done = torch.cuda.Event()
+                    done.record(st)
+                for t in (xyz, new_xyz, features, idx):
+                    if t is not None:
+                        t.record_stream(st)
+                res.record_stream(main)
+                main.wait_event(done)   # (the join is only needed before the cat; waiting here keeps the code simple:
+                pooled.append(res)      #  scale 0 was launched first and is already running on `main`)
+                continue
             grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
             B, C, M, K = grouped.shape
             if fused and fused_mlp.supported(M * K, K):
