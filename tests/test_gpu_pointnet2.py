@@ -71,6 +71,41 @@ def test_fps_matches_oracle_and_reference(b, n, m, kind):
         assert torch.equal(rtemp, temp)
 
 
+TILE_CASES = [(2, 16384, 4096, "scene"), (3, 4096, 1024, "uniform"), (2, 2048, 512, "grid"), (2, 5000, 700, "grid"),
+              (1, 16384, 300, "uniform"), (3, 8192, 2048, "scene"), (2, 3000, 3000, "uniform"), (1, 2500, 64, "special")]
+
+
+@pytest.mark.parametrize("b,n,m,kind", TILE_CASES)
+def test_fps_throughput_mode_matches_oracle(b, n, m, kind):
+    """ws3d_set_fps_mode(1): the one-SM-per-cloud kernel with spatial buckets and exact culling (csrc/fps_bucket.cu)
+    against the oracle: indices, coordinates and the written-back temp, incl. duplicates / lattice ties, non-finite
+    points, far outliers and a cloud collapsed to a line."""
+    from ws3d_b200 import native
+    rng = np.random.default_rng(b * 7919 + n + m)
+    if kind == "special":
+        xyz = rng.uniform(-5, 5, (b, n, 3)).astype(np.float32)
+        xyz[:, 100:400, 1:] = 0.0                    # a 1-D segment
+        xyz[:, 400:500] = xyz[:, 399:400]            # 100 copies of one point
+        xyz[:, 500] = [1e6, -1e6, 1e6]               # far outlier (stretches the Morton box)
+        xyz[:, 600, 0] = np.nan
+        xyz[:, 601, 2] = np.inf
+    else:
+        xyz = _cloud(rng, b, n, kind)
+    exp_idx, exp_temp = oracle.furthest_point_sample(xyz, m, return_temp=True)
+    x = _t(xyz)
+    temp = torch.full((b, n), 1e10, device=dev)
+    idx = torch.empty((b, m), dtype=torch.int32, device=dev)
+    new_xyz = torch.empty((b, m, 3), device=dev)
+    prev = native.set_fps_mode(1)
+    try:
+        native.furthest_point_sampling_gather(b, n, m, x, temp, idx, new_xyz)
+    finally:
+        native.set_fps_mode(prev)
+    np.testing.assert_array_equal(idx.cpu().numpy(), exp_idx)
+    np.testing.assert_array_equal(temp.cpu().numpy(), exp_temp)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), np.take_along_axis(xyz, exp_idx[..., None].astype(np.int64), 1))
+
+
 BQ_CASES = [
     (1, 16384, 4096, 0.8, 32, "scene"), (2, 4096, 1024, 0.5, 16, "scene"), (2, 1024, 256, 1.0, 16, "uniform"),
     (3, 1001, 77, 3.0, 32, "uniform"),   # n*12 not 16-byte aligned for b > 0: exercises the non-TMA staging

@@ -52,7 +52,10 @@ def launches(src, dst, passes):
 def full(reports, dst):
     out = []
     for rep in reports:
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if rep.endswith(".csv"):   # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`)
+            txt = open(rep).read()
+        else:
+            txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
         hdr, units = rows[0], rows[1]
         scale = {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9,
