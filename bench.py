@@ -391,7 +391,11 @@ def run_gpu(args):
         # on its own streams beside the feature phase (ws3d_b200.graphs.StreamedBackboneRunner).  K steps, one event pair.
         from ws3d_b200.graphs import StreamedBackboneRunner
         look = args.inflight - 1
-        sr = StreamedBackboneRunner(model, resident, lookahead=look)
+        sr = StreamedBackboneRunner(model, resident, lookahead=look, feature_streams=args.feature_streams)
+
+        def flush_stream(runner, j):   # the stream the feature phase of step j will run on
+            fs = runner.feature_streams
+            return torch.cuda.current_stream(dev) if fs is None else fs[runner.tail % len(fs)]
         residents = [resident, host_b.to(dev)]
 
         def timed_streamed(sr, steps, from_host):
@@ -403,17 +407,25 @@ def run_gpu(args):
             sync_all()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            for j in range(steps):
-                flush_small.fill_(0)                      # in-stream L2 flush, inside the timed region
-                out = sr.complete()                       # rest of the forward pass of batch j
-                sr.submit(src[(j + look) % 2])            # staging copy + level-1 FPS of batch j + look (own stream)
-                if from_host:
-                    if read_ev[j % 2] is not None:
+            sr.fork()
+
+            def consume(j):
+                def fn(out):
+                    if read_ev[j % 2] is not None:            # the pinned slot of step j-2 has been read by now
                         read_ev[j % 2].synchronize()
-                    pinned[j % 2].copy_(out.sum(dim=(1, 2)), non_blocking=True)
+                    pinned[j % 2].copy_(out.sum(dim=(1, 2)), non_blocking=True)   # per-cloud checksum -> async D2H
                     ev = torch.cuda.Event()
                     ev.record()
                     read_ev[j % 2] = ev
+                return fn
+
+            for j in range(steps):
+                # (the runner alternates consecutive feature phases between its `feature_streams` internal streams)
+                with torch.cuda.stream(flush_stream(sr, j)):
+                    flush_small.fill_(0)                      # in-stream L2 flush, inside the timed region
+                sr.complete(consume(j) if from_host else None)    # feature phase of batch j (+ result read-back)
+                sr.submit(src[(j + look) % 2])                # staging copy + coordinate phase of batch j + look (own stream)
+            sr.join()
             e.record()
             e.synchronize()
             for _ in range(look):                         # drain the batches sampled ahead
@@ -477,7 +489,7 @@ def run_gpu(args):
             o = rpn(pc, plan=plan)
             return o["rpn_cls"], o["rpn_reg"]
 
-        rpn_sr = StreamedBackboneRunner(model, resident, fn=rpn_heads_plan, lookahead=look)
+        rpn_sr = StreamedBackboneRunner(model, resident, fn=rpn_heads_plan, lookahead=look, feature_streams=args.feature_streams)
         timed_streamed(rpn_sr, 3, False)
         ms_rpn = timed_streamed(rpn_sr, args.steps, False)
     if sampler:
@@ -522,8 +534,9 @@ def run_gpu(args):
                        "launch": "one CUDA graph replay per step" if use_graph else "eager launches",
                        "pipeline": ((f"{args.inflight} batches in flight: the coordinate phase (4 FPS levels in throughput mode = one "
                                      f"SM per cloud, ball queries, interpolation stencils) runs {args.inflight - 1} batches ahead on "
-                                     "its own streams beside the graph-replayed feature phase; one batch of 16 clouds completes "
-                                     "per step; K steps under one event pair, L2 flushed in-stream") if deep else
+                                     f"its own streams beside the graph-replayed feature phases, which alternate between "
+                                     f"{args.feature_streams} stream(s); one batch of 16 clouds completes per step; K steps under "
+                                     "one event pair, L2 flushed in-stream") if deep else
                                     ("2 batches in flight: each replay runs level-1 FPS of batch i+1 (high-priority stream) beside "
                                      "the rest of the forward pass of batch i; one batch of 16 clouds completes per step")
                                     if pipelined else "none (one batch in flight)"),
@@ -571,9 +584,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "5")),
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "6")),
                     help=">= 3: coordinate phase (FPS, ball queries, stencils) N-1 batches ahead of the feature phase "
                          "(StreamedBackboneRunner); 2: level-1 FPS of the next batch beside the current batch; 1: no pipeline")
+    ap.add_argument("--feature-streams", type=int, default=int(os.environ.get("WS3D_FEATURE_STREAMS", "2")),
+                    help="streams the feature phases of consecutive batches alternate between (streamed pipeline)")
     ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "0")),
                     help="SMs the persistent MLP kernel spreads over in pipelined mode (0 = all; 84 = the SMs level-1 FPS leaves free)")
     args = ap.parse_args()

@@ -186,6 +186,20 @@ def test_streamed_runner_equals_plain_forward():
     for k, (g, w) in enumerate(zip(got, want)):
         assert torch.equal(g, w), f"batch {k} differs"
     assert native.set_fps_mode(0) == 0          # the runner restores the calling thread's mode
+    # feature phases of consecutive batches on two internal streams; results consumed on those streams
+    runner2 = StreamedBackboneRunner(model, batches[0].to(dev), lookahead=3, feature_streams=2)
+    for k in range(3):
+        runner2.submit(pinned[k])
+    runner2.fork()
+    got2 = []
+    for k in range(len(batches)):
+        got2.append(runner2.complete(consume=lambda o: o.clone()))
+        if k + 3 < len(batches):
+            runner2.submit(pinned[k + 3])
+    runner2.join()
+    torch.cuda.synchronize()
+    for k, (g, w) in enumerate(zip(got2, want)):
+        assert torch.equal(g, w), f"batch {k} differs (two feature streams)"
 
 
 def test_fps_modes_are_bit_identical():

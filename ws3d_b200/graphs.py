@@ -172,12 +172,17 @@ class StreamedBackboneRunner:
     kernels on the same inputs.
     """
 
-    def __init__(self, backbone, example: torch.Tensor, fn: Callable = None, lookahead: int = 3, fps_mode: int = 1,
-                 warmup: int = 2):
+    def __init__(self, backbone, example: torch.Tensor, fn: Callable = None, lookahead: int = 4, fps_mode: int = 1,
+                 feature_streams: int = 1, warmup: int = 2):
         from . import native
         assert example.is_cuda and lookahead >= 1
         dev = example.device
         self.device, self.backbone, self.lookahead = dev, backbone, lookahead
+        # feature_streams > 1: the feature phases of consecutive batches alternate between that many internal streams
+        # (the deeper levels are chains of sub-wave kernels: two batches side by side fill the SMs one leaves idle);
+        # complete(consume=...) then runs the caller's post-processing on the same stream and join() orders the
+        # caller's stream after all of them.  1: the feature phase runs on the caller's current stream.
+        self.feature_streams = ([torch.cuda.Stream(device=dev) for _ in range(feature_streams)] if feature_streams > 1 else None)
         self.fn = fn or (lambda pc, plan: backbone.feature_phase(pc, plan)[1])
         self.nbuf = lookahead + 1
         self.inputs = [example.clone() for _ in range(self.nbuf)]
@@ -247,15 +252,35 @@ class StreamedBackboneRunner:
         self._ready[k] = ev
         self.head += 1
 
-    def complete(self):
-        """Runs the feature phase of the oldest submitted batch (graph replay on the current stream); returns its output."""
+    def complete(self, consume: Callable = None):
+        """Runs the feature phase of the oldest submitted batch (graph replay) and returns its output -- or, with
+        `consume`, the value of consume(output), called on the stream the feature phase runs on (so a reduction or a
+        device-to-host copy of the result is ordered after it without blocking anything else)."""
         assert self.tail < self.head, "nothing submitted"
         k = self.tail % self.nbuf
-        main = torch.cuda.current_stream(self.device)
-        main.wait_event(self._ready[k])
-        self.feat_graphs[k].replay()
-        ev = torch.cuda.Event()
-        ev.record(main)
-        self._done[k] = ev
-        self.tail += 1
-        return self.outputs[k]
+        cur = torch.cuda.current_stream(self.device)
+        st = cur if self.feature_streams is None else self.feature_streams[self.tail % len(self.feature_streams)]
+        with torch.cuda.stream(st):
+            st.wait_event(self._ready[k])
+            self.feat_graphs[k].replay()
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self._done[k] = ev
+            self.tail += 1
+            out = self.outputs[k]
+            return out if consume is None else consume(out)
+
+    def fork(self):
+        """Orders the internal feature streams after the work already queued on the caller's stream."""
+        if self.feature_streams is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            for st in self.feature_streams:
+                st.wait_event(ev)
+
+    def join(self):
+        """Orders the caller's stream after everything queued on the internal feature streams."""
+        if self.feature_streams is not None:
+            cur = torch.cuda.current_stream(self.device)
+            for st in self.feature_streams:
+                cur.wait_stream(st)

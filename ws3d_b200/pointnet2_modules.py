@@ -37,6 +37,15 @@ class _PointnetSAModuleBase(nn.Module):
             cache[k] = fused_mlp.FoldedMLP(self.mlps[k])
         return cache[k]
 
+    def _scale_side_streams(self, xyz):
+        """One extra CUDA stream per scale beyond the first (cached per module and device)."""
+        if not xyz.is_cuda or len(self.groupers) < 2:
+            return None
+        side = self.__dict__.get("_scale_streams")
+        if side is None or side[0].device != xyz.device:
+            side = self.__dict__["_scale_streams"] = [torch.cuda.Stream(device=xyz.device) for _ in self.groupers[1:]]
+        return side
+
     def _neighbour_indices(self, xyz, new_xyz):
         """ball_query for every scale; scales are scanned two at a time."""
         specs = [(g.radius, g.nsample) for g in self.groupers]
@@ -75,12 +84,31 @@ class _PointnetSAModuleBase(nn.Module):
                 cache = self.__dict__.setdefault("_fused_scales", {})
                 widths = [mlp[-1].conv.out_channels for mlp in self.mlps]
                 out = torch.empty((xyz.shape[0], sum(widths), new_xyz.shape[1]), dtype=torch.float32, device=xyz.device)
-                off = 0
+                streams = self._scale_side_streams(xyz) if os.environ.get("WS3D_SCALE_STREAMS", "1") != "0" else None
+                main = torch.cuda.current_stream(xyz.device)
+                if streams:
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                off, joins = 0, []
                 for k, (mlp, idx) in enumerate(zip(self.mlps, indices)):
                     if k not in cache:
                         cache[k] = fused_mlp.FusedSAScale(mlp)
-                    cache[k](xyz, new_xyz, features, idx, out, off)
+                    if streams and k > 0:
+                        st = streams[k - 1]
+                        st.wait_event(fork)
+                        with torch.cuda.stream(st):
+                            cache[k](xyz, new_xyz, features, idx, out, off)
+                            done = torch.cuda.Event()
+                            done.record(st)
+                        for t in (xyz, new_xyz, features, idx, out):
+                            if t is not None:
+                                t.record_stream(st)
+                        joins.append(done)
+                    else:
+                        cache[k](xyz, new_xyz, features, idx, out, off)
                     off += widths[k]
+                for ev in joins:
+                    main.wait_event(ev)
                 return new_xyz, out
         # inference, several scales: the scales are independent chains of small launches (group + three layers, each
         # well under one wave at the deeper levels), so they run side by side on per-scale streams
@@ -88,9 +116,7 @@ class _PointnetSAModuleBase(nn.Module):
         if (fused and len(self.groupers) > 1 and xyz.is_cuda and self.npoint is not None
                 and all(fused_mlp.supported(new_xyz.shape[1] * g.nsample, g.nsample) for g in self.groupers)
                 and os.environ.get("WS3D_SCALE_STREAMS", "1") != "0"):
-            side = self.__dict__.get("_scale_streams")
-            if side is None or side[0].device != xyz.device:
-                side = self.__dict__["_scale_streams"] = [torch.cuda.Stream(device=xyz.device) for _ in self.groupers[1:]]
+            side = self._scale_side_streams(xyz)
             main = torch.cuda.current_stream(xyz.device)
             fork = torch.cuda.Event()
             fork.record(main)
