@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="scenes per GPU")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the whole training step (forward, loss, backward, Adam) as one "
+                                                         "CUDA graph (single GPU); 0: eager launches")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -41,7 +43,8 @@ def main():
     net = models.RPN().to(dev).train()
     n_param_bytes = sum(p.numel() for p in net.parameters()) * 4
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
-    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    use_graph = bool(args.graph) and world == 1
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3, capturable=use_graph)
     pts = torch.from_numpy(synth.make_batch(args.batch, 16384, first_scene=rank * args.batch)).to(dev)
     g = torch.Generator(device="cpu").manual_seed(rank)
     cls_label = (torch.rand(args.batch, 16384, generator=g) < 0.05).float().to(dev)
@@ -62,6 +65,24 @@ def main():
         opt.step()
         return loss
 
+    if use_graph:
+        # ~2000 launches per step (this library's ops + cuDNN / ATen kernels of the MLPs, their backward and Adam): eager,
+        # the host cannot issue them as fast as the GPU retires them.  The step has static shapes, so it is captured once.
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(args.warmup, 3)):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = step()
+        eager_step = step
+
+        def step():   # noqa: F811
+            graph.replay()
+            return static_loss
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -84,7 +105,8 @@ def main():
                           "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "ms_per_step": round(ms, 3), "scaling": "weak",
                           "config": {"scenes_per_gpu": args.batch, "points_per_scene": 16384, "optimizer": "Adam", "collective":
                                      "DDP gradient all-reduce (NCCL), %.2f MB fp32" % (n_param_bytes / 1e6) if world > 1 else "none (1 GPU)",
-                                     "mlp": "PyTorch/cuDNN (training: batch-norm statistics, autograd)"},
+                                     "mlp": "PyTorch/cuDNN (training: batch-norm statistics, autograd)",
+                                     "launch": "one CUDA graph replay per training step" if use_graph else "eager launches"},
                           "final_loss": round(float(loss), 4), "gpu_launches": int(_C.launch_count() - l0)}), flush=True)
     if world > 1:
         dist.destroy_process_group()

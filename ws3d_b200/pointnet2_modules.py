@@ -23,6 +23,15 @@ from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
 
+def _train_channels_last(x: torch.Tensor) -> bool:
+    """Training-mode shared MLPs run on channels-last activations (WS3D_TRAIN_CHANNELS_LAST=0 keeps NCHW).
+    Measured on B200 (tools/train_profile.py): on the NCHW (B, C, npoint, nsample) tensors cuDNN's training BatchNorm
+    takes `bn_fw_tr_1C11` / `bn_bw_1C11`, one thread block per channel -- 31 of the 55 ms of a Stage-1 RPN training step
+    (ATen's native kernels are slower still: 41 ms); channels-last selects the NHWC semi-persistent kernels (6 ms) and
+    the 1x1 convolutions become plain GEMMs: 55 -> 31 ms per step."""
+    return x.is_cuda and torch.is_grad_enabled() and os.environ.get("WS3D_TRAIN_CHANNELS_LAST", "1") != "0"
+
+
 class _PointnetSAModuleBase(nn.Module):
     def __init__(self):
         super().__init__()
@@ -143,6 +152,10 @@ class _PointnetSAModuleBase(nn.Module):
                 # inference: every layer is one tensor-core launch; the last one also max-pools over nsample
                 pooled.append(self._folded(k)(grouped.view(B, C, M * K), pool=K))
                 continue
+            if _train_channels_last(grouped):
+                # training: NHWC activations -- the 1x1 convolutions become plain GEMMs and BatchNorm reduces over the
+                # contiguous channel vectors instead of cuDNN's one-thread-block-per-channel NCHW kernels
+                grouped = grouped.contiguous(memory_format=torch.channels_last)
             grouped = mlp(grouped)
             if self.pool_method == 'max_pool':
                 grouped = F.max_pool2d(grouped, kernel_size=[1, grouped.size(3)])
@@ -150,7 +163,7 @@ class _PointnetSAModuleBase(nn.Module):
                 grouped = F.avg_pool2d(grouped, kernel_size=[1, grouped.size(3)])
             else:
                 raise NotImplementedError
-            pooled.append(grouped.squeeze(-1))
+            pooled.append(grouped.squeeze(-1).contiguous())
         return new_xyz, torch.cat(pooled, dim=1)
 
 
@@ -215,4 +228,7 @@ class PointnetFPModule(nn.Module):
             skip = None if unknow_feats is None else unknow_feats.contiguous()
             return folded(interpolated, skip)
         new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
-        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+        new_features = new_features.unsqueeze(-1)
+        if _train_channels_last(new_features):
+            new_features = new_features.contiguous(memory_format=torch.channels_last)
+        return self.mlp(new_features).squeeze(-1).contiguous()
