@@ -48,13 +48,14 @@ void *scratch(size_t bytes, int slot) {
   std::lock_guard<std::mutex> lk(g_mu);
   Slot &s = g_slots[dev][g_arena][slot];
   if (s.cap < bytes) {
-    if (s.p) {
-      cudaDeviceSynchronize();  // earlier work may still be using the old buffer
-      cudaFree(s.p);
-      s.p = nullptr;
-      s.cap = 0;
-    }
+    // A buffer that is outgrown is RETIRED, not freed: launches already queued and -- more importantly -- captured
+    // CUDA graphs (graphs.py) hold its address for as long as they live.  Buffers grow geometrically, so the retired
+    // ones add up to less than the live one.
+    const size_t old_cap = s.cap;
+    s.p = nullptr;
+    s.cap = 0;
     size_t want = bytes + (bytes >> 2);
+    if (want < 2 * old_cap) want = 2 * old_cap;
     cudaError_t e = cudaMalloc(&s.p, want);
     if (e != cudaSuccess) {
       set_error("scratch: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
