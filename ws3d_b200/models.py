@@ -207,7 +207,25 @@ class RPN(nn.Module):
             backbone_xyz, backbone_features = self.backbone_net.feature_phase(pts_input, plan)
         else:
             backbone_xyz, backbone_features = self.backbone_net(pts_input, first_samples=first_samples)
-        rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
-        rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()
+        if (backbone_features.is_cuda and fused_mlp.enabled_for(self) and os.environ.get("WS3D_SCALE_STREAMS", "1") != "0"):
+            # inference: the two heads are independent chains of two launches each -> side by side on two streams
+            main = torch.cuda.current_stream(backbone_features.device)
+            side = self.__dict__.get("_head_stream")
+            if side is None or side.device != backbone_features.device:
+                side = self.__dict__["_head_stream"] = torch.cuda.Stream(device=backbone_features.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()
+                done = torch.cuda.Event()
+                done.record(side)
+            backbone_features.record_stream(side)
+            rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
+            rpn_reg.record_stream(main)
+            main.wait_event(done)
+        else:
+            rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
+            rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()
         return {'rpn_cls': rpn_cls, 'rpn_reg': rpn_reg, 'backbone_xyz': backbone_xyz,
                 'backbone_features': backbone_features}
