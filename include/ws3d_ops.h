@@ -233,6 +233,19 @@ int ws3d_radius_nms(const float *centers, int n, float radius, int64_t *keep, in
 int ws3d_cylinder_query(int n, int m, int cap, float radius, const float *pts, const float *centers,
                         int *idx, int *cnt, unsigned char *any, ws3d_stream_t stream);
 
+/* Extension (row f4): Stage-1 training labels, KittiRCNNDataset.generate_gaussian_training_labels
+ * (lib/datasets/kitti_rcnn_dataset.py:529-573), batched.  pts (B,n,3) rect-camera points, gt_boxes3d
+ * (B,g_max,7) [x,y,z,h,w,l,ry] padded, num_gt (B) valid boxes per scene (NULL = g_max everywhere;
+ * g_max <= 512).  Per point: d_k = sqrt((x-bx)^2 + (y*gauss_height)^2 + (z-bz)^2) in float32 as numpy
+ * evaluates it; cls_label (B,n) = exp(-m^2 / (2 gauss_cov)) with m = min_k clip(d_k - gauss_status,
+ * 0, 100) (the scipy Gaussian of :563-564, float64 inside, stored as float32); reg_label (B,n,3) =
+ * (bx - x, 0, bz - z) of the nearest box where min_k d_k < fg_radius (4.0 there), else 0.  Scenes
+ * without boxes get zeros.  cfg defaults: gauss_height 0.707, gauss_status 0.7, gauss_cov 1.5. */
+int ws3d_gaussian_rpn_labels(int b, int n, int g_max, const float *pts, const float *gt_boxes3d,
+                             const int *num_gt, float gauss_height, float gauss_status,
+                             float gauss_cov, float fg_radius, float *cls_label, float *reg_label,
+                             ws3d_stream_t stream);
+
 /* ---- roipool3d_cuda -------------------------------------------------------- */
 
 /* Replaces roipool3dLauncher (lib/utils/roipool3d/src/roipool3d.cpp:12-13,

@@ -243,3 +243,13 @@ def cylinder_query(pts, centers, radius, cap):
     lib().oracle_cylinder_query(p.shape[0], c.shape[0], int(cap), ctypes.c_float(radius), _p(p), _p(c), _p(idx), _p(cnt),
                                 _p(any_))
     return idx, cnt, any_
+
+
+def gaussian_rpn_labels(pts_rect, gt_boxes3d, gauss_height=0.707, gauss_status=0.7, gauss_cov=1.5, fg_radius=4.0):
+    """kitti_rcnn_dataset.py:529-573 for one scene: pts (n,3), boxes (g,7) -> cls (n) float64, reg (n,3) float32."""
+    p, b = _f(pts_rect), _f(gt_boxes3d).reshape(-1, 7)
+    cls = np.zeros(p.shape[0], dtype=np.float64)
+    reg = np.zeros((p.shape[0], 3), dtype=np.float32)
+    lib().oracle_gaussian_rpn_labels(p.shape[0], b.shape[0], _p(p), _p(b), ctypes.c_float(gauss_height), ctypes.c_float(gauss_status),
+                                     ctypes.c_double(gauss_cov), ctypes.c_float(fg_radius), _p(cls), _p(reg))
+    return cls, reg

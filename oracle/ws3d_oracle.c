@@ -682,3 +682,36 @@ ORACLE_API void oracle_cylinder_query(int n, int m, int cap, float radius, const
     cnt[c] = k;
   }
 }
+
+/* Row f4: KittiRCNNDataset.generate_gaussian_training_labels (lib/datasets/kitti_rcnn_dataset.py:529-573) for one
+ * scene.  pts (n,3), boxes (g,7).  float32 arithmetic as numpy runs it -- np.power(v, 2) rounds like v * v, the Python
+ * float constants meet float32 arrays as float32 -- and the Gaussian in double:
+ * multivariate_normal.pdf(d, 0, cov) / (1 / sqrt(2 pi cov)) = exp(-d^2 / (2 cov)).  cls (n) double, reg (n,3) float. */
+ORACLE_API void oracle_gaussian_rpn_labels(int n, int g, const float *pts, const float *boxes, float gauss_height,
+                                           float gauss_status, double gauss_cov, float fg_radius, double *cls, float *reg) {
+  for (int i = 0; i < n; ++i) {
+    const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    const float hy = y * gauss_height;
+    const float hy2 = hy * hy;
+    float centre_dist = 100.0f, best = 0.0f;
+    int target = -1;
+    for (int k = 0; k < g; ++k) {
+      const float dx = x - boxes[7 * k], dz = z - boxes[7 * k + 2];
+      const float s = (dx * dx + hy2) + dz * dz;                       /* :545-548 */
+      const float d = sqrtf(s);
+      float c = d - gauss_status;                                      /* :550 np.clip(d - status, 0, 100) */
+      c = c < 0.0f ? 0.0f : (c > 100.0f ? 100.0f : c);
+      if (c < centre_dist) centre_dist = c;                            /* np.minimum */
+      if (target < 0 || d < best) { best = d; target = k; }            /* :561-562 min / first argmin */
+    }
+    cls[i] = 0.0;
+    reg[3 * i] = reg[3 * i + 1] = reg[3 * i + 2] = 0.0f;
+    if (g > 0) {
+      cls[i] = exp(-0.5 * (double)centre_dist * (double)centre_dist / gauss_cov);   /* :563-564 */
+      if (best < fg_radius) {                                          /* :568-572 */
+        reg[3 * i] = boxes[7 * target] - x;
+        reg[3 * i + 2] = boxes[7 * target + 2] - z;
+      }
+    }
+  }
+}

@@ -164,3 +164,33 @@ def test_cylinder_crop_edge_cases():
     assert idx.shape == (0, 5) and not bool(any_.any())
     idx, cnt, any_ = proposal_utils.cylinder_crop(pts[:0], cen, 4.0, cap=4)
     assert cnt.tolist() == [0, 0, 0]
+
+
+def test_gaussian_labels_match_golden_and_oracle():
+    """Row f4: ws3d_gaussian_rpn_labels against the reference's generate_gaussian_training_labels (fixture) and the
+    oracle: reg_label bit-exact, cls_label to float32 rounding (float64 in the reference); batched with padded boxes."""
+    from ws3d_b200 import label_utils, synth
+    g = np.load(GOLD)
+    pts, boxes = torch.from_numpy(g["f4_points"]).to(dev), torch.from_numpy(g["f4_boxes"]).to(dev)
+    cls, reg = label_utils.generate_gaussian_training_labels(pts, boxes)
+    np.testing.assert_array_equal(reg.cpu().numpy(), g["f4_reg"])
+    np.testing.assert_allclose(cls.cpu().numpy(), g["f4_cls"], rtol=0, atol=1e-6)
+    cls0, reg0 = label_utils.generate_gaussian_training_labels(pts[:100], boxes[:0])
+    assert float(cls0.abs().max()) == 0.0 and float(reg0.abs().max()) == 0.0
+    # a batch of three scenes with different numbers of (padded) boxes, n not a multiple of the block size
+    rng = np.random.default_rng(4)
+    scenes = np.stack([synth.make_scene(30 + k)[:5000, :3] for k in range(3)])
+    counts = [9, 0, 23]
+    padded = np.zeros((3, 23, 7), np.float32)
+    for k, c in enumerate(counts):
+        padded[k, :c] = synth.make_boxes(scenes[k], c, seed=k) if c else 0
+        padded[k, c:] = rng.normal(0, 50, (23 - c, 7))                       # garbage in the padding must be ignored
+    cls, reg = label_utils.generate_gaussian_training_labels(torch.from_numpy(scenes).to(dev), torch.from_numpy(padded).to(dev),
+                                                             num_gt=torch.tensor(counts))
+    for k, c in enumerate(counts):
+        ocls, oreg = oracle.gaussian_rpn_labels(scenes[k], padded[k, :c])
+        np.testing.assert_array_equal(reg[k].cpu().numpy(), oreg)
+        np.testing.assert_allclose(cls[k].cpu().numpy(), ocls, rtol=0, atol=1e-6)
+    assert float(cls[1].abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        label_utils.generate_gaussian_training_labels(torch.from_numpy(scenes).to(dev), torch.zeros(3, 600, 7, device=dev))

@@ -75,3 +75,17 @@ def test_next_rows_f2_f3_match_reference_python():
     np.testing.assert_array_equal(cnt, g["f3_cnt"])
     np.testing.assert_array_equal(idx, g["f3_idx"])
     np.testing.assert_array_equal(any_, g["f3_any"])
+
+
+def test_next_row_f4_gaussian_labels_match_reference_python():
+    """oracle_gaussian_rpn_labels against the output of the reference's own
+    generate_gaussian_training_labels (executed from its source text by tools/make_golden_next.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "next_rows.npz"))
+    cls, reg = oracle.gaussian_rpn_labels(g["f4_points"], g["f4_boxes"])
+    np.testing.assert_array_equal(reg, g["f4_reg"])                        # float32 arithmetic: bit-exact
+    np.testing.assert_allclose(cls, g["f4_cls"], rtol=0, atol=1e-12)       # scipy's float64 Gaussian vs exp(-d^2 / 2 cov)
+    assert 0 < int((reg[:, 0] != 0).sum()) < reg.shape[0] and float(cls.max()) == 1.0
+    cls0, reg0 = oracle.gaussian_rpn_labels(g["f4_points"][:100], g["f4_boxes"][:0])
+    np.testing.assert_array_equal(cls0, g["f4_cls_empty"])
+    np.testing.assert_array_equal(reg0, g["f4_reg_empty"])

@@ -10,6 +10,10 @@ reference's own Python (read from /root/reference at generation time; nothing is
       time, which is stripped), driven by the radius-NMS loop and the cylinder membership test of
       tools/eval_auto.py:272-279,:289-291,:327-343 (script-level code there, transcribed below line by line).
 
+  f4  lib/datasets/kitti_rcnn_dataset.py::KittiRCNNDataset.generate_gaussian_training_labels: a static method of a
+      module that cannot be imported here (easydict, matplotlib, cv2, a .cuda() call at import time), so its source
+      text is cut out of the file and executed as it stands, with `cfg` = the three constants of lib/config.py:45-47.
+
     python tools/make_golden_next.py      ->  tests/golden/next_rows.npz
 """
 import os
@@ -48,6 +52,22 @@ def load_reference_distance_2():
     ns = {"torch": torch}
     exec(line.replace(".cuda()", ""), ns)
     return ns["distance_2"]
+
+
+def load_reference_gaussian_labels():
+    import math
+    import textwrap
+    from scipy.stats import multivariate_normal
+    src = open(os.path.join(REF, "lib/datasets/kitti_rcnn_dataset.py")).read()
+    a = src.index("    def generate_gaussian_training_labels(")
+    b = src.index("    def generate_rpn_training_labels(")
+    body = textwrap.dedent(src[a:b])
+    cfg_src = open(os.path.join(REF, "lib/config.py")).read()
+    vals = {k: float(re.search(r"__C\.RPN\.%s = ([0-9.]+)" % k, cfg_src).group(1)) for k in ("GAUSS_HEIGHT", "GAUSS_STATUS", "GAUSS_COV")}
+    cfg = types.SimpleNamespace(RPN=types.SimpleNamespace(**vals))
+    ns = {"np": np, "math": math, "multivariate_normal": multivariate_normal, "cfg": cfg}
+    exec(body, ns)
+    return ns["generate_gaussian_training_labels"], vals
 
 
 def main():
@@ -108,6 +128,17 @@ def main():
         w = np.nonzero(member[:, c])[0][:cap]
         idx[c, :len(w)] = w
     out["f3_idx"] = idx
+    # ---- f4
+    labels_fn, cfg_vals = load_reference_gaussian_labels()
+    assert cfg_vals == {"GAUSS_HEIGHT": 0.707, "GAUSS_STATUS": 0.7, "GAUSS_COV": 1.5}, cfg_vals
+    scene4 = synth.make_scene(12)[:, :3].copy()
+    gt = synth.make_boxes(scene4, 14, seed=21)
+    gt[3] = gt[2]                                    # duplicate box: argmin must take the first
+    cls4, reg4 = labels_fn(scene4, gt)
+    out["f4_points"], out["f4_boxes"] = scene4, gt
+    out["f4_cls"], out["f4_reg"] = np.asarray(cls4, dtype=np.float64), np.asarray(reg4, dtype=np.float32)
+    cls0, reg0 = labels_fn(scene4[:100], gt[:0])     # a scene without boxes
+    out["f4_cls_empty"], out["f4_reg_empty"] = np.asarray(cls0, dtype=np.float64), np.asarray(reg0, dtype=np.float32)
     path = os.path.join(ROOT, "tests", "golden", "next_rows.npz")
     np.savez_compressed(path, **out)
     print(path, {k: v.shape for k, v in out.items()}, "kept", len(keep_id), "max cnt", int(out["f3_cnt"].max()))

@@ -86,6 +86,22 @@ def main():
                 "reference_dense_matrix_ms": ev_time(dense)}
         out[f"cylinder_crop_p{p}"] = rec2
         print(p, rec2, flush=True)
+    # f4: Gaussian RPN labels for a batch of 16 scenes x 16384 points x 24 boxes, next to the reference's per-sample numpy
+    from ws3d_b200 import label_utils
+    scenes = np.stack([synth.make_scene(40 + k)[:, :3] for k in range(16)])
+    gts = np.stack([synth.make_boxes(scenes[k], 24, seed=k) for k in range(16)])
+    tp, tg = torch.from_numpy(scenes).to(dev), torch.from_numpy(gts).to(dev)
+    rec = {"gpu_batch16_ms": ev_time(lambda: label_utils.generate_gaussian_training_labels(tp, tg))}
+    t0 = time.perf_counter()
+    for k in range(16):   # numpy restatement of kitti_rcnn_dataset.py:529-573 (same operations, one scene at a time, host)
+        d = np.sqrt((scenes[k][:, None, 0] - gts[k][None, :, 0]) ** 2 + ((scenes[k][:, 1] * 0.707) ** 2)[:, None]
+                    + (scenes[k][:, None, 2] - gts[k][None, :, 2]) ** 2)
+        m = np.minimum(100.0, np.clip(d - 0.7, 0, 100).min(1))
+        _ = np.exp(-0.5 * m.astype(np.float64) ** 2 / 1.5)
+        _ = d.argmin(1)
+    rec["numpy_host_batch16_ms"] = (time.perf_counter() - t0) * 1e3
+    out["gaussian_labels_b16_n16384_g24"] = rec
+    print(rec, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "next_rows_bench.json"), "w"), indent=1)
 

@@ -216,6 +216,17 @@ def cylinder_query(pts, centers, radius, idx, cnt, any_flag=None):
                                         ptr(idx), ptr(cnt), ptr(any_flag), stream()), "cylinder_query")
 
 
+def gaussian_rpn_labels(pts, gt_boxes3d, num_gt, gauss_height, gauss_status, gauss_cov, fg_radius, cls_label, reg_label):
+    """Extension: pts (B,n,3), gt_boxes3d (B,G,7), num_gt (B) int32 or None -> cls_label (B,n), reg_label (B,n,3)."""
+    _check_boxes(pts, gt_boxes3d, num_gt, cls_label, reg_label)
+    if pts.dim() != 3 or pts.size(2) != 3 or gt_boxes3d.dim() != 3 or gt_boxes3d.size(2) != 7 or gt_boxes3d.size(0) != pts.size(0):
+        raise RuntimeError("gaussian_rpn_labels: pts must be (B, n, 3) and gt_boxes3d (B, G, 7)")
+    with device_of(pts):
+        check(lib().ws3d_gaussian_rpn_labels(pts.size(0), pts.size(1), gt_boxes3d.size(1), ptr(pts), ptr(gt_boxes3d), ptr(num_gt),
+                                             float(gauss_height), float(gauss_status), float(gauss_cov), float(fg_radius),
+                                             ptr(cls_label), ptr(reg_label), stream()), "gaussian_rpn_labels")
+
+
 # ---- roipool3d_cuda ---------------------------------------------------------------------------
 def roipool3d_forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
     """Reference `forward` (roipool3d.cpp:48): xyz (B,N,3), boxes3d (B,M,7), pts_feature (B,N,C),
