@@ -142,6 +142,17 @@ int ws3d_three_interpolate(int b, int c, int m, int n, const float *points, cons
 int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                 const float *weight, float *grad_points, ws3d_stream_t stream);
 
+/* Extension: three_interpolate with an affine epilogue,
+ *   out[b,c,i] = act( sum_k weight[b,i,k] * points[b,c,idx[b,i,k]] + scale1[c] * row1[b,i] + shift[c] ),
+ * scale1 (c) and row1 (B,n) optional (both or neither), shift (c) optional; flags bit 0 = ReLU, bit 1 =
+ * round the result to TF32.  The stencil weights do not depend on the channel, so the interpolated part
+ * of a feature-propagation layer's first 1x1 convolution (pointnet2_modules.py:139-154) can be applied
+ * to the KNOWN points (m, typically n / 4 columns) and its product interpolated: interp(W f) = W interp(f).
+ * Shapes served: m <= 8192, n >= 256, c % 4 == 0 (others: invalid argument). */
+int ws3d_three_interpolate_affine(int b, int c, int m, int n, const float *points, const int *idx,
+                                  const float *weight, const float *scale1, const float *row1,
+                                  const float *shift, int flags, float *out, ws3d_stream_t stream);
+
 /* Extension: one shared-MLP layer -- 1x1 conv with BatchNorm(eval) folded
  * in, optional ReLU, optional max-pool over runs of `pool` consecutive columns -- on the tcgen05 tensor
  * cores (TF32 inputs, FP32 accumulate), replacing the conv / BN / ReLU / max-pool kernel sequence of

@@ -160,3 +160,63 @@ def test_fused_sa_scale_matches_module_fp32_path(n, m, c, radii, nsamples, mlps,
     with torch.no_grad():
         layered = sa(xyz, feat, new_xyz=new_xyz)[1]
     assert float((got - layered).abs().max()) <= TOL * scale + 1e-4
+
+
+def test_three_interpolate_affine_epilogue():
+    """ws3d_three_interpolate_affine = three_interpolate + scale1[c] * row1 + shift[c] (+ ReLU, + TF32 rounding)."""
+    from ws3d_b200 import native, pointnet2_utils
+    torch.manual_seed(3)
+    B, c, m, n = 2, 24, 512, 2048
+    pts = torch.randn(B, c, m, device=dev)
+    idx = torch.randint(0, m, (B, n, 3), device=dev, dtype=torch.int32)
+    w = torch.rand(B, n, 3, device=dev)
+    w = w / w.sum(-1, keepdim=True)
+    scale1, row1, shift = torch.randn(c, device=dev), torch.randn(B, n, device=dev), torch.randn(c, device=dev)
+    base = pointnet2_utils.three_interpolate(pts, idx, w)
+    out = torch.empty_like(base)
+    native.three_interpolate_affine(B, c, m, n, pts, idx, w, None, None, None, 0, out)
+    assert torch.equal(out, base)                                   # no epilogue: the plain kernel
+    native.three_interpolate_affine(B, c, m, n, pts, idx, w, scale1, row1, shift, 1, out)
+    want = torch.relu(base + scale1[None, :, None] * row1[:, None, :] + shift[None, :, None])
+    assert float((out - want).abs().max()) < 1e-5
+    native.three_interpolate_affine(B, c, m, n, pts, idx, w, None, None, shift, 2, out)
+    assert int((out.view(torch.int32) & 0x1FFF).abs().max()) == 0   # rounded to TF32
+    assert float((out - (base + shift[None, :, None])).abs().max()) < 2e-3 * float(base.abs().max())
+    with pytest.raises(RuntimeError):
+        native.three_interpolate_affine(B, 6, m, n, pts[:, :6].contiguous(), idx, w, None, None, shift[:6].contiguous(), 0,
+                                        out[:, :6].contiguous())     # c % 4 != 0 is not served
+
+
+@pytest.mark.parametrize("c_known,c_skip,spec,m,n", [(256, 1, (257, 128, 128), 1024, 4096), (64, 0, (64, 32, 48), 512, 1024),
+                                                     (40, 1, (41, 24), 256, 300)])
+def test_fp_module_premultiplied_first_layer(c_known, c_skip, spec, m, n, monkeypatch):
+    """PointnetFPModule with a thin skip input: W_a applied to the known points, the product interpolated, skip term +
+    shift + ReLU in the interpolation epilogue -- against the module's FP32 PyTorch path and the per-layer path."""
+    from ws3d_b200 import pointnet2_modules, synth
+    torch.manual_seed(c_known + n)
+    fp = pointnet2_modules.PointnetFPModule(mlp=list(spec)).to(dev).eval()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for mod in fp.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.2)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.bias.shape, generator=g) * 0.2)
+    pts = torch.from_numpy(synth.make_batch(2, n)[..., :3].copy()).to(dev)
+    known = pts[:, :m].contiguous()
+    kf = torch.randn(2, c_known, m, device=dev)
+    sf = torch.randn(2, c_skip, n, device=dev) if c_skip else None
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        want = fp(pts, known, sf, kf)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    with torch.no_grad():
+        got = fp(pts, known, sf, kf)
+    assert "_premul" in fp.__dict__ and got.shape == want.shape
+    scale = float(want.abs().max()) + 1e-6
+    assert float((got - want).abs().max()) <= TOL * scale + 1e-4, float((got - want).abs().max()) / scale
+    monkeypatch.setenv("WS3D_FP_PREMUL", "0")
+    with torch.no_grad():
+        layered = fp(pts, known, sf, kf)
+    assert float((got - layered).abs().max()) <= TOL * scale + 1e-4

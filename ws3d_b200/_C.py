@@ -35,6 +35,7 @@ _SIGNATURES = {
     "ws3d_group_concat": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "ws3d_three_interpolate_affine": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "ws3d_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_mlp_layer": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ws3d_sa_mlp_fused_supported": [_i, _i, _i, _i, _i],

@@ -420,9 +420,21 @@ __global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem_ker
 // serves four channels.  The gathers are random in k, so a 4-byte read per lane costs ~3.5 bank-conflict
 // wavefronts per warp instruction; a 16-byte read is issued per quarter warp and costs ~1.6 per 8 lanes,
 // i.e. less than half the shared-memory time per output (the kernel's bottleneck in ncu: 22 % DRAM).
+// Optional epilogue (EPI): out = act(interp + scale1[c] * row1[b, i] + shift[c]), flags bit 0 = ReLU, bit 1 = round the
+// result to TF32.  It lets a feature-propagation layer apply the interpolated part of its first 1x1 convolution to the
+// KNOWN points (4x fewer columns) and interpolate the product: conv(interp(f)) = interp(conv(f)) because the stencil
+// weights do not depend on the channel (ws3d_three_interpolate_affine).
+struct InterpEpilogue {
+  const float *scale1;   // (c) or null
+  const float *row1;     // (B, n) or null
+  const float *shift;    // (c) or null
+  int flags;
+};
+
+template <bool EPI>
 __global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem4_kernel(
     int c, int m, int n, int cb, int n_per_cta, const float *__restrict__ points, const int *__restrict__ idx,
-    const float *__restrict__ weight, float *__restrict__ out) {
+    const float *__restrict__ weight, float *__restrict__ out, InterpEpilogue epi) {
   extern __shared__ __align__(16) float s_rows[];  // (cb/4) groups x m x 4
   const size_t cloud = blockIdx.z;
   const int c0 = blockIdx.x * cb, cn = min(cb, c - c0);  // cn % 4 == 0 (host guarantees c % 4 == 0 and cb % 4 == 0)
@@ -456,14 +468,29 @@ __global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem4_ke
       v0 = __ldg(wp); v1 = __ldg(wp + 1); v2 = __ldg(wp + 2);
     }
     float *o = out + (cloud * (size_t)c + c0) * n + i;
+    const float r1 = (EPI && epi.row1) ? __ldg(epi.row1 + cloud * (size_t)n + i) : 0.f;
 #pragma unroll 2
     for (int g = 0; g < (cn >> 2); ++g) {
       const float4 *row = s4 + (size_t)g * m;
       const float4 p0 = row[i0], p1 = row[i1], p2 = row[i2];
-      __stcs(o + (size_t)(g * 4 + 0) * n, __fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x))));
-      __stcs(o + (size_t)(g * 4 + 1) * n, __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y))));
-      __stcs(o + (size_t)(g * 4 + 2) * n, __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z))));
-      __stcs(o + (size_t)(g * 4 + 3) * n, __fmaf_rn(w2, p2.w, __fmaf_rn(w0, p0.w, __fmul_rn(w1, p1.w))));
+      float v[4] = {__fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x))),
+                    __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y))),
+                    __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z))),
+                    __fmaf_rn(w2, p2.w, __fmaf_rn(w0, p0.w, __fmul_rn(w1, p1.w)))};
+      if (EPI) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = c0 + g * 4 + q;
+          if (epi.scale1) v[q] = fmaf(__ldg(epi.scale1 + ch), r1, v[q]);
+          if (epi.shift) v[q] += __ldg(epi.shift + ch);
+          if (epi.flags & 1) v[q] = fmaxf(v[q], 0.f);
+          if (epi.flags & 2) v[q] = __uint_as_float((__float_as_uint(v[q]) + 0x1000u) & 0xFFFFE000u);
+        }
+      }
+      __stcs(o + (size_t)(g * 4 + 0) * n, v[0]);
+      __stcs(o + (size_t)(g * 4 + 1) * n, v[1]);
+      __stcs(o + (size_t)(g * 4 + 2) * n, v[2]);
+      __stcs(o + (size_t)(g * 4 + 3) * n, v[3]);
     }
     i0 = j0; i1 = j1; i2 = j2; w0 = v0; w1 = v1; w2 = v2;
   }
@@ -556,8 +583,8 @@ WS3D_API int ws3d_three_nn(int b, int n, int m, const float *unknown, const floa
   return check_launch("three_nn");
 }
 
-WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
-                                    const float *weight, float *out, ws3d_stream_t stream) {
+static int three_interpolate_impl(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                                  float *out, const InterpEpilogue *epi, ws3d_stream_t stream) {
   if (b < 0 || c < 0 || m < 0 || n < 0) return fail_arg("three_interpolate");
   if (b == 0 || c == 0 || n == 0) return 0;
   if (!points || !idx || !weight || !out) return fail_arg("three_interpolate (null pointer)");
@@ -568,6 +595,7 @@ WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *poi
     if (cb > 64) cb = 64;
     if (cb > c) cb = c;
     while (cb > 8 && (long long)ceil_div(c, cb) * b < 2LL * kNumSMs) cb >>= 1;
+    if (c % 4 == 0 && cb % 4 != 0) cb = cb > 4 ? (cb & ~3) : 4;   // keep the four-channel interleaved kernel available
     const int chunks = ceil_div(c, cb);
     int nsplit = 1;
     while ((long long)chunks * b * nsplit < 2LL * kNumSMs && ceil_div(n, nsplit * 2) >= 2 * 512) nsplit <<= 1;
@@ -577,13 +605,15 @@ WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *poi
     cudaError_t e = cudaFuncSetAttribute(three_interpolate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("three_interpolate: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     if (chunks <= 65535 * 32 && nsplit <= 65535 && c % 4 == 0 && cb % 4 == 0) {
-      e = cudaFuncSetAttribute(three_interpolate_smem4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      auto kern = epi ? three_interpolate_smem4_kernel<true> : three_interpolate_smem4_kernel<false>;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("three_interpolate: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
       dim3 grid((unsigned)chunks, (unsigned)nsplit, (unsigned)b);
-      three_interpolate_smem4_kernel<<<grid, threads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx,
-                                                                                          weight, out);
+      const InterpEpilogue none = {nullptr, nullptr, nullptr, 0};
+      kern<<<grid, threads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx, weight, out, epi ? *epi : none);
       return check_launch("three_interpolate");
     }
+    if (epi) return fail_arg("three_interpolate_affine (needs c % 4 == 0)");
     if (chunks <= 65535 * 32 && nsplit <= 65535) {
       dim3 grid((unsigned)chunks, (unsigned)nsplit, (unsigned)b);
       three_interpolate_smem_kernel<<<grid, threads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx,
@@ -591,9 +621,26 @@ WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *poi
       return check_launch("three_interpolate");
     }
   }
+  if (epi) return fail_arg("three_interpolate_affine (shape outside the shared-memory kernel: m <= 8192, n >= 256, c % 4 == 0)");
   dim3 grid((unsigned)ceil_div(n, kInterpThreads), (unsigned)ceil_div(c, kInterpChannels), (unsigned)b);
   three_interpolate_kernel<<<grid, kInterpThreads, 0, to_stream(stream)>>>(c, m, n, points, idx, weight, out);
   return check_launch("three_interpolate");
+}
+
+WS3D_API int ws3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                                    const float *weight, float *out, ws3d_stream_t stream) {
+  return three_interpolate_impl(b, c, m, n, points, idx, weight, out, nullptr, stream);
+}
+
+// Extension: three_interpolate with an affine epilogue,
+//   out[b,c,i] = act( sum_k weight[b,i,k] * points[b,c,idx[b,i,k]] + scale1[c] * row1[b,i] + shift[c] ),
+// scale1 / row1 / shift optional; flags bit 0 = ReLU, bit 1 = round to TF32.  Shapes served: m <= 8192, n >= 256, c % 4 == 0.
+WS3D_API int ws3d_three_interpolate_affine(int b, int c, int m, int n, const float *points, const int *idx,
+                                           const float *weight, const float *scale1, const float *row1, const float *shift,
+                                           int flags, float *out, ws3d_stream_t stream) {
+  if ((scale1 == nullptr) != (row1 == nullptr)) return fail_arg("three_interpolate_affine (scale1 and row1 go together)");
+  const InterpEpilogue epi = {scale1, row1, shift, flags};
+  return three_interpolate_impl(b, c, m, n, points, idx, weight, out, &epi, stream);
 }
 
 WS3D_API int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,

@@ -271,6 +271,14 @@ def sa_mlp_fused(b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, 
                                       ptr(w[2]), ptr(shift[2]), ptr(out), out_ctot, out_coff, stream()), "sa_mlp_fused")
 
 
+def three_interpolate_affine(b, c, m, n, points, idx, weight, scale1, row1, shift, flags, out):
+    """Extension: out = act(three_interpolate(points) + scale1[c] * row1[b, i] + shift[c]); flags: 1 ReLU, 2 TF32 rounding."""
+    require_cuda(points, idx, weight, scale1, row1, shift, out)
+    with device_of(points):
+        check(lib().ws3d_three_interpolate_affine(b, c, m, n, ptr(points), ptr(idx), ptr(weight), ptr(scale1), ptr(row1),
+                                                  ptr(shift), int(flags), ptr(out), stream()), "three_interpolate_affine")
+
+
 def set_workspace_arena(arena: int) -> int:
     """Scratch arena (0..7) for this thread's subsequent launches; returns the previous one (ws3d_ops.h)."""
     return int(lib().ws3d_set_workspace_arena(int(arena)))

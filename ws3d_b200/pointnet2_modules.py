@@ -216,6 +216,23 @@ class PointnetFPModule(nn.Module):
                 known_feats: torch.Tensor, nn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
         if known is not None:
             idx, weight = nn if nn is not None else self.interpolation_weights(unknown, known)
+            c_skip = 0 if unknow_feats is None else unknow_feats.shape[1]
+            if (fused_mlp.enabled_for(self) and known_feats.is_cuda and known_feats.is_contiguous() and c_skip <= 1
+                    and (unknow_feats is None or unknow_feats.is_contiguous())
+                    and os.environ.get("WS3D_FP_PREMUL", "1") != "0"
+                    and fused_mlp.FoldedFPFirstLayer.eligible(self.mlp[0], known_feats.shape[1], c_skip, known_feats.shape[2],
+                                                              unknown.shape[1])):
+                # inference, thin skip input: first convolution on the known points, its product interpolated, the skip
+                # term + shift + ReLU in the interpolation epilogue; the remaining layers as usual
+                cache = self.__dict__.setdefault("_premul", {})
+                key = (known_feats.shape[1], c_skip)
+                if key not in cache:
+                    rest = list(self.mlp)[1:]
+                    cache[key] = (fused_mlp.FoldedFPFirstLayer(self.mlp[0], *key),
+                                  fused_mlp.FoldedMLP(torch.nn.Sequential(*rest)) if rest else None)
+                first, rest = cache[key]
+                x = first(known_feats, unknow_feats, idx, weight, unknown.shape[1], round_out=rest is not None)
+                return rest(x) if rest is not None else x
             interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
