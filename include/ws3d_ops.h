@@ -142,6 +142,18 @@ int ws3d_three_interpolate(int b, int c, int m, int n, const float *points, cons
 int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                 const float *weight, float *grad_points, ws3d_stream_t stream);
 
+/* Extension: grouping with an affine epilogue,
+ *   out[b,c,j,s] = act( P[b,c,i] + wx[c,:] . (xyz[b,i,:] - new_xyz[b,j,:]) + shift[c] ),  i = idx[b,j,s];
+ * flags bit 0 = ReLU, bit 1 = round to TF32.  P (B,c,n), xyz (B,n,3), new_xyz (B,m,3), wx (c,3), shift (c),
+ * idx (B,m,nsample) -> out (B,c,m,nsample).  It is the first layer of a set-abstraction MLP
+ * (pointnet2_modules.py:37-44) with the feature part of the 1x1 convolution moved in front of QueryAndGroup:
+ * W [xyz[i] - centre ; f[i]] = (W_f f)[i] + W_x (xyz[i] - centre): P = W_f f is formed on the n source points
+ * instead of the m * nsample grouped columns, the coordinate channels are applied in FP32, and the
+ * (3 + C)-channel grouped tensor is never written. */
+int ws3d_group_affine(int b, int n, int m, int c, int nsample, const float *P, const float *xyz,
+                      const float *new_xyz, const float *wx, const float *shift, const int *idx, int flags,
+                      float *out, ws3d_stream_t stream);
+
 /* Extension: three_interpolate with an affine epilogue,
  *   out[b,c,i] = act( sum_k weight[b,i,k] * points[b,c,idx[b,i,k]] + scale1[c] * row1[b,i] + shift[c] ),
  * scale1 (c) and row1 (B,n) optional (both or neither), shift (c) optional; flags bit 0 = ReLU, bit 1 =

@@ -220,3 +220,38 @@ def test_fp_module_premultiplied_first_layer(c_known, c_skip, spec, m, n, monkey
     with torch.no_grad():
         layered = fp(pts, known, sf, kf)
     assert float((got - layered).abs().max()) <= TOL * scale + 1e-4
+
+
+@pytest.mark.parametrize("n,m,c,radii,nsamples,mlps", [
+    (1024, 256, 256, [1.0, 2.0], [16, 32], [[256, 128, 196, 256], [256, 128, 196, 256]]),      # SA3 of the backbone
+    (256, 64, 512, [2.0, 4.0], [16, 32], [[512, 256, 256, 512], [512, 256, 384, 512]]),        # SA4
+    (2000, 100, 6, [1.5], [8], [[6, 24, 40]]),                                                   # two layers, ragged
+])
+def test_sa_first_layer_premultiplied(n, m, c, radii, nsamples, mlps, monkeypatch):
+    """Scales outside the one-kernel path: W_f applied to the source points, ws3d_group_affine gathers the product and
+    adds the FP32 coordinate term, shift and ReLU -- against the module's FP32 PyTorch path and the grouped path."""
+    from ws3d_b200 import pointnet2_modules, pointnet2_utils, synth
+    torch.manual_seed(n + c)
+    sa = pointnet2_modules.PointnetSAModuleMSG(npoint=m, radii=radii, nsamples=nsamples, mlps=[list(s) for s in mlps],
+                                              use_xyz=True).to(dev).eval()
+    g = torch.Generator(device="cpu").manual_seed(c)
+    for mod in sa.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.2)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.bias.shape, generator=g) * 0.2)
+    pts = torch.from_numpy(synth.make_batch(2, n)).to(dev)
+    xyz = pts[..., :3].contiguous()
+    feat = torch.randn(2, c, n, device=dev)
+    _, new_xyz = pointnet2_utils.sample_and_gather(xyz, m)
+    want = _sa_reference(sa, xyz, feat, new_xyz)
+    with torch.no_grad():
+        got = sa(xyz, feat, new_xyz=new_xyz)[1]
+    assert len(sa.__dict__.get("_premul", {})) == len(radii) and "_fused_scales" not in sa.__dict__
+    scale = float(want.abs().max()) + 1e-6
+    assert float((got - want).abs().max()) <= TOL * scale + 1e-4, float((got - want).abs().max()) / scale
+    monkeypatch.setenv("WS3D_SA_PREMUL", "0")
+    with torch.no_grad():
+        grouped_path = sa(xyz, feat, new_xyz=new_xyz)[1]
+    assert float((got - grouped_path).abs().max()) <= TOL * scale + 1e-4

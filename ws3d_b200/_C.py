@@ -33,6 +33,7 @@ _SIGNATURES = {
     "ws3d_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_query_and_group": [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_group_concat": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ws3d_group_affine": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "ws3d_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_three_interpolate_affine": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],

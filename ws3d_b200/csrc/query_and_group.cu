@@ -81,6 +81,68 @@ __global__ void __launch_bounds__(kThreads) group_concat_kernel(int c, int n, in
   }
 }
 
+// Gather with an affine epilogue:
+//   out[b,c,j,s] = act( P[b,c,i] + wx[c] . (xyz[b,i] - new_xyz[b,j]) + shift[c] ),  i = idx[b,j,s];
+// flags bit 0 = ReLU, bit 1 = round to TF32.  It is the FIRST LAYER of a set-abstraction MLP with the feature part of
+// the 1x1 convolution moved in front of the grouping: W [xyz[i] - centre ; f[i]] = (W_f f)[i] + W_x (xyz[i] - centre),
+// so P = W_f f is formed on the n source points (instead of a GEMM over the m * nsample grouped columns), the three
+// coordinate channels are applied here in FP32 (they must not go through TF32: the difference of two large coordinates
+// would lose its low bits), and the grouped (3 + C)-channel tensor is never written.  Thread mapping of group_concat_kernel.
+template <int EPT>
+__global__ void __launch_bounds__(kThreads) group_affine_kernel(int c, int n, int m, int K, int c_per_cta, int flags,
+                                                                 const float *__restrict__ P, const float *__restrict__ xyz,
+                                                                 const float *__restrict__ new_xyz,
+                                                                 const float *__restrict__ wx, const float *__restrict__ shift,
+                                                                 const int *__restrict__ idx, float *__restrict__ out) {
+  const size_t cloud = blockIdx.y;
+  const long long per_cloud = (long long)m * K;
+  const long long e0 = ((long long)blockIdx.x * kThreads + threadIdx.x) * EPT;
+  if (e0 >= per_cloud) return;
+  const int j = (int)(e0 / K);
+  int id[EPT];
+  const int *ip = idx + cloud * per_cloud + e0;
+  if (EPT == 4) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(ip));
+    id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) id[t] = __ldg(ip + t);
+  }
+  float d[3][EPT];
+  {
+    const float *ctr = new_xyz + (cloud * (size_t)m + j) * 3;
+    const float *pts = xyz + cloud * (size_t)n * 3;
+    const float c0 = __ldg(ctr), c1 = __ldg(ctr + 1), c2 = __ldg(ctr + 2);
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) {
+      const float *p = pts + (size_t)id[t] * 3;
+      d[0][t] = __fsub_rn(__ldg(p), c0); d[1][t] = __fsub_rn(__ldg(p + 1), c1); d[2][t] = __fsub_rn(__ldg(p + 2), c2);
+    }
+  }
+  const int cb = blockIdx.z * c_per_cta, ce = min(c, cb + c_per_cta);
+  const float *src = P + cloud * (size_t)c * n;
+  float *dst = out + (cloud * (size_t)c + cb) * per_cloud + e0;
+  const bool relu = (flags & 1) != 0, rnd = (flags & 2) != 0;
+#pragma unroll 4
+  for (int ci = cb; ci < ce; ++ci) {
+    const float *row = src + (size_t)ci * n;
+    const float w0 = __ldg(wx + ci * 3), w1 = __ldg(wx + ci * 3 + 1), w2 = __ldg(wx + ci * 3 + 2), sh = __ldg(shift + ci);
+    float v[EPT];
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) {
+      v[t] = __ldg(row + id[t]) + fmaf(w2, d[2][t], fmaf(w1, d[1][t], fmaf(w0, d[0][t], sh)));
+      if (relu) v[t] = fmaxf(v[t], 0.f);
+      if (rnd) v[t] = __uint_as_float((__float_as_uint(v[t]) + 0x1000u) & 0xFFFFE000u);
+    }
+    if (EPT == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    else {
+#pragma unroll
+      for (int t = 0; t < EPT; ++t) dst[t] = v[t];
+    }
+    dst += per_cloud;
+  }
+}
+
 }  // namespace
 
 int group_concat(int b, int n, int m, int c, int K, int use_xyz, const float *xyz, const float *new_xyz,
@@ -134,4 +196,26 @@ WS3D_API int ws3d_query_and_group(int b, int n, int m, int c, float radius, int 
   int rc = ball_query_multi(1, b, n, m, &radius, &nsample, new_xyz, xyz, rows, to_stream(stream));
   if (rc) return rc;
   return ws3d_group_concat(b, n, m, c, nsample, use_xyz, xyz, new_xyz, features, idx, out, stream);
+}
+
+// P (B,c,n), xyz (B,n,3), new_xyz (B,m,3), wx (c,3), shift (c), idx (B,m,nsample) -> out (B,c,m,nsample); see group_affine_kernel.
+WS3D_API int ws3d_group_affine(int b, int n, int m, int c, int nsample, const float *P, const float *xyz, const float *new_xyz,
+                               const float *wx, const float *shift, const int *idx, int flags, float *out, ws3d_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || c <= 0 || nsample < 0 || b > 65535) return fail_arg("group_affine");
+  if (b == 0 || m == 0 || nsample == 0) return 0;
+  if (!P || !xyz || !new_xyz || !wx || !shift || !idx || !out) return fail_arg("group_affine (null pointer)");
+  const long long per_cloud = (long long)m * nsample;
+  const bool vec = (nsample % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+  const long long gx = (per_cloud + kThreads * (vec ? 4 : 1) - 1) / (kThreads * (vec ? 4 : 1));
+  int c_per_cta = c;
+  if (gx * b < 4LL * kNumSMs && c > 8) {
+    const long long splits = (4LL * kNumSMs + gx * b - 1) / (gx * b);
+    c_per_cta = (int)((c + splits - 1) / splits);
+    if (c_per_cta < 8) c_per_cta = 8;
+  }
+  dim3 grid((unsigned)gx, (unsigned)b, (unsigned)ceil_div(c, c_per_cta));
+  if (vec) group_affine_kernel<4><<<grid, kThreads, 0, to_stream(stream)>>>(c, n, m, nsample, c_per_cta, flags, P, xyz, new_xyz, wx, shift, idx, out);
+  else group_affine_kernel<1><<<grid, kThreads, 0, to_stream(stream)>>>(c, n, m, nsample, c_per_cta, flags, P, xyz, new_xyz, wx, shift, idx, out);
+  return check_launch("group_affine");
 }

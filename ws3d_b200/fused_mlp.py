@@ -241,3 +241,60 @@ class FoldedFPFirstLayer:
         native.three_interpolate_affine(B, self.c_out, m, n, pre, idx, weight, self.scale1 if skip is not None else None, row1,
                                         self.shift, int(self.relu) | (2 if round_out else 0), out)
         return out
+
+
+class FoldedSAFirstLayer:
+    """First layer of a set-abstraction MLP with the feature part of the 1x1 convolution moved IN FRONT of the grouping.
+
+    W [xyz[i] - centre ; f[i]] = (W_f f)[i] + W_x (xyz[i] - centre): P = W_f f is one tensor-core launch over the N
+    source points (4-8x fewer columns than npoint * nsample), and `ws3d_group_affine` gathers it, adds the coordinate
+    term in FP32, the shift and the ReLU and writes the layer's OUTPUT -- the (3 + C)-channel grouped tensor and the big
+    first GEMM disappear.  Used for the scales whose weights do not fit the one-kernel path (SA3, SA4)."""
+
+    def __init__(self, block: nn.Module, c_feat: int):
+        self._block, self._c_feat, self._versions = block, c_feat, None
+        self._build()
+
+    @staticmethod
+    def eligible(block: nn.Module, c_feat: int, n: int) -> bool:
+        conv = getattr(block, "conv", None)
+        act = getattr(block, "activation", None)
+        return (conv is not None and c_feat > 0 and conv.in_channels == 3 + c_feat and n % 4 == 0
+                and (act is None or isinstance(act, nn.ReLU)))
+
+    def _stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self._block.parameters()) + list(self._block.buffers()))
+
+    def _build(self):
+        block, c_feat = self._block, self._c_feat
+        conv = block.conv
+        w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
+        shift = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+        if hasattr(block, "bn"):
+            bn = block.bn.bn
+            scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+            w = w * scale[:, None]
+            shift = (shift - bn.running_mean) * scale + bn.bias.detach()
+        self.c_out = w.shape[0]
+        self.c_out_pad = _ceil(self.c_out, _TILE_M)
+        wf = torch.zeros((self.c_out_pad, _ceil(c_feat, _CHUNK_K)), dtype=torch.float32, device=w.device)
+        wf[:self.c_out, :c_feat] = _round_tf32(w[:, 3:])
+        self.wf = wf.contiguous()
+        self.zero_shift = torch.zeros(self.c_out_pad, dtype=torch.float32, device=w.device)
+        self.wx = w[:, :3].contiguous()
+        self.shift = shift.contiguous()
+        self.relu = hasattr(block, "activation")
+        self._versions = self._stamp()
+
+    def __call__(self, xyz, new_xyz, features, idx, round_out: bool):
+        """xyz (B,N,3), new_xyz (B,M,3), features (B,C,N), idx (B,M,K) -> first-layer output (B, c_out, M*K)."""
+        if self._versions != self._stamp():
+            self._build()
+        B, C, N = features.shape
+        M, K = idx.shape[1], idx.shape[2]
+        pre = torch.empty((B, self.c_out, N), dtype=torch.float32, device=features.device)
+        native.mlp_layer(B, self.c_out, self.c_out_pad, C, 0, N, self.wf, self.zero_shift, features, None, pre, 0, 0)
+        out = torch.empty((B, self.c_out, M * K), dtype=torch.float32, device=features.device)
+        native.group_affine(B, N, M, self.c_out, K, pre, xyz, new_xyz, self.wx, self.shift, idx,
+                            int(self.relu) | (2 if round_out else 0), out)
+        return out

@@ -271,6 +271,14 @@ def sa_mlp_fused(b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, 
                                       ptr(w[2]), ptr(shift[2]), ptr(out), out_ctot, out_coff, stream()), "sa_mlp_fused")
 
 
+def group_affine(b, n, m, c, nsample, P, xyz, new_xyz, wx, shift, idx, flags, out):
+    """Extension: out[b,c,j,s] = act(P[b,c,i] + wx[c] . (xyz[b,i] - new_xyz[b,j]) + shift[c]), i = idx[b,j,s]; flags: 1 ReLU, 2 TF32."""
+    require_cuda(P, xyz, new_xyz, wx, shift, idx, out)
+    with device_of(P):
+        check(lib().ws3d_group_affine(b, n, m, c, nsample, ptr(P), ptr(xyz), ptr(new_xyz), ptr(wx), ptr(shift), ptr(idx),
+                                      int(flags), ptr(out), stream()), "group_affine")
+
+
 def three_interpolate_affine(b, c, m, n, points, idx, weight, scale1, row1, shift, flags, out):
     """Extension: out = act(three_interpolate(points) + scale1[c] * row1[b, i] + shift[c]); flags: 1 ReLU, 2 TF32 rounding."""
     require_cuda(points, idx, weight, scale1, row1, shift, out)

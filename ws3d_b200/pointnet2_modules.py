@@ -46,6 +46,23 @@ class _PointnetSAModuleBase(nn.Module):
             cache[k] = fused_mlp.FoldedMLP(self.mlps[k])
         return cache[k]
 
+    def _scale_inference(self, k, grouper, xyz, new_xyz, features, idx):
+        """One scale on the per-layer tensor-core path (inference): (B, c_last, npoint)."""
+        K = grouper.nsample
+        if (features is not None and getattr(grouper, "use_xyz", False) and len(self.mlps[k]) >= 2 and features.is_contiguous()
+                and os.environ.get("WS3D_SA_PREMUL", "1") != "0"
+                and fused_mlp.FoldedSAFirstLayer.eligible(self.mlps[k][0], features.shape[1], features.shape[2])):
+            # first convolution on the source points, gathered with the coordinate term / shift / ReLU in the epilogue
+            cache = self.__dict__.setdefault("_premul", {})
+            if k not in cache:
+                cache[k] = (fused_mlp.FoldedSAFirstLayer(self.mlps[k][0], features.shape[1]),
+                            fused_mlp.FoldedMLP(torch.nn.Sequential(*list(self.mlps[k])[1:])))
+            first, rest = cache[k]
+            return rest(first(xyz, new_xyz, features, idx, round_out=True), pool=K)
+        grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
+        B, C, M, _ = grouped.shape
+        return self._folded(k)(grouped.view(B, C, M * K), pool=K)
+
     def _scale_side_streams(self, xyz):
         """One extra CUDA stream per scale beyond the first (cached per module and device)."""
         if not xyz.is_cuda or len(self.groupers) < 2:
@@ -134,9 +151,7 @@ class _PointnetSAModuleBase(nn.Module):
                 st = side[k - 1]
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
-                    grouped = grouper(xyz, new_xyz, features, idx=idx)
-                    B, C, M, K = grouped.shape
-                    res = self._folded(k)(grouped.view(B, C, M * K), pool=K)
+                    res = self._scale_inference(k, grouper, xyz, new_xyz, features, idx)
                     done = torch.cuda.Event()
                     done.record(st)
                 for t in (xyz, new_xyz, features, idx):
@@ -146,10 +161,13 @@ class _PointnetSAModuleBase(nn.Module):
                 main.wait_event(done)   # (the join is only needed before the cat; waiting here keeps the code simple:
                 pooled.append(res)      #  scale 0 was launched first and is already running on `main`)
                 continue
+            if fused and self.npoint is not None and fused_mlp.supported(new_xyz.shape[1] * grouper.nsample, grouper.nsample):
+                # inference: every layer is one tensor-core launch; the last one also max-pools over nsample
+                pooled.append(self._scale_inference(k, grouper, xyz, new_xyz, features, idx))
+                continue
             grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
             B, C, M, K = grouped.shape
-            if fused and fused_mlp.supported(M * K, K):
-                # inference: every layer is one tensor-core launch; the last one also max-pools over nsample
+            if fused and fused_mlp.supported(M * K, K):   # GroupAll
                 pooled.append(self._folded(k)(grouped.view(B, C, M * K), pool=K))
                 continue
             if _train_channels_last(grouped):
