@@ -431,68 +431,102 @@ struct InterpEpilogue {
   int flags;
 };
 
-template <bool EPI>
-__global__ void __launch_bounds__(kInterpSmemThreads) three_interpolate_smem4_kernel(
+// MODE: bit 0 = epilogue present, bit 1 = ReLU, bit 2 = round to TF32 (compile-time: ncu showed 46 instructions per output
+// element with run-time flag tests and per-element loads of the per-channel terms)
+template <int MODE>
+__global__ void __launch_bounds__((MODE & 1) ? 512 : kInterpSmemThreads) three_interpolate_smem4_kernel(
     int c, int m, int n, int cb, int n_per_cta, const float *__restrict__ points, const int *__restrict__ idx,
     const float *__restrict__ weight, float *__restrict__ out, InterpEpilogue epi) {
   extern __shared__ __align__(16) float s_rows[];  // (cb/4) groups x m x 4
+  __shared__ float4 s_scale[16], s_shift[16];      // per-channel epilogue terms of this CTA's channels (cb <= 64)
+  constexpr bool EPI = (MODE & 1) != 0;
   const size_t cloud = blockIdx.z;
   const int c0 = blockIdx.x * cb, cn = min(cb, c - c0);  // cn % 4 == 0 (host guarantees c % 4 == 0 and cb % 4 == 0)
   const int i_begin = blockIdx.y * n_per_cta, i_end = min(n, i_begin + n_per_cta);
   const float *src = points + (cloud * (size_t)c + c0) * m;
-  for (int e = threadIdx.x; e < cn * m; e += (int)blockDim.x) {
-    const int cc = e / m, k = e - cc * m;
-    s_rows[((size_t)(cc >> 2) * m + k) * 4 + (cc & 3)] = __ldg(src + e);
+  if (EPI && threadIdx.x < cn) {
+    reinterpret_cast<float *>(s_scale)[threadIdx.x] = epi.scale1 ? __ldg(epi.scale1 + c0 + threadIdx.x) : 0.f;
+    reinterpret_cast<float *>(s_shift)[threadIdx.x] = epi.shift ? __ldg(epi.shift + c0 + threadIdx.x) : 0.f;
+  }
+  // The stencils (3 indices + 3 weights per point) do not depend on shared memory: the first two points' loads are
+  // issued BEFORE the rows are staged, later ones two points ahead of their use (ncu: the kernel waited on these
+  // global loads more than on anything else; one point of look-ahead left most of the latency exposed).
+  constexpr int PB = 2;
+  const int stride = (int)blockDim.x;
+  int si[PB][3];
+  float sw[PB][3], sr[PB];
+  auto load_stencil = [&](int q, int i) {
+    if (i < i_end) {
+      const int *ip = idx + (cloud * (size_t)n + i) * 3;
+      const float *wp = weight + (cloud * (size_t)n + i) * 3;
+      si[q][0] = __ldg(ip); si[q][1] = __ldg(ip + 1); si[q][2] = __ldg(ip + 2);
+      sw[q][0] = __ldg(wp); sw[q][1] = __ldg(wp + 1); sw[q][2] = __ldg(wp + 2);
+      sr[q] = (EPI && epi.row1) ? __ldg(epi.row1 + cloud * (size_t)n + i) : 0.f;
+    } else {
+      si[q][0] = si[q][1] = si[q][2] = 0;
+      sw[q][0] = sw[q][1] = sw[q][2] = 0.f;
+      sr[q] = 0.f;
+    }
+  };
+  int i = i_begin + (int)threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < PB; ++q) load_stencil(q, i + q * stride);
+  // stage the rows: the four channels of a group at one position k are four coalesced loads and ONE conflict-free
+  // 16-byte shared-memory store ([group][k][4] layout)
+  {
+    float4 *d4 = reinterpret_cast<float4 *>(s_rows);
+    for (int g = 0; g < (cn >> 2); ++g) {
+      const float *r0 = src + (size_t)(g * 4) * m;
+#pragma unroll 2
+      for (int k = threadIdx.x; k < m; k += stride)
+        d4[(size_t)g * m + k] = make_float4(__ldg(r0 + k), __ldg(r0 + m + k), __ldg(r0 + 2 * (size_t)m + k), __ldg(r0 + 3 * (size_t)m + k));
+    }
   }
   __syncthreads();
   const float4 *s4 = reinterpret_cast<const float4 *>(s_rows);
-  // the stencil (3 indices + 3 weights) of the NEXT point is loaded while the current one is interpolated:
-  // in ncu the kernel waited on these global loads (long scoreboard) more than on anything else
-  int i = i_begin + (int)threadIdx.x;
-  int i0 = 0, i1 = 0, i2 = 0;
-  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-  if (i < i_end) {
-    const int *ip = idx + (cloud * (size_t)n + i) * 3;
-    const float *wp = weight + (cloud * (size_t)n + i) * 3;
-    i0 = __ldg(ip); i1 = __ldg(ip + 1); i2 = __ldg(ip + 2);
-    w0 = __ldg(wp); w1 = __ldg(wp + 1); w2 = __ldg(wp + 2);
-  }
-  for (; i < i_end; i += (int)blockDim.x) {
-    const int nx = i + (int)blockDim.x;
-    int j0 = 0, j1 = 0, j2 = 0;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (nx < i_end) {
-      const int *ip = idx + (cloud * (size_t)n + nx) * 3;
-      const float *wp = weight + (cloud * (size_t)n + nx) * 3;
-      j0 = __ldg(ip); j1 = __ldg(ip + 1); j2 = __ldg(ip + 2);
-      v0 = __ldg(wp); v1 = __ldg(wp + 1); v2 = __ldg(wp + 2);
-    }
-    float *o = out + (cloud * (size_t)c + c0) * n + i;
-    const float r1 = (EPI && epi.row1) ? __ldg(epi.row1 + cloud * (size_t)n + i) : 0.f;
-#pragma unroll 2
-    for (int g = 0; g < (cn >> 2); ++g) {
-      const float4 *row = s4 + (size_t)g * m;
-      const float4 p0 = row[i0], p1 = row[i1], p2 = row[i2];
-      float v[4] = {__fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x))),
-                    __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y))),
-                    __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z))),
-                    __fmaf_rn(w2, p2.w, __fmaf_rn(w0, p0.w, __fmul_rn(w1, p1.w)))};
-      if (EPI) {
+  for (; i < i_end; i += PB * stride) {
+    int ci[PB][3];
+    float cw[PB][3], cr[PB];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = c0 + g * 4 + q;
-          if (epi.scale1) v[q] = fmaf(__ldg(epi.scale1 + ch), r1, v[q]);
-          if (epi.shift) v[q] += __ldg(epi.shift + ch);
-          if (epi.flags & 1) v[q] = fmaxf(v[q], 0.f);
-          if (epi.flags & 2) v[q] = __uint_as_float((__float_as_uint(v[q]) + 0x1000u) & 0xFFFFE000u);
-        }
-      }
-      __stcs(o + (size_t)(g * 4 + 0) * n, v[0]);
-      __stcs(o + (size_t)(g * 4 + 1) * n, v[1]);
-      __stcs(o + (size_t)(g * 4 + 2) * n, v[2]);
-      __stcs(o + (size_t)(g * 4 + 3) * n, v[3]);
+    for (int q = 0; q < PB; ++q) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { ci[q][a] = si[q][a]; cw[q][a] = sw[q][a]; }
+      cr[q] = sr[q];
     }
-    i0 = j0; i1 = j1; i2 = j2; w0 = v0; w1 = v1; w2 = v2;
+#pragma unroll
+    for (int q = 0; q < PB; ++q) load_stencil(q, i + (PB + q) * stride);   // two points ahead
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const int iq = i + q * stride;
+      if (iq >= i_end) break;
+      const int i0 = ci[q][0], i1 = ci[q][1], i2 = ci[q][2];
+      const float w0 = cw[q][0], w1 = cw[q][1], w2 = cw[q][2], r1 = cr[q];
+      float *o = out + (cloud * (size_t)c + c0) * n + iq;
+      const float4 *row = s4;
+      const int ng = cn >> 2;
+#pragma unroll 2
+      for (int g = 0; g < ng; ++g, row += m, o += 4 * (size_t)n) {
+        const float4 p0 = row[i0], p1 = row[i1], p2 = row[i2];
+        float v[4] = {__fmaf_rn(w2, p2.x, __fmaf_rn(w0, p0.x, __fmul_rn(w1, p1.x))),
+                      __fmaf_rn(w2, p2.y, __fmaf_rn(w0, p0.y, __fmul_rn(w1, p1.y))),
+                      __fmaf_rn(w2, p2.z, __fmaf_rn(w0, p0.z, __fmul_rn(w1, p1.z))),
+                      __fmaf_rn(w2, p2.w, __fmaf_rn(w0, p0.w, __fmul_rn(w1, p1.w)))};
+        if (EPI) {
+          const float4 sc = s_scale[g], sh = s_shift[g];
+          v[0] = fmaf(sc.x, r1, v[0]) + sh.x; v[1] = fmaf(sc.y, r1, v[1]) + sh.y;
+          v[2] = fmaf(sc.z, r1, v[2]) + sh.z; v[3] = fmaf(sc.w, r1, v[3]) + sh.w;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (MODE & 2) v[u] = fmaxf(v[u], 0.f);
+            if (MODE & 4) v[u] = __uint_as_float((__float_as_uint(v[u]) + 0x1000u) & 0xFFFFE000u);
+          }
+        }
+        __stcs(o, v[0]);
+        __stcs(o + n, v[1]);
+        __stcs(o + 2 * (size_t)n, v[2]);
+        __stcs(o + 3 * (size_t)n, v[3]);
+      }
+    }
   }
 }
 
@@ -605,12 +639,16 @@ static int three_interpolate_impl(int b, int c, int m, int n, const float *point
     cudaError_t e = cudaFuncSetAttribute(three_interpolate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("three_interpolate: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     if (chunks <= 65535 * 32 && nsplit <= 65535 && c % 4 == 0 && cb % 4 == 0) {
-      auto kern = epi ? three_interpolate_smem4_kernel<true> : three_interpolate_smem4_kernel<false>;
+      const int mode = epi ? (1 | ((epi->flags & 1) ? 2 : 0) | ((epi->flags & 2) ? 4 : 0)) : 0;
+      const int threads_k = mode ? 512 : threads;   // the epilogue variants need more than the 64 registers of a 1024-thread CTA
+      auto kern = mode == 0 ? three_interpolate_smem4_kernel<0> : mode == 1 ? three_interpolate_smem4_kernel<1>
+                  : mode == 3 ? three_interpolate_smem4_kernel<3> : mode == 5 ? three_interpolate_smem4_kernel<5>
+                                                                              : three_interpolate_smem4_kernel<7>;
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("three_interpolate: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
       dim3 grid((unsigned)chunks, (unsigned)nsplit, (unsigned)b);
       const InterpEpilogue none = {nullptr, nullptr, nullptr, 0};
-      kern<<<grid, threads, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx, weight, out, epi ? *epi : none);
+      kern<<<grid, threads_k, smem, to_stream(stream)>>>(c, m, n, cb, n_per_cta, points, idx, weight, out, epi ? *epi : none);
       return check_launch("three_interpolate");
     }
     if (epi) return fail_arg("three_interpolate_affine (needs c % 4 == 0)");
