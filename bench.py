@@ -528,10 +528,13 @@ def run_gpu(args):
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": "flushed between timed iterations (256 MiB write)",
-                       "mlp": ("tcgen05 TF32 shared-MLP layers (conv1x1+BN+ReLU[+max-pool] per launch, FP32 accumulate)"
+            "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": ("flushed before every step, in-stream and inside the timed region (160 MiB write > 126 MB L2)" if deep else
+                              "flushed between timed iterations (256 MiB write, outside the per-step event pair)"),
+                       "mlp": ("tcgen05 TF32, FP32 accumulate: SA1 / SA2 one fused kernel per scale (grouping + 3 layers + max-pool in "
+                               "tensor memory), other layers one launch per conv1x1+BN+ReLU[+max-pool]"
                                if torch.backends.cudnn.allow_tf32 else "PyTorch/cuDNN fp32 (TF32 off)"),
-                       "launch": "one CUDA graph replay per step" if use_graph else "eager launches",
+                       "launch": ("two CUDA graph replays per step (coordinate phase of batch i+N-1, feature phase of batch i)" if deep
+                                  else "one CUDA graph replay per step" if use_graph else "eager launches"),
                        "pipeline": ((f"{args.inflight} batches in flight: the coordinate phase (4 FPS levels in throughput mode = one "
                                      f"SM per cloud, ball queries, interpolation stencils) runs {args.inflight - 1} batches ahead on "
                                      f"its own streams beside the graph-replayed feature phases, which alternate between "
