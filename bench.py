@@ -592,8 +592,10 @@ def main():
                          "(StreamedBackboneRunner); 2: level-1 FPS of the next batch beside the current batch; 1: no pipeline")
     ap.add_argument("--feature-streams", type=int, default=int(os.environ.get("WS3D_FEATURE_STREAMS", "2")),
                     help="streams the feature phases of consecutive batches alternate between (streamed pipeline)")
-    ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "0")),
-                    help="SMs the persistent MLP kernel spreads over in pipelined mode (0 = all; 84 = the SMs level-1 FPS leaves free)")
+    ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "100")),
+                    help="SMs a persistent MLP kernel spreads over in the pipelined modes (0 = all 148; the coordinate phases of the "
+                         "batches ahead hold 3-5 x 16 SMs, so full-width grids would queue behind them: 185.4 / 186.8 / 187.6 Mpoints/s "
+                         "at 0 / 72 / 100)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_cpu(args)
