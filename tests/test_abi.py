@@ -95,3 +95,20 @@ def test_host_roipool_entry_points_match_oracle_and_reference():
         rflag = torch.zeros(boxes.shape[0], xyz.shape[0], dtype=torch.int64)
         ref.pts_in_boxes3d_cpu(rflag, torch.from_numpy(xyz), torch.from_numpy(boxes))
         np.testing.assert_array_equal(rflag.numpy(), eflag)
+
+
+def test_next_row_entry_points_reject_cpu_tensors_and_bad_shapes():
+    from ws3d_b200 import iou3d_utils, label_utils, native, proposal_utils
+    with pytest.raises(RuntimeError):
+        iou3d_utils.boxes_iou3d_aligned(torch.zeros(3, 7), torch.zeros(3, 7))
+    with pytest.raises(RuntimeError):
+        proposal_utils.cylinder_crop(torch.zeros(10, 3), torch.zeros(2, 2))
+    with pytest.raises(RuntimeError):
+        label_utils.generate_gaussian_training_labels(torch.zeros(10, 3), torch.zeros(2, 7))
+    with pytest.raises(RuntimeError):
+        native.radius_nms_device(torch.zeros(4, 2), 0.3)
+    assert native.set_fps_mode(1) == 0 and native.set_fps_mode(0) == 1            # host-only knobs work without a GPU
+    assert native.set_workspace_arena(3) == 0 and native.set_workspace_arena(0) == 3
+    assert native.set_sm_budget(100) == 0 and native.set_sm_budget(0) == 100
+    assert native.sa_mlp_fused_supported(96, 32, 64, 96, 128) and not native.sa_mlp_fused_supported(256, 16, 128, 196, 256)
+    assert not native.sa_mlp_fused_supported(1, 4, 16, 16, 32)                    # nsample below 16 is not served

@@ -122,3 +122,36 @@ def test_roipool_truncation_wraparound_and_empty():
     assert (pooled[0, 1] == 0).all()                                            # empty box untouched
     pooled, flag = oracle.roipool3d(xyz, feat, box, 10)
     np.testing.assert_array_equal(pooled[0, 0, :, 3], [0, 1, 2, 3, 4, 5, 6, 0, 1, 2])  # wrap-around k % cnt
+
+
+def test_next_rows_oracle_properties():
+    """Size-independent properties of the f3 / f4 restatements (no fixtures involved)."""
+    rng = np.random.default_rng(5)
+    cen = rng.uniform(0, 6, (400, 2)).astype(np.float32)
+    keep = oracle.radius_nms(cen, 0.5)
+    assert keep[0] == 0 and np.all(np.diff(keep) > 0)
+    kept = cen[keep]
+    d = np.sqrt(((kept[:, None] - kept[None]) ** 2).sum(-1))
+    np.fill_diagonal(d, 9.0)
+    assert d.min() > 0.5                                                  # kept centres are pairwise farther than the radius
+    dropped = np.setdiff1d(np.arange(400), keep)
+    for i in dropped[:50]:                                                # each dropped one has an EARLIER kept centre within it
+        earlier = keep[keep < i]
+        assert np.sqrt(((cen[earlier] - cen[i]) ** 2).sum(-1)).min() <= 0.5 + 1e-6
+    # cylinder membership: counts, order, any-flag
+    pts = rng.uniform(-10, 10, (3000, 3)).astype(np.float32)
+    idx, cnt, any_ = oracle.cylinder_query(pts, kept[:20] - 3.0, 4.0, 64)
+    for c in range(20):
+        inside = np.nonzero(np.sqrt(((pts[:, [0, 2]] - (kept[c] - 3.0)) ** 2).sum(-1)) < 4.0)[0]
+        assert abs(cnt[c] - len(inside)) <= 1                             # float64 here vs float32 there: boundary ties only
+        got = idx[c, :min(cnt[c], 64)]
+        assert np.all(np.diff(got) > 0)
+    assert any_.sum() > 0
+    # Gaussian labels: cls in (0, 1], 1 inside the 0.7 m core, regression target points at the nearest box within 4 m
+    boxes = np.array([[0, 1.6, 10, 1.5, 1.6, 3.9, 0.3], [8, 1.6, 30, 1.5, 1.6, 3.9, -1.0]], np.float32)
+    p = np.array([[0.1, 0.0, 10.1], [7.0, 0.0, 29.0], [40, 0, 60], [0, 0, 13.5]], np.float32)
+    cls, reg = oracle.gaussian_rpn_labels(p, boxes)
+    assert cls[0] == 1.0 and 0 < cls[1] < 1 and cls[2] < 1e-100          # 40 m from the nearest box: exp(-d^2 / 3)
+    np.testing.assert_allclose(reg[0], [-0.1, 0, -0.1], atol=1e-6)
+    np.testing.assert_allclose(reg[1], [1.0, 0, 1.0], atol=1e-6)
+    assert np.all(reg[2] == 0) and reg[3, 2] == np.float32(10) - np.float32(13.5)
