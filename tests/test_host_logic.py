@@ -95,3 +95,67 @@ def test_folded_mlp_weights_equal_conv_bn_eval_on_cpu():
     assert r.tolist() == [1.0 + 2 ** -10, 1.0, -(1.0 + 2 ** -10), 3.0]
     assert fused_mlp.supported(4096, 32) and fused_mlp.supported(4096, 0) and not fused_mlp.supported(4098, 0) \
         and fused_mlp.supported(4096, 64) and not fused_mlp.supported(4096, 256) and not fused_mlp.supported(4096, 24)
+
+
+def _randomize_bn_cpu(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
+
+
+def test_premultiplied_first_layers_fold_the_same_function_on_cpu():
+    """Host logic of fused_mlp.FoldedSAFirstLayer / FoldedFPFirstLayer / FusedSAScale (BN folding, the [xyz ; features]
+    column order, padding): the folded tensors, combined the way the kernels combine them, reproduce the module's
+    conv + BN(eval) + ReLU on CPU.  (Weights are rounded to TF32 in the folded copies: 2e-3 of the output scale.)"""
+    from ws3d_b200 import fused_mlp
+    from ws3d_b200 import pytorch_utils as pt_utils
+    torch.manual_seed(0)
+    B, C, N, M, K = 2, 10, 50, 7, 4
+    mlp = pt_utils.SharedMLP([C + 3, 12, 20, 24], bn=True).eval()
+    _randomize_bn_cpu(mlp, 1)
+    xyz, ctr, feat = torch.randn(B, N, 3), torch.randn(B, M, 3), torch.randn(B, C, N)
+    idx = torch.randint(0, N, (B, M, K))
+    gx = torch.gather(xyz, 1, idx.view(B, -1, 1).expand(-1, -1, 3)).view(B, M, K, 3) - ctr[:, :, None, :]
+    gf = torch.gather(feat, 2, idx.view(B, 1, -1).expand(-1, C, -1)).view(B, C, M, K)
+    grouped = torch.cat([gx.permute(0, 3, 1, 2), gf], dim=1)                    # xyz channels first (pointnet2_utils.py:257)
+    with torch.no_grad():
+        want1 = mlp[0](grouped)
+        want3 = mlp(grouped)
+    # set abstraction: P = W_f f on the source points, gathered, + W_x (xyz[i] - centre) + shift, ReLU
+    first = fused_mlp.FoldedSAFirstLayer(mlp[0], C)
+    assert fused_mlp.FoldedSAFirstLayer.eligible(mlp[0], C, 48) and not fused_mlp.FoldedSAFirstLayer.eligible(mlp[0], C, 50)
+    P = torch.einsum("oc,bcn->bon", first.wf[:first.c_out, :C], feat)
+    Pg = torch.gather(P, 2, idx.view(B, 1, -1).expand(-1, first.c_out, -1)).view(B, first.c_out, M, K)
+    got1 = torch.relu(Pg + torch.einsum("oa,bmka->bomk", first.wx, gx) + first.shift[None, :, None, None])
+    assert float((got1 - want1).abs().max()) < 2e-3 * float(want1.abs().max())
+    # the one-kernel scale: three folded layers chained on the grouped tensor
+    scale = fused_mlp.FusedSAScale(mlp)
+    assert scale.widths == [12, 20, 24] and [tuple(w.shape) for w in scale.w] == [(16, 32), (32, 32), (32, 32)]
+    act, k_real = grouped, C + 3
+    for w, sh, c_out in zip(scale.w, scale.shift, scale.widths):
+        act = torch.relu(torch.einsum("oc,bcmk->bomk", w[:c_out, :k_real], act) + sh[None, :c_out, None, None])
+        k_real = c_out
+    assert float((act - want3).abs().max()) < 3e-3 * float(want3.abs().max())
+    # feature propagation: W_a on the known points, interpolated, + W_b[c] * skip + shift, ReLU
+    fp_mlp = pt_utils.SharedMLP([C + 1, 16], bn=True).eval()
+    _randomize_bn_cpu(fp_mlp, 2)
+    n, m = 256, 8
+    known, skip = torch.randn(B, C, m), torch.randn(B, 1, n)
+    nn_idx = torch.randint(0, m, (B, n, 3))
+    w3 = torch.rand(B, n, 3)
+    w3 = w3 / w3.sum(-1, keepdim=True)
+
+    def interp(f):
+        return sum(torch.gather(f, 2, nn_idx[..., k].unsqueeze(1).expand(-1, f.shape[1], -1)) * w3[..., k].unsqueeze(1) for k in range(3))
+
+    with torch.no_grad():
+        want_fp = fp_mlp(torch.cat([interp(known), skip], dim=1).unsqueeze(-1)).squeeze(-1)
+    assert fused_mlp.FoldedFPFirstLayer.eligible(fp_mlp[0], C, 1, m, n) and not fused_mlp.FoldedFPFirstLayer.eligible(fp_mlp[0], C, 2, m, n)
+    ff = fused_mlp.FoldedFPFirstLayer(fp_mlp[0], C, 1)
+    pre = torch.einsum("oc,bcm->bom", ff.wa[:ff.c_out, :C], known)
+    got_fp = torch.relu(interp(pre) + ff.scale1[None, :, None] * skip + ff.shift[None, :, None])
+    assert float((got_fp - want_fp).abs().max()) < 2e-3 * float(want_fp.abs().max())
