@@ -40,6 +40,10 @@ def test_library_is_sm100a_only_and_uses_tma_and_clusters():
     assert "UBLKCP" in sass                              # cp.async.bulk (TMA) staging
     assert "REDUX" in sass                               # warp arg-max in FPS
     assert re.search(r"UCGABAR|CGABAR", sass)            # cluster barrier of the FPS cluster kernel
+    assert re.search(r"UTC\w*MMA", sass)                 # tcgen05.mma: the shared-MLP layer and the fused SA scale
+    assert "UTMALDG" in sass                             # cp.async.bulk.tensor operand / weight loads
+    assert "LDTM" in sass and "STTM" in sass             # tcgen05.ld epilogues; tcgen05.st: gathered tile + activations kept in TMEM
+    assert "HMMA." not in sass.replace("UTCHMMA", "")    # no legacy mma.sync / wmma path
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
