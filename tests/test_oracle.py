@@ -155,3 +155,48 @@ def test_next_rows_oracle_properties():
     np.testing.assert_allclose(reg[0], [-0.1, 0, -0.1], atol=1e-6)
     np.testing.assert_allclose(reg[1], [1.0, 0, 1.0], atol=1e-6)
     assert np.all(reg[2] == 0) and reg[3, 2] == np.float32(10) - np.float32(13.5)
+
+
+def _fps_thread_level(xyz, m):
+    """A thread-by-thread emulation of furthest_point_sampling_kernel<block_size> (sampling_gpu.cu:93-209) for one cloud:
+    strided per-thread scan with strict '>', shared arrays dists / dists_i, the unrolled tree of __update calls
+    (:86-91: the lower slot keeps its index unless the upper value is strictly larger), old = dists_i[0].
+    Integer-lattice inputs only: every distance is exact in float32, so the FMA shape does not matter here."""
+    n = xyz.shape[0]
+    bs = oracle.opt_n_threads(n)
+    temp = np.full(n, 1e10, np.float32)
+    idx = np.zeros(m, np.int32)
+    old = 0
+    for j in range(1, m):
+        dists = np.full(bs, -1.0, np.float32)
+        dists_i = np.zeros(bs, np.int64)
+        d = ((xyz - xyz[old]) ** 2).sum(1).astype(np.float32)
+        temp = np.minimum(d, temp)
+        for tid in range(bs):
+            best, besti = np.float32(-1), 0
+            for k in range(tid, n, bs):
+                if temp[k] > best:
+                    best, besti = temp[k], k
+            dists[tid], dists_i[tid] = best, besti
+        s = bs // 2
+        while s >= 1:
+            for tid in range(s):
+                v1, v2 = dists[tid], dists[tid + s]
+                if v2 > v1:
+                    dists_i[tid] = dists_i[tid + s]
+                dists[tid] = max(v1, v2)
+            s //= 2
+        old = int(dists_i[0])
+        idx[j] = old
+    return idx
+
+
+@pytest.mark.parametrize("n,m,span", [(8, 8, 2), (37, 20, 3), (64, 40, 3), (100, 100, 4), (300, 120, 5)])
+def test_fps_oracle_equals_thread_level_emulation_on_lattices(n, m, span):
+    """Lattice clouds are full of exact ties and duplicates: the oracle's closed-form tie rule (largest value, then the
+    smallest bit-reversed k mod BS, then the smallest k) must pick what the reference kernel's shared-memory tree picks."""
+    rng = np.random.default_rng(n * 31 + m)
+    xyz = rng.integers(-span, span + 1, (n, 3)).astype(np.float32)
+    want = _fps_thread_level(xyz, m)
+    got = oracle.furthest_point_sample(xyz[None], m)[0]
+    np.testing.assert_array_equal(got, want)
