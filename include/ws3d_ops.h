@@ -14,8 +14,8 @@
  * All pointers are DEVICE pointers to contiguous row-major arrays unless a
  * parameter is explicitly named *_host.  float = IEEE binary32, int = int32.
  * The caller owns and pre-initialises every output exactly as the reference's
- * Python wrappers do (zero-filled idx for ball_query, 1e10-filled temp for FPS,
- * zero-filled grads / pooled features / flags).  No entry point allocates device
+ * Python wrappers do (1e10-filled temp for FPS, zero-filled grads / pooled
+ * features / flags; ball_query's idx needs no fill here).  No entry point allocates device
  * memory except the *_host convenience wrappers and ws3d_roipool3d / ws3d_nms*
  * when called with workspace == NULL (they then use a cached per-device scratch
  * buffer that is grown on demand and never shrunk).
@@ -49,6 +49,16 @@ uint64_t ws3d_launch_count(void);
  * (or captured) under different arenas.  The reference has no counterpart (it cudaMallocs per call,
  * iou3d.cpp:87, roipool3d_kernel.cu:214). */
 int ws3d_set_workspace_arena(int arena);
+/* Number of scratch arenas (valid arguments of ws3d_set_workspace_arena are 0 .. ws3d_num_arenas() - 1). */
+int ws3d_num_arenas(void);
+/* Bytes of cached scratch on the current device: retired (outgrown, kept alive because a captured CUDA graph or a
+ * queued launch may still hold the address) plus, unless retired_only, the live buffers of every arena. */
+size_t ws3d_scratch_bytes(int retired_only);
+/* Frees the retired scratch buffers of the current device (all = 0) or every cached buffer (all = 1).  Synchronises
+ * the device first.  The CALLER guarantees that no captured graph that will be replayed again was captured while a
+ * buffer that is freed here was live (destroy such graphs first; ws3d_b200.graphs runners do so in close()).  The
+ * reference frees its scratch after every call (iou3d.cpp:118, roipool3d_kernel.cu:235-236). */
+int ws3d_release_scratch(int all);
 /* Upper bound on the SMs a persistent kernel (ws3d_mlp_layer) spreads over; 0 = all 148.  Used when a
  * latency-bound kernel of another batch (FPS) is meant to run beside it.  Returns the previous value. */
 int ws3d_set_sm_budget(int sms);
@@ -90,15 +100,17 @@ int ws3d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_
 
 /* Replaces ball_query_kernel_launcher_fast (ball_query_gpu.h:12-13, ball_query_gpu.cu:48-67).
  * NOTE the argument order: new_xyz (B,M,3) comes BEFORE xyz (B,N,3), as in the
- * reference wrapper (ball_query.cpp:14-25).  idx (B,M,nsample) must be zero-filled
- * by the caller; rows with no neighbour are left untouched. */
+ * reference wrapper (ball_query.cpp:14-25).  idx (B,M,nsample): every row is written.  A row
+ * with no neighbour is ZERO-FILLED by the kernel: the reference leaves it untouched and relies
+ * on the caller's zero fill (pointnet2_utils.py:218) -- same result, and callers of this library
+ * may pass uninitialised memory. */
 int ws3d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                     const float *xyz, int *idx, ws3d_stream_t stream);
 
 /* Extension: ball_query for TWO radii over the same centres in one scan (the multi-scale
  * grouping of PointnetSAModuleMSG, pointnet2_modules.py:37-38, queries the same new_xyz/xyz once
- * per scale).  idx0 (B,M,nsample0), idx1 (B,M,nsample1), both zero-filled by the caller; each is
- * identical to what ws3d_ball_query returns for its radius. */
+ * per scale).  idx0 (B,M,nsample0), idx1 (B,M,nsample1); each is identical to what
+ * ws3d_ball_query returns for its radius (no-neighbour rows zero-filled by the kernel). */
 int ws3d_ball_query2(int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
                      const float *new_xyz, const float *xyz, int *idx0, int *idx1, ws3d_stream_t stream);
 
@@ -131,6 +143,13 @@ int ws3d_group_concat(int b, int n, int m, int c, int nsample, int use_xyz, cons
  * unknown (B,N,3), known (B,M,3) -> dist2 (B,N,3) SQUARED distances, idx (B,N,3). */
 int ws3d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
                   int *idx, ws3d_stream_t stream);
+
+/* Extension: three_nn that also emits the normalised inverse-distance interpolation weights
+ * PointnetFPModule.forward derives from its result with five elementwise torch kernels
+ * (pointnet2_modules.py:139-144): dist = sqrt(dist2); r = 1 / (dist + 1e-8); weight = r / sum_k r_k,
+ * each step one IEEE float32 operation.  weight (B,N,3); dist2 may be NULL (not written). */
+int ws3d_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                          int *idx, float *weight, ws3d_stream_t stream);
 
 /* Replaces three_interpolate_kernel_launcher_fast (interpolate_gpu.h:20-21, interpolate_gpu.cu:99-117).
  * points (B,C,M), idx (B,N,3), weight (B,N,3) -> out (B,C,N). */
@@ -179,6 +198,16 @@ int ws3d_three_interpolate_affine(int b, int c, int m, int n, const float *point
 int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w,
                    const float *shift, const float *x1, const float *x2, float *out, int relu, int pool,
                    ws3d_stream_t stream);
+/* Same, writing channels [out_coff, out_coff + c_out) of an (B, out_ctot, cols or cols / pool) tensor: the slot of one
+ * scale in the concatenated multi-scale output (pointnet2_modules.py:55) without a torch.cat pass. */
+int ws3d_mlp_layer_into(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w,
+                        const float *shift, const float *x1, const float *x2, float *out, int out_ctot,
+                        int out_coff, int relu, int pool, ws3d_stream_t stream);
+
+/* Extension: the `_break_up_pc` step of lib/net/pointnet2_msg.py:52-60 in one launch:
+ * pc (B,N,3+C) -> xyz (B,N,3) and features (B,C,N) (channel-major; NULL when C == 0). */
+int ws3d_split_pointcloud(int b, int n, int c, const float *pc, float *xyz, float *features,
+                          ws3d_stream_t stream);
 
 /* Extension (complete form): ONE set-abstraction scale in one kernel --
  * QueryAndGroup's grouping (pointnet2_utils.py:241-264, use_xyz = True), the three SharedMLP layers

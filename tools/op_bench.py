@@ -1,6 +1,6 @@
 """Per-op timings at the BASELINE config shapes: B200 ops vs the reference kernels (oracle/_ref).
 
-    gpurun -- 'python tools/op_bench.py --out gpurun_out/op_bench.json [--fps-sweep]'
+    gpurun -- 'python tools/op_bench.py --out gpurun_out/op_bench.json'
 
 CUDA events on torch's current stream, 3 warm-ups, L2 flushed (256 MiB write) before every timed
 launch, median of `--iters`.  Prints one JSON line per (op, shape, impl).
@@ -51,7 +51,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/op_bench.json")
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--fps-sweep", action="store_true")
     ap.add_argument("--batch", type=int, default=16)
     args = ap.parse_args()
     ref = load_ref("pointnet2_cuda")
@@ -95,20 +94,8 @@ def main():
                 ms, best = timeit(run_ref, max(3, args.iters // 3))
                 rec("fps", shape, "reference", ms, best, b * (12 * n + 4 * m), {"us_per_iter": round(ms * 1e3 / max(1, m - 1), 4)})
                 assert torch.equal(idx, ridx)
-            if args.fps_sweep and li < 2:
-                for C in (1, 2, 4, 8, 16):
-                    for T in (128, 256, 512, 1024):
-                        os.environ["WS3D_FPS_C"], os.environ["WS3D_FPS_T"] = str(C), str(T)
-                        os.environ["WS3D_FPS_ALLOW16"] = "1"
-                        if b * C > 148 or (n + C * T - 1) // (C * T) > 8:
-                            continue
-                        try:
-                            ms, best = timeit(run_mine, 5)
-                            rec("fps_sweep", shape, f"C{C}_T{T}", ms, best, None, {"us_per_iter": round(ms * 1e3 / max(1, m - 1), 4)})
-                        except RuntimeError as ex:
-                            print("sweep fail", C, T, ex, flush=True)
-                for k in ("WS3D_FPS_C", "WS3D_FPS_T", "WS3D_FPS_ALLOW16"):
-                    os.environ.pop(k, None)
+            # (decomposition sweeps: tools/fps_sweep.py, one subprocess per setting -- the library reads its
+            #  WS3D_FPS_* overrides once per process)
         # full-batch sample for the next level
         idxB = torch.empty((B, m), dtype=torch.int32, device=dev)
         new_xyz = torch.empty((B, m, 3), device=dev)

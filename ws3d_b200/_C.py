@@ -21,6 +21,9 @@ _SIGNATURES = {
     "ws3d_last_error": [],
     "ws3d_launch_count": [],
     "ws3d_set_workspace_arena": [_i],
+    "ws3d_num_arenas": [],
+    "ws3d_scratch_bytes": [_i],
+    "ws3d_release_scratch": [_i],
     "ws3d_set_sm_budget": [_i],
     "ws3d_set_fps_mode": [_i],
     "ws3d_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
@@ -35,10 +38,13 @@ _SIGNATURES = {
     "ws3d_group_concat": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_group_affine": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "ws3d_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "ws3d_three_nn_weights": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_three_interpolate_affine": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "ws3d_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_mlp_layer": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "ws3d_mlp_layer_into": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "ws3d_split_pointcloud": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_sa_mlp_fused_supported": [_i, _i, _i, _i, _i],
     "ws3d_sa_mlp_fused": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ws3d_boxes_overlap_bev": [_i, _vp, _i, _vp, _vp, _vp],
@@ -60,6 +66,7 @@ _RESTYPES = {
     "ws3d_last_error": ctypes.c_char_p,
     "ws3d_launch_count": c_uint64,
     "ws3d_nms_workspace_bytes": c_size_t,
+    "ws3d_scratch_bytes": c_size_t,
 }
 EXPORTS = tuple(sorted(_SIGNATURES))
 
@@ -108,15 +115,42 @@ def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def require_cuda(*tensors, dtype_map=None):
-    """Same preconditions the reference wrappers assert (CUDA, contiguous); dtype checked too."""
+def require_cuda(*tensors, what: str = "ws3d_b200"):
+    """Same preconditions the reference wrappers assert (CUDA, contiguous) for tensors whose dtype / size are checked
+    elsewhere."""
     for k, t in enumerate(tensors):
         if t is None:
             continue
         if not t.is_cuda:
-            raise RuntimeError(f"argument {k} must be a CUDA tensor")
+            raise RuntimeError(f"{what}: argument {k} must be a CUDA tensor")
         if not t.is_contiguous():
-            raise RuntimeError(f"argument {k} must be contiguous")
+            raise RuntimeError(f"{what}: argument {k} must be contiguous")
+    return True
+
+
+F32, I32, I64, U8 = torch.float32, torch.int32, torch.int64, torch.uint8
+
+
+def require(what: str, *specs, cuda: bool = True):
+    """Argument validation of one launch.  Every spec is (tensor or None, dtype, minimum element count or None).
+
+    The C ABI takes raw pointers, so a tensor of the wrong dtype would be silently reinterpreted (int64 indices from
+    argsort / topk read as int32 pairs, float64 features read as float32) and one that is smaller than the dimensions
+    passed beside it would be read or written out of bounds.  The reference's pybind layer raises for the first
+    (`tensor.data<int>()` / `data<float>()` type-check) and checks nothing for the second; here both raise RuntimeError."""
+    for k, (t, dtype, numel) in enumerate(specs):
+        if t is None:
+            continue
+        if cuda and not t.is_cuda:
+            raise RuntimeError(f"{what}: argument {k} must be a CUDA tensor")
+        if not cuda and t.is_cuda:
+            raise RuntimeError(f"{what}: argument {k} must be a CPU tensor")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{what}: argument {k} must be contiguous")
+        if t.dtype != dtype:
+            raise RuntimeError(f"{what}: argument {k} must be {dtype}, got {t.dtype}")
+        if numel is not None and t.numel() < int(numel):
+            raise RuntimeError(f"{what}: argument {k} has {t.numel()} elements, the dimensions passed need {int(numel)}")
     return True
 
 

@@ -85,7 +85,14 @@ __global__ void __launch_bounds__(kQueryWarps * 32) grid_query_kernel(GridQueryP
   for (int q = blockIdx.x * kQueryWarps + warp; q < m; q += gridDim.x * kQueryWarps) {
     const float *qp = prm.new_xyz + (cloud * (size_t)m + q) * 3;
     const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-    if (!finite3(qx, qy, qz)) continue;  // nothing can be inside the ball
+    if (!finite3(qx, qy, qz)) {  // nothing can be inside the ball: zero rows (what the reference's caller pre-fills)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        int *row = prm.idx[r] + (cloud * (size_t)m + q) * prm.nsample[r];
+        for (int s = lane; s < prm.nsample[r]; s += 32) row[s] = 0;
+      }
+      continue;
+    }
     // ---- the 9 runs of cells (x-1..x+1 contiguous) round the centre's cell
     {
       // unclamped float cell coordinates, limited so that the int conversion cannot overflow
@@ -150,7 +157,10 @@ __global__ void __launch_bounds__(kQueryWarps * 32) grid_query_kernel(GridQueryP
     for (int r = 0; r < NR; ++r) {
       const int K = prm.nsample[r];
       int *row = prm.idx[r] + (cloud * (size_t)m + q) * K;
-      if (cnt[r] == 0 || K == 0) continue;
+      if (cnt[r] == 0) {
+        for (int s = lane; s < K; s += 32) row[s] = 0;
+        continue;
+      }
       if (cnt[r] > kHitCap) {
         scan_in_order(pts, n, qx, qy, qz, prm.r2[r], K, row, lane);
         continue;
@@ -203,7 +213,7 @@ int launch_grid(int b, int n, int m, const float *radius, const int *nsample, co
     prm.idx[r] = idx[r];
   }
   int gx = ceil_div(m, kQueryWarps);
-  const int cap = ceil_div(8 * kNumSMs, b);  // ~8 CTAs per SM in flight
+  const int cap = ceil_div(8 * num_sms(), b);  // ~8 CTAs per SM in flight
   if (gx > cap) gx = cap;
   grid_query_kernel<NR><<<dim3((unsigned)gx, (unsigned)b), kQueryWarps * 32, 0, stream>>>(prm);
   return check_launch("ball_query (grid query)");

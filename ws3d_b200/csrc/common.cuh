@@ -16,7 +16,8 @@ namespace ws3d {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
-// cached per-device scratch (grown on demand, never shrunk); nullptr + error on failure
+// cached per-device scratch (grown on demand; outgrown buffers are retired until ws3d_release_scratch());
+// nullptr + error on failure
 void *scratch(size_t bytes, int slot);
 // grid size of a persistent kernel with `per_sm` CTAs per SM, honouring ws3d_set_sm_budget()
 int persistent_ctas(int per_sm);
@@ -41,7 +42,9 @@ inline int fail_arg(const char *what) {
   return (int)cudaErrorInvalidValue;
 }
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a full B200, fewer on
+// a MIG slice or an SM-limited context).  Grid sizes of persistent kernels and the FPS decomposition derive from it.
+int num_sms();
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -71,6 +74,28 @@ __device__ __forceinline__ void sqdist_ref_x2(float x0, float x1, float y0, floa
   asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(T) : "l"(X), "l"(T));
   asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(T) : "l"(Z), "l"(T));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(T));
+}
+
+// Output stage shared by the two three_nn kernels: squared distances and indices as the reference writes them
+// (interpolate_gpu.cu:49-51) and / or the normalised inverse-distance weights PointnetFPModule.forward derives from
+// them with five elementwise torch kernels (pointnet2_modules.py:139-144): dist = sqrt(d2); r = 1 / (dist + 1e-8);
+// w = r / (r0 + r1 + r2) -- every step one IEEE round-to-nearest float32 operation, as torch evaluates it.
+__device__ __forceinline__ void store_three_nn(float *__restrict__ dist2, int *__restrict__ idx, float *__restrict__ weight,
+                                               size_t row, float d1, float d2, float d3, int i1, int i2, int i3) {
+  int *oi = idx + row * 3;
+  oi[0] = i1; oi[1] = i2; oi[2] = i3;
+  if (dist2) {
+    float *od = dist2 + row * 3;
+    od[0] = d1; od[1] = d2; od[2] = d3;
+  }
+  if (weight) {
+    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d1), 1e-8f));
+    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d2), 1e-8f));
+    const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d3), 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+    float *ow = weight + row * 3;
+    ow[0] = __fdiv_rn(r1, norm); ow[1] = __fdiv_rn(r2, norm); ow[2] = __fdiv_rn(r3, norm);
+  }
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

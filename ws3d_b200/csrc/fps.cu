@@ -483,20 +483,23 @@ int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, f
   if (fps_bucket_applicable(b, n, m)) return fps_bucket_launch(prm, b, stream);
 
   // --- decomposition: C CTAs per cloud, T threads per CTA, P points per thread
-  int cmax = kNumSMs / (b < 1 ? 1 : b);
+  // (tuning overrides are read from the environment ONCE: getenv walks the whole environment block)
+  static const int env_allow16 = env_int("WS3D_FPS_ALLOW16", 0), env_c = env_int("WS3D_FPS_C", 0),
+                   env_ppt = env_int("WS3D_FPS_PPT", 0), env_t = env_int("WS3D_FPS_T", 0);
+  int cmax = num_sms() / (b < 1 ? 1 : b);
   cmax = cmax >= 16 ? 16 : cmax >= 8 ? 8 : cmax >= 4 ? 4 : cmax >= 2 ? 2 : 1;
-  if (cmax > 8) cmax = env_int("WS3D_FPS_ALLOW16", 0) ? 16 : 8;
+  if (cmax > 8) cmax = env_allow16 ? 16 : 8;
   // measured on B200 (profiles/r1_op_bench_v2.json): one CTA (T=512, P=8) beats any cluster up to 4096 points;
   // above that a cluster of 8 x 512 threads x 4 points is best when the SMs are there
   int C = n <= 4096 ? 1 : pow2_ceil(ceil_div(n, 2048));
   if (C > cmax) C = cmax;
   while (ceil_div(n, C) > 8 * 1024 && C < 8) C <<= 1;  // registers: P <= 8 at T = 1024
-  C = env_int("WS3D_FPS_C", C);
+  if (env_c > 0) C = env_c;
   int npc = ceil_div(n, C);
-  int T = pow2_ceil(ceil_div(npc, env_int("WS3D_FPS_PPT", npc > 2048 ? 8 : 4)));
+  int T = pow2_ceil(ceil_div(npc, env_ppt > 0 ? env_ppt : (npc > 2048 ? 8 : 4)));
   if (T < 32) T = 32;
   if (T > 1024) T = 1024;
-  T = env_int("WS3D_FPS_T", T);
+  if (env_t > 0) T = env_t;
   int P = pow2_ceil(ceil_div(npc, T));
   prm.log2T = ilog2(T);
 
@@ -510,8 +513,8 @@ int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, f
     static const int flat = env_int("WS3D_FPS_FLAT", 1);
     static const int flat_min = env_int("WS3D_FPS_FLAT_MIN", 2048);
     if (flat && n >= flat_min && (size_t)n * 12 <= 200 * 1024 && cmax >= 2) {
-      int Cf = env_int("WS3D_FPS_C", cmax >= 4 ? 4 : 2);
-      int Tf = pow2_ceil(ceil_div(ceil_div(n, Cf), env_int("WS3D_FPS_PPT", n > 8192 ? 16 : 8)));
+      int Cf = env_c > 0 ? env_c : (cmax >= 4 ? 4 : 2);
+      int Tf = pow2_ceil(ceil_div(ceil_div(n, Cf), env_ppt > 0 ? env_ppt : (n > 8192 ? 16 : 8)));
       if (Tf < 32) Tf = 32;
       if (Tf > 512) Tf = 512;
       const int Pf = pow2_ceil(ceil_div(ceil_div(n, Cf), Tf));

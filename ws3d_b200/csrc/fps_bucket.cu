@@ -361,7 +361,7 @@ bool fps_bucket_applicable(int b, int n, int m) {
   const int rt = fps_mode();
   const int mode = rt == 1 ? 1 : rt == 2 ? 0 : env_mode;
   if (mode == 0 || n < 2048 || n > 16384 || m < 64 || b < 1 || b > 65535) return false;
-  return mode == 1 || b * 2 > kNumSMs;
+  return mode == 1 || b * 2 > num_sms();
 }
 
 int fps_bucket_launch(const FpsParams &prm, int b, cudaStream_t stream) {

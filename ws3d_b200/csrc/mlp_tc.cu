@@ -41,6 +41,7 @@ struct MlpParams {
   int flags;        // bit 0: ReLU, bit 1: round the stored output to TF32, bits 4-5: log2(copies of the weight rows)
   const float *shift;  // (c_out_padded)
   float *out;
+  int out_ctot, out_coff;   // out is (B, out_ctot, cols or cols / pool); this layer writes channels [out_coff, out_coff + c_out)
   int n_col_tiles, n_m_tiles, n_tiles;   // tile = (cloud, 128-channel block, NT-column block), column block fastest
 };
 
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
             const int row = k * 4 + srow;
             const uint4 val = *reinterpret_cast<const uint4 *>(stage + row * 36 + scol);
             if (co_base + row < prm.c_out)
-              __stcs(reinterpret_cast<uint4 *>(prm.out + ((size_t)cloud * prm.c_out + co_base + row) * prm.cols + col0 + c + scol), val);
+              __stcs(reinterpret_cast<uint4 *>(prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + co_base + row) * prm.cols + col0 + c + scol), val);
           }
         }
         __syncwarp();
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
     } else if (warp_live) {
       const int ns = prm.pool;                  // power of two dividing the warp's column share
       const int lg = __ffs(ns) - 1;
-      float *dst = prm.out + ((size_t)cloud * prm.c_out + co) * (prm.cols >> lg) + (col0 >> lg);
+      float *dst = prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + co) * (prm.cols >> lg) + (col0 >> lg);
       if (ns == 16)
         pooled_chunks<16>(trow, cbeg, cend, col0, prm.cols, live, shift, relu, dst);
       else if (ns == 32)
@@ -362,9 +363,13 @@ using namespace ws3d;
 //    zero padded; columns [0, 32*nk1) multiply x1's channels, the rest x2's.
 // x1: (B, c1, cols), x2: (B, c2, cols) or NULL.  shift: (c_out_pad).  cols % 4 == 0.
 // out: (B, c_out, cols) or, when pool > 0, (B, c_out, cols / pool) with the max over each run of `pool` columns.
-WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *shift,
-                            const float *x1, const float *x2, float *out, int relu, int pool, ws3d_stream_t stream) {
+// out_ctot / out_coff: the layer writes channels [out_coff, out_coff + c_out) of an (B, out_ctot, .) tensor (the slot of one
+//    scale in the concatenated multi-scale output of pointnet2_modules.py:55: no torch.cat pass).
+WS3D_API int ws3d_mlp_layer_into(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *shift,
+                                 const float *x1, const float *x2, float *out, int out_ctot, int out_coff, int relu, int pool,
+                                 ws3d_stream_t stream) {
   const char *what = "mlp_layer";
+  if (out_coff < 0 || out_coff + c_out > out_ctot) return fail_arg("mlp_layer (output channel slot)");
   if (b < 0 || c_out <= 0 || c1 <= 0 || c2 < 0 || cols < 0 || c_out_pad % kTileM || c_out_pad < c_out) return fail_arg(what);
   if (b == 0 || cols == 0) return 0;
   if (!w || !shift || !x1 || !out || (c2 > 0 && !x2)) return fail_arg(what);
@@ -386,6 +391,7 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
     return fail_arg("mlp_layer (pool must be a power of two dividing the column tile and cols)");
   MlpParams prm;
   prm.c_out = c_out; prm.cols = cols; prm.pool = pool; prm.flags = relu; prm.shift = shift; prm.out = out;
+  prm.out_ctot = out_ctot; prm.out_coff = out_coff;
   prm.nk1 = ceil_div(c1, kChunkK);
   prm.nk2 = c2 > 0 ? ceil_div(c2, kChunkK) : 0;
   prm.n_m_tiles = c_out_pad / kTileM;
@@ -434,4 +440,9 @@ WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int
   }
 #undef WS3D_MLP_LAUNCH
   return check_launch(what);
+}
+
+WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *shift,
+                            const float *x1, const float *x2, float *out, int relu, int pool, ws3d_stream_t stream) {
+  return ws3d_mlp_layer_into(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, c_out, 0, relu, pool, stream);
 }

@@ -28,7 +28,8 @@ int ball_query_grid(int nr, int b, int n, int m, const float *radius, const int 
 
 // three_nn_grid.cu: ring search over a cell grid of the known points
 bool three_nn_grid_applicable(int b, int n, int m);
-int three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, cudaStream_t stream);
+int three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, float *weight,
+                  cudaStream_t stream);
 
 namespace {
 
@@ -119,8 +120,10 @@ __global__ void __launch_bounds__(1024, 1) ball_query_kernel(BqParams<NR> prm) {
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int K = prm.nsample[r];
-      if (cnt[r] > 0)
-        for (int s = cnt[r] + lane; s < K; s += 32) row[r][s] = first[r];
+      // a centre without any neighbour gets a zero row: what the caller's zero fill (pointnet2_utils.py:218) leaves
+      // there in the reference -- written here so that callers of this library need no fill pass
+      const int fill = cnt[r] > 0 ? first[r] : 0;
+      for (int s = cnt[r] + lane; s < K; s += 32) row[r][s] = fill;
     }
   }
 }
@@ -143,8 +146,7 @@ __global__ void ball_query_generic_kernel(int n, int m, float r2, int K, const f
       row[cnt++] = k;
     }
   }
-  if (cnt > 0)
-    for (int s = cnt; s < K; ++s) row[s] = first;
+  for (int s = cnt; s < K; ++s) row[s] = cnt > 0 ? first : 0;   // no neighbour: zero row (see ball_query_kernel)
 }
 
 template <int NR>
@@ -163,10 +165,10 @@ int launch_ball_query(int b, int n, int m, const float *radius, const int *nsamp
   int ctas_per_cloud, q_per_cta;
   if (smem > 100 * 1024) {
     // one resident CTA per SM: exactly one wave, queries handed out dynamically inside the CTA
-    ctas_per_cloud = kNumSMs / b > 0 ? kNumSMs / b : 1;
+    ctas_per_cloud = num_sms() / b > 0 ? num_sms() / b : 1;
     q_per_cta = ceil_div(m, ctas_per_cloud);
   } else {
-    ctas_per_cloud = ceil_div(2 * kNumSMs, b);
+    ctas_per_cloud = ceil_div(2 * num_sms(), b);
     q_per_cta = ceil_div(m, ctas_per_cloud);
     if (q_per_cta < warps) q_per_cta = warps;  // do not reload the cloud for less than a query per warp
   }
@@ -184,7 +186,15 @@ int ball_query_dispatch(int nr, int b, int n, int m, const float *radius, const 
   if (b < 0 || n < 0 || m < 0) return fail_arg("ball_query");
   for (int r = 0; r < nr; ++r)
     if (nsample[r] < 0) return fail_arg("ball_query (nsample)");
-  if (b == 0 || m == 0 || n == 0) return 0;
+  if (b == 0 || m == 0) return 0;
+  if (n == 0) {  // no points: every row is a no-neighbour row
+    for (int r = 0; r < nr; ++r) {
+      if (!idx[r] || nsample[r] == 0) continue;
+      cudaError_t e = cudaMemsetAsync(idx[r], 0, (size_t)b * m * nsample[r] * sizeof(int), stream);
+      if (e != cudaSuccess) { set_error("ball_query: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    return 0;
+  }
   if (!new_xyz || !xyz) return fail_arg("ball_query (null pointer)");
   if (b > 65535) return fail_arg("ball_query (batch > 65535)");
   {
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(kGatherThreads) group_points_grad_kernel(int c
 // Channels handled by one CTA: all of them when the (element tile x cloud) grid already fills the
 // GPU, otherwise split so that at least ~4 CTAs per SM exist (idx is re-read once per split only).
 int channels_per_cta(long long ctas_without_split, int c) {
-  const long long want = 4LL * kNumSMs;
+  const long long want = 4LL * num_sms();
   if (ctas_without_split >= want || c <= 8) return c > 0 ? c : 1;
   long long splits = (want + ctas_without_split - 1) / ctas_without_split;
   int per = (int)((c + splits - 1) / splits);
@@ -305,7 +315,8 @@ constexpr int kNnChunk = 4096;  // known points per stage (64 KB)
 
 __global__ void __launch_bounds__(kNnThreads) three_nn_kernel(int n, int m, const float *__restrict__ unknown,
                                                                const float *__restrict__ known,
-                                                               float *__restrict__ dist2, int *__restrict__ idx) {
+                                                               float *__restrict__ dist2, int *__restrict__ idx,
+                                                               float *__restrict__ weight) {
   extern __shared__ __align__(16) float4 s_known[];
   const size_t cloud = blockIdx.y;
   const int i = blockIdx.x * kNnThreads + threadIdx.x;
@@ -345,12 +356,7 @@ __global__ void __launch_bounds__(kNnThreads) three_nn_kernel(int n, int m, cons
       }
     }
   }
-  if (i < n) {
-    float *od = dist2 + (cloud * (size_t)n + i) * 3;
-    int *oi = idx + (cloud * (size_t)n + i) * 3;
-    od[0] = b1; od[1] = b2; od[2] = b3;
-    oi[0] = i1; oi[1] = i2; oi[2] = i3;
-  }
+  if (i < n) store_three_nn(dist2, idx, weight, cloud * (size_t)n + i, b1, b2, b3, i1, i2, i3);
 }
 
 // three_interpolate: out[b,c,i] = fma(w2,p2, fma(w0,p0, rn(w1*p1)))  (reference SASS order)
@@ -602,19 +608,35 @@ WS3D_API int ws3d_gather_points_grad(int b, int c, int n, int npoints, const flo
                         "gather_points_grad");
 }
 
-WS3D_API int ws3d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
-                           ws3d_stream_t stream) {
+namespace ws3d {
+namespace {
+int three_nn_dispatch(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, float *weight,
+                      cudaStream_t stream) {
   if (b < 0 || n < 0 || m < 0) return fail_arg("three_nn");
   if (b == 0 || n == 0) return 0;
-  if (!unknown || !dist2 || !idx || (m > 0 && !known)) return fail_arg("three_nn (null pointer)");
+  if (!unknown || (!dist2 && !weight) || !idx || (m > 0 && !known)) return fail_arg("three_nn (null pointer)");
   if (b > 65535) return fail_arg("three_nn (batch > 65535)");
-  if (three_nn_grid_applicable(b, n, m)) return three_nn_grid(b, n, m, unknown, known, dist2, idx, to_stream(stream));
+  if (three_nn_grid_applicable(b, n, m)) return three_nn_grid(b, n, m, unknown, known, dist2, idx, weight, stream);
   const size_t smem = (size_t)(m < kNnChunk ? (m > 0 ? m : 1) : kNnChunk) * sizeof(float4);
   cudaError_t e = cudaFuncSetAttribute(three_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNnChunk * sizeof(float4)));
   if (e != cudaSuccess) { set_error("three_nn: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   dim3 grid((unsigned)ceil_div(n, kNnThreads), (unsigned)b);
-  three_nn_kernel<<<grid, kNnThreads, smem, to_stream(stream)>>>(n, m, unknown, known, dist2, idx);
+  three_nn_kernel<<<grid, kNnThreads, smem, stream>>>(n, m, unknown, known, dist2, idx, weight);
   return check_launch("three_nn");
+}
+}  // namespace
+}  // namespace ws3d
+
+WS3D_API int ws3d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                           ws3d_stream_t stream) {
+  if (b > 0 && n > 0 && !dist2) return fail_arg("three_nn (null pointer)");
+  return three_nn_dispatch(b, n, m, unknown, known, dist2, idx, nullptr, to_stream(stream));
+}
+
+WS3D_API int ws3d_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                                   float *weight, ws3d_stream_t stream) {
+  if (b > 0 && n > 0 && !weight) return fail_arg("three_nn_weights (null pointer)");
+  return three_nn_dispatch(b, n, m, unknown, known, dist2, idx, weight, to_stream(stream));
 }
 
 static int three_interpolate_impl(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
@@ -628,11 +650,11 @@ static int three_interpolate_impl(int b, int c, int m, int n, const float *point
     int cb = (int)((128 * 1024) / ((size_t)m * 4));
     if (cb > 64) cb = 64;
     if (cb > c) cb = c;
-    while (cb > 8 && (long long)ceil_div(c, cb) * b < 2LL * kNumSMs) cb >>= 1;
+    while (cb > 8 && (long long)ceil_div(c, cb) * b < 2LL * num_sms()) cb >>= 1;
     if (c % 4 == 0 && cb % 4 != 0) cb = cb > 4 ? (cb & ~3) : 4;   // keep the four-channel interleaved kernel available
     const int chunks = ceil_div(c, cb);
     int nsplit = 1;
-    while ((long long)chunks * b * nsplit < 2LL * kNumSMs && ceil_div(n, nsplit * 2) >= 2 * 512) nsplit <<= 1;
+    while ((long long)chunks * b * nsplit < 2LL * num_sms() && ceil_div(n, nsplit * 2) >= 2 * 512) nsplit <<= 1;
     const int n_per_cta = ceil_div(n, nsplit);
     const int threads = n_per_cta >= 8192 ? 1024 : 512;  // more warps hide the stencil loads when there is enough work
     const size_t smem = (size_t)cb * m * sizeof(float);

@@ -153,8 +153,8 @@ int group_concat(int b, int n, int m, int c, int K, int use_xyz, const float *xy
                    ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
   const long long gx = (per_cloud + kThreads * (vec ? 4 : 1) - 1) / (kThreads * (vec ? 4 : 1));
   int c_per_cta = c > 0 ? c : 1;
-  if (gx * b < 4LL * kNumSMs && c > 8) {
-    const long long splits = (4LL * kNumSMs + gx * b - 1) / (gx * b);
+  if (gx * b < 4LL * num_sms() && c > 8) {
+    const long long splits = (4LL * num_sms() + gx * b - 1) / (gx * b);
     c_per_cta = (int)((c + splits - 1) / splits);
     if (c_per_cta < 8) c_per_cta = 8;
   }
@@ -209,8 +209,8 @@ WS3D_API int ws3d_group_affine(int b, int n, int m, int c, int nsample, const fl
                    ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
   const long long gx = (per_cloud + kThreads * (vec ? 4 : 1) - 1) / (kThreads * (vec ? 4 : 1));
   int c_per_cta = c;
-  if (gx * b < 4LL * kNumSMs && c > 8) {
-    const long long splits = (4LL * kNumSMs + gx * b - 1) / (gx * b);
+  if (gx * b < 4LL * num_sms() && c > 8) {
+    const long long splits = (4LL * num_sms() + gx * b - 1) / (gx * b);
     c_per_cta = (int)((c + splits - 1) / splits);
     if (c_per_cta < 8) c_per_cta = 8;
   }
@@ -218,4 +218,28 @@ WS3D_API int ws3d_group_affine(int b, int n, int m, int c, int nsample, const fl
   if (vec) group_affine_kernel<4><<<grid, kThreads, 0, to_stream(stream)>>>(c, n, m, nsample, c_per_cta, flags, P, xyz, new_xyz, wx, shift, idx, out);
   else group_affine_kernel<1><<<grid, kThreads, 0, to_stream(stream)>>>(c, n, m, nsample, c_per_cta, flags, P, xyz, new_xyz, wx, shift, idx, out);
   return check_launch("group_affine");
+}
+
+namespace ws3d {
+namespace {
+// pc (B,N,3+C) -> xyz (B,N,3), features (B,C,N): thread per point (lib/net/pointnet2_msg.py:52-60)
+__global__ void __launch_bounds__(256) split_pointcloud_kernel(int n, int c, const float *__restrict__ pc, float *__restrict__ xyz,
+                                                                float *__restrict__ feat) {
+  const size_t cloud = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float *p = pc + (cloud * (size_t)n + i) * (size_t)(3 + c);
+  float *x = xyz + (cloud * (size_t)n + i) * 3;
+  x[0] = __ldg(p); x[1] = __ldg(p + 1); x[2] = __ldg(p + 2);
+  for (int k = 0; k < c; ++k) feat[(cloud * (size_t)c + k) * n + i] = __ldg(p + 3 + k);
+}
+}  // namespace
+}  // namespace ws3d
+
+WS3D_API int ws3d_split_pointcloud(int b, int n, int c, const float *pc, float *xyz, float *features, ws3d_stream_t stream) {
+  if (b < 0 || n < 0 || c < 0 || b > 65535) return fail_arg("split_pointcloud");
+  if (b == 0 || n == 0) return 0;
+  if (!pc || !xyz || (c > 0 && !features)) return fail_arg("split_pointcloud (null pointer)");
+  split_pointcloud_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)b), 256, 0, to_stream(stream)>>>(n, c, pc, xyz, features);
+  return check_launch("split_pointcloud");
 }

@@ -159,7 +159,7 @@ int roipool_dispatch(int batch, int n, int m, int c, int s, const float *xyz, co
   const size_t smem = (size_t)((chunk_cap * 3 + 3) & ~3) * sizeof(float) +
                       (prm.sel_g ? 0 : (size_t)kMaxWarps * (s < kMaxSel ? s : kMaxSel) * sizeof(int)) + 16;
   const int resident = smem > 110 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 4);  // CTAs per SM by shared memory
-  int ctas_per_cloud = (kNumSMs * resident) / batch;
+  int ctas_per_cloud = (num_sms() * resident) / batch;
   if (ctas_per_cloud < 1) ctas_per_cloud = 1;
   int boxes_per_cta = ceil_div(m, ctas_per_cloud);
   boxes_per_cta = ceil_div(boxes_per_cta, kMaxWarps) * kMaxWarps;  // whole groups of one box per warp

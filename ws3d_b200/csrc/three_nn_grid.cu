@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(kThreads) three_nn_grid_kernel(int n, int m, c
                                                                   const GridHdr *__restrict__ hdrs,
                                                                   const int *__restrict__ cell_start,
                                                                   const float4 *__restrict__ sorted,
-                                                                  float *__restrict__ dist2, int *__restrict__ idx) {
+                                                                  float *__restrict__ dist2, int *__restrict__ idx,
+                                                                  float *__restrict__ weight) {
   const size_t cloud = blockIdx.y;
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
@@ -94,10 +95,7 @@ __global__ void __launch_bounds__(kThreads) three_nn_grid_kernel(int n, int m, c
       }
     }
   }
-  float *od = dist2 + (cloud * (size_t)n + i) * 3;
-  int *oi = idx + (cloud * (size_t)n + i) * 3;
-  od[0] = b.d1; od[1] = b.d2; od[2] = b.d3;
-  oi[0] = b.i1; oi[1] = b.i2; oi[2] = b.i3;
+  store_three_nn(dist2, idx, weight, cloud * (size_t)n + i, b.d1, b.d2, b.d3, b.i1, b.i2, b.i3);
 }
 
 }  // namespace
@@ -107,7 +105,8 @@ bool three_nn_grid_applicable(int b, int n, int m) {
   return enabled && m >= 512 && m <= 65536 && n >= 1024 && b >= 1 && b <= 65535;
 }
 
-int three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, cudaStream_t stream) {
+int three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, float *weight,
+                  cudaStream_t stream) {
   const size_t hdr_bytes = ((size_t)b * sizeof(GridHdr) + 255) & ~(size_t)255;
   const size_t start_bytes = ((size_t)b * (kMaxCells + 1) * sizeof(int) + 255) & ~(size_t)255;
   const size_t sorted_bytes = (size_t)b * m * sizeof(float4);
@@ -125,7 +124,7 @@ int three_nn_grid(int b, int n, int m, const float *unknown, const float *known,
   int rc = check_launch("three_nn (grid build)");
   if (rc) return rc;
   dim3 grid((unsigned)ceil_div(n, kThreads), (unsigned)b);
-  three_nn_grid_kernel<<<grid, kThreads, 0, stream>>>(n, m, unknown, hdrs, cell_start, sorted, dist2, idx);
+  three_nn_grid_kernel<<<grid, kThreads, 0, stream>>>(n, m, unknown, hdrs, cell_start, sorted, dist2, idx, weight);
   return check_launch("three_nn (grid)");
 }
 

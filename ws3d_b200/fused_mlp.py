@@ -29,9 +29,50 @@ def _round_tf32(t: torch.Tensor) -> torch.Tensor:
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def block_foldable(block: nn.Module) -> bool:
+    """A block the folded kernels reproduce: children exactly [conv 1x1, optional BatchNorm wrapper (`bn.bn`), optional
+    nn.ReLU] in that order.  pytorch_utils also builds preact blocks (norm / activation BEFORE the convolution), instance
+    norm (`in`) and arbitrary activations: those keep the PyTorch path."""
+    names = [n for n, _ in block.named_children()]
+    if not names or names[0] != "conv" or names != [n for n in ("conv", "bn", "activation") if n in names]:
+        return False
+    conv = block.conv
+    if not isinstance(conv, (nn.Conv1d, nn.Conv2d)) or any(k != 1 for k in conv.kernel_size) or any(k != 1 for k in conv.stride):
+        return False
+    if any(p != 0 for p in conv.padding) or conv.groups != 1:
+        return False
+    if "bn" in names and not isinstance(getattr(block.bn, "bn", None), (nn.BatchNorm1d, nn.BatchNorm2d)):
+        return False
+    return "activation" not in names or isinstance(block.activation, nn.ReLU)
+
+
+def mlp_foldable(mlp) -> bool:
+    blocks = [m for m in mlp if not isinstance(m, nn.Dropout)]   # dropout is the identity in eval mode
+    return len(blocks) > 0 and all(block_foldable(b) for b in blocks)
+
+
+def _module_foldable(module: nn.Module) -> bool:
+    """Structure check of every shared MLP the module owns (`mlps` of an SA layer, `mlp` of an FP layer, the heads of
+    the RPN), cached on the module."""
+    ok = module.__dict__.get("_ws3d_foldable")
+    if ok is None:
+        seqs = []
+        if isinstance(getattr(module, "mlps", None), nn.ModuleList):
+            seqs += list(module.mlps)
+        if isinstance(getattr(module, "mlp", None), nn.Sequential):
+            seqs.append(module.mlp)
+        for name in ("rpn_cls_layer", "rpn_reg_layer"):
+            if isinstance(getattr(module, name, None), nn.Sequential):
+                seqs.append(getattr(module, name))
+        ok = module.__dict__["_ws3d_foldable"] = all(mlp_foldable(q) for q in seqs)
+    return ok
+
+
 def enabled_for(module: nn.Module) -> bool:
-    """The fused path is taken in eval mode, without autograd, when TF32 convolutions are allowed."""
-    return (not module.training) and (not torch.is_grad_enabled()) and torch.backends.cudnn.allow_tf32
+    """The fused path is taken in eval mode, without autograd, when TF32 convolutions are allowed and every block of the
+    module's shared MLPs is conv -> [BatchNorm] -> [ReLU] (anything else keeps the PyTorch path)."""
+    return ((not module.training) and (not torch.is_grad_enabled()) and torch.backends.cudnn.allow_tf32
+            and _module_foldable(module))
 
 
 class _Layer:
@@ -55,18 +96,26 @@ class FoldedMLP:
     def _stamp(self):
         return tuple((p.data_ptr(), p._version) for p in self._params())
 
+    @staticmethod
+    def fold_block(block: nn.Module):
+        """(W', shift, relu) of one conv1x1 [+ BatchNorm(eval)] [+ ReLU] block: y = relu(W' x + shift)."""
+        conv = block.conv
+        assert conv.kernel_size in ((1, 1), (1,)) and conv.stride in ((1, 1), (1,)), "shared MLPs are 1x1 convolutions"
+        w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
+        shift = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+        if hasattr(block, "bn"):
+            bn = block.bn.bn
+            scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+            w = w * scale[:, None]
+            shift = (shift - bn.running_mean) * scale + bn.bias.detach()
+        return w, shift, hasattr(block, "activation")
+
+    def _matrices(self):
+        return [self.fold_block(block) for block in self._mlp]
+
     def _build(self):
         self.layers = []
-        for li, block in enumerate(self._mlp):
-            conv = block.conv
-            assert conv.kernel_size in ((1, 1), (1,)) and conv.stride in ((1, 1), (1,)), "shared MLPs are 1x1 convolutions"
-            w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
-            shift = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
-            if hasattr(block, "bn"):
-                bn = block.bn.bn
-                scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
-                w = w * scale[:, None]
-                shift = (shift - bn.running_mean) * scale + bn.bias.detach()
+        for li, (w, shift, relu) in enumerate(self._matrices()):
             c_out, c_in = w.shape
             splits = self._first_split if (li == 0 and self._first_split is not None and self._first_split[1] > 0) else (c_in, 0)
             assert sum(splits) == c_in
@@ -87,12 +136,14 @@ class FoldedMLP:
                 wp[o:o + c_out] = wp[:c_out]
                 sp[o:o + c_out] = sp[:c_out]
             lay.w, lay.shift, lay.splits = wp.contiguous(), sp, splits
-            lay.relu = hasattr(block, "activation")
+            lay.relu = relu
             self.layers.append(lay)
         self._versions = self._stamp()
 
-    def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, pool: int = 0) -> torch.Tensor:
-        """x1 (B, c1, cols) [, x2 (B, c2, cols)] -> (B, c_last, cols) or (B, c_last, cols // pool)."""
+    def __call__(self, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, pool: int = 0,
+                 out: Optional[torch.Tensor] = None, out_coff: int = 0) -> torch.Tensor:
+        """x1 (B, c1, cols) [, x2 (B, c2, cols)] -> (B, c_last, cols) or (B, c_last, cols // pool).
+        `out` (B, c_total, .) / `out_coff`: the last layer writes its channels into that slot instead of a new tensor."""
         if self._versions != self._stamp():
             self._build()  # parameters were updated (training step, load_state_dict, .to())
         B, _, cols = x1.shape
@@ -100,7 +151,9 @@ class FoldedMLP:
         for li, lay in enumerate(self.layers):
             last = li == len(self.layers) - 1
             p = pool if last else 0
-            out = torch.empty((B, lay.c_out, cols // p if p else cols), dtype=torch.float32, device=x1.device)
+            into = out if (last and out is not None) else None
+            res = into if into is not None else torch.empty((B, lay.c_out, cols // p if p else cols), dtype=torch.float32,
+                                                            device=x1.device)
             c1 = cur1.shape[1]
             c2 = cur2.shape[1] if cur2 is not None else 0
             assert (c1, c2) == tuple(lay.splits), ((c1, c2), lay.splits)
@@ -108,9 +161,35 @@ class FoldedMLP:
             while p and (_TILE_M >> rep) % p:   # a pooling group must fit the column share of one epilogue warp
                 rep -= 1                        # (fewer copies are used; the extra replicated rows are simply masked)
             flags = int(lay.relu) | (0 if last else 2) | (rep << 4)  # intermediates are stored TF32-rounded
-            native.mlp_layer(B, lay.c_out, lay.c_out_pad, c1, c2, cols, lay.w, lay.shift, cur1, cur2, out, flags, p)
-            cur1, cur2 = out, None
+            if into is not None:
+                native.mlp_layer(B, lay.c_out, lay.c_out_pad, c1, c2, cols, lay.w, lay.shift, cur1, cur2, res, flags, p,
+                                 out_ctot=into.shape[1], out_coff=out_coff)
+            else:
+                native.mlp_layer(B, lay.c_out, lay.c_out_pad, c1, c2, cols, lay.w, lay.shift, cur1, cur2, res, flags, p)
+            cur1, cur2 = res, None
         return cur1
+
+
+class FoldedHeads(FoldedMLP):
+    """Several per-point heads of the same depth over the same input (the RPN's classification and regression heads,
+    lib/net/rpn.py:31-45) as ONE chain of launches: the first layers are stacked (they read the same features), the
+    deeper ones are block-diagonal.  Output channels are the heads' outputs in order."""
+
+    def __init__(self, heads):
+        self._heads = [nn.Sequential(*[m for m in h if not isinstance(m, nn.Dropout)]) for h in heads]
+        assert len({len(h) for h in self._heads}) == 1, "heads must have the same number of layers"
+        self.out_channels = [h[-1].conv.out_channels for h in self._heads]
+        super().__init__(nn.Sequential(*[b for h in self._heads for b in h]))   # (parameters for the version stamp)
+
+    def _matrices(self):
+        per_head = [[self.fold_block(b) for b in h] for h in self._heads]
+        out = []
+        for li in range(len(per_head[0])):
+            ws, shifts, relus = zip(*[ph[li] for ph in per_head])
+            assert len(set(relus)) == 1, "heads must agree on the activation of every layer"
+            w = torch.cat(ws, dim=0) if li == 0 else torch.block_diag(*ws)
+            out.append((w, torch.cat(shifts), relus[0]))
+        return out
 
 
 def supported(cols: int, pool: int) -> bool:

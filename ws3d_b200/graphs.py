@@ -176,6 +176,12 @@ class StreamedBackboneRunner:
                  feature_streams: int = 1, warmup: int = 2):
         from . import native
         assert example.is_cuda and lookahead >= 1
+        # every buffer set captures its cell grids in its own scratch arena (arena 0 stays with eager callers): two
+        # sets sharing an arena would replay on different coordinate streams over the same scratch addresses
+        arenas = native.num_arenas()
+        if lookahead + 1 > arenas - 1:
+            raise ValueError(f"lookahead {lookahead} needs {lookahead + 1} scratch arenas; the library has {arenas - 1} besides "
+                             "the default one (ws3d_num_arenas)")
         dev = example.device
         self.device, self.backbone, self.lookahead = dev, backbone, lookahead
         # feature_streams > 1: the feature phases of consecutive batches alternate between that many internal streams
@@ -199,7 +205,7 @@ class StreamedBackboneRunner:
         prev_mode = native.set_fps_mode(fps_mode)
         try:
             for k in range(self.nbuf):   # the library's cached scratch of every arena must exist before capture
-                prev_arena = native.set_workspace_arena(1 + k % 7)
+                prev_arena = native.set_workspace_arena(1 + k)
                 try:
                     with torch.no_grad():
                         backbone.coordinate_phase(self.inputs[k])
@@ -208,7 +214,7 @@ class StreamedBackboneRunner:
             torch.cuda.synchronize(dev)
             for k in range(self.nbuf):
                 # every buffer set owns its scratch arena: coordinate phases of different batches overlap in time
-                prev_arena = native.set_workspace_arena(1 + k % 7)
+                prev_arena = native.set_workspace_arena(1 + k)
                 try:
                     g = torch.cuda.CUDAGraph()
                     with torch.no_grad(), torch.cuda.graph(g):

@@ -62,6 +62,14 @@ class Pointnet2MSG(nn.Module):
 
     @staticmethod
     def _break_up_pc(pc):
+        """(B,N,3+C) -> xyz (B,N,3), features (B,C,N) or None (lib/net/pointnet2_msg.py:52-60); one launch on the GPU."""
+        if pc.is_cuda and pc.is_contiguous() and pc.dtype == torch.float32 and not (torch.is_grad_enabled() and pc.requires_grad):
+            from . import native
+            B, N, C = pc.shape[0], pc.shape[1], pc.shape[2] - 3
+            xyz = torch.empty((B, N, 3), dtype=torch.float32, device=pc.device)
+            features = torch.empty((B, C, N), dtype=torch.float32, device=pc.device) if C > 0 else None
+            native.split_pointcloud(pc, xyz, features)
+            return xyz, features
         xyz = pc[..., 0:3].contiguous()
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
@@ -79,19 +87,22 @@ class Pointnet2MSG(nn.Module):
         every scale and the three-nearest-neighbour interpolation stencils.  It is a chain of latency-bound kernels
         that needs few SMs and no bandwidth, so a caller with a stream of batches runs it AHEAD of the feature phase,
         beside the previous batches' feature phases (graphs.StreamedBackboneRunner)."""
-        xyz = pointcloud[..., 0:3].contiguous()
+        xyz, features = self._break_up_pc(pointcloud)
         l_xyz, idx = [xyz], []
         for sa in self.SA_modules:
             _, nx = pointnet2_utils.sample_and_gather(l_xyz[-1], sa.npoint)
             idx.append(sa._neighbour_indices(l_xyz[-1], nx))
             l_xyz.append(nx)
         nn_ = [PointnetFPModule.interpolation_weights(l_xyz[i], l_xyz[i + 1]) for i in range(len(self.FP_modules))]
-        return {"xyz": l_xyz[1:], "idx": idx, "nn": nn_}
+        return {"xyz": l_xyz[1:], "idx": idx, "nn": nn_, "xyz0": xyz, "feat0": features}
 
     def feature_phase(self, pointcloud: torch.Tensor, plan: dict):
         """The rest: grouping + MLPs of the SA levels, interpolation + MLPs of the FP levels, on precomputed samples,
         neighbour indices and stencils.  Same kernels and arithmetic as forward()."""
-        xyz, features = self._break_up_pc(pointcloud)
+        if "xyz0" in plan:   # the coordinate phase has already split the cloud
+            xyz, features = plan["xyz0"], plan["feat0"]
+        else:
+            xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features = [xyz] + list(plan["xyz"]), [features]
         for k, sa in enumerate(self.SA_modules):
             _, nf = sa(l_xyz[k], l_features[k], new_xyz=l_xyz[k + 1], indices=plan["idx"][k])
@@ -207,23 +218,16 @@ class RPN(nn.Module):
             backbone_xyz, backbone_features = self.backbone_net.feature_phase(pts_input, plan)
         else:
             backbone_xyz, backbone_features = self.backbone_net(pts_input, first_samples=first_samples)
-        if (backbone_features.is_cuda and fused_mlp.enabled_for(self) and os.environ.get("WS3D_SCALE_STREAMS", "1") != "0"):
-            # inference: the two heads are independent chains of two launches each -> side by side on two streams
-            main = torch.cuda.current_stream(backbone_features.device)
-            side = self.__dict__.get("_head_stream")
-            if side is None or side.device != backbone_features.device:
-                side = self.__dict__["_head_stream"] = torch.cuda.Stream(device=backbone_features.device)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            with torch.cuda.stream(side):
-                side.wait_event(fork)
-                rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()
-                done = torch.cuda.Event()
-                done.record(side)
-            backbone_features.record_stream(side)
-            rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
-            rpn_reg.record_stream(main)
-            main.wait_event(done)
+        if (backbone_features.is_cuda and fused_mlp.enabled_for(self) and backbone_features.is_contiguous()
+                and fused_mlp.supported(backbone_features.shape[2], 0) and len(self.rpn_cls_layer) == len(self.rpn_reg_layer)):
+            # inference: both heads as one chain of two launches (stacked first layers, block-diagonal second layers)
+            heads = self.__dict__.get("_folded_heads2")
+            if heads is None:
+                heads = self.__dict__["_folded_heads2"] = fused_mlp.FoldedHeads([self.rpn_cls_layer, self.rpn_reg_layer])
+            both = heads(backbone_features)                                   # (B, 1 + reg_channel, N)
+            n_cls = heads.out_channels[0]
+            rpn_cls = both[:, :n_cls].transpose(1, 2).contiguous()            # (B, N, 1)
+            rpn_reg = both[:, n_cls:].transpose(1, 2).contiguous()            # (B, N, reg_channel)
         else:
             rpn_cls = self._head("rpn_cls_layer", backbone_features).transpose(1, 2).contiguous()
             rpn_reg = self._head("rpn_reg_layer", backbone_features).transpose(1, 2).contiguous()

@@ -10,12 +10,12 @@ the reference module names so the reference's Python wrappers run on top unmodif
 import torch
 
 from . import _C
-from ._C import check, device_of, lib, ptr, require_cuda, stream
+from ._C import F32, I32, I64, U8, check, device_of, lib, ptr, require, stream
 
 
 # ---- pointnet2_cuda ---------------------------------------------------------------------------
 def furthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_tensor):
-    require_cuda(points_tensor, temp_tensor, idx_tensor)
+    require("furthest_point_sampling", (points_tensor, F32, b * n * 3), (temp_tensor, F32, b * n), (idx_tensor, I32, b * m))
     with device_of(points_tensor):
         check(lib().ws3d_furthest_point_sampling(b, n, m, ptr(points_tensor), ptr(temp_tensor), ptr(idx_tensor),
                                                  stream()), "furthest_point_sampling")
@@ -23,7 +23,7 @@ def furthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_ten
 
 
 def gather_points_wrapper(b, c, n, npoints, points_tensor, idx_tensor, out_tensor):
-    require_cuda(points_tensor, idx_tensor, out_tensor)
+    require("gather_points", (points_tensor, F32, b * c * n), (idx_tensor, I32, b * npoints), (out_tensor, F32, b * c * npoints))
     with device_of(points_tensor):
         check(lib().ws3d_gather_points(b, c, n, npoints, ptr(points_tensor), ptr(idx_tensor), ptr(out_tensor),
                                        stream()), "gather_points")
@@ -31,7 +31,8 @@ def gather_points_wrapper(b, c, n, npoints, points_tensor, idx_tensor, out_tenso
 
 
 def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, grad_points_tensor):
-    require_cuda(grad_out_tensor, idx_tensor, grad_points_tensor)
+    require("gather_points_grad", (grad_out_tensor, F32, b * c * npoints), (idx_tensor, I32, b * npoints),
+            (grad_points_tensor, F32, b * c * n))
     with device_of(grad_out_tensor):
         check(lib().ws3d_gather_points_grad(b, c, n, npoints, ptr(grad_out_tensor), ptr(idx_tensor),
                                             ptr(grad_points_tensor), stream()), "gather_points_grad")
@@ -39,7 +40,7 @@ def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, gr
 
 
 def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx_tensor):
-    require_cuda(new_xyz_tensor, xyz_tensor, idx_tensor)
+    require("ball_query", (new_xyz_tensor, F32, b * m * 3), (xyz_tensor, F32, b * n * 3), (idx_tensor, I32, b * m * nsample))
     with device_of(xyz_tensor):
         check(lib().ws3d_ball_query(b, n, m, float(radius), nsample, ptr(new_xyz_tensor), ptr(xyz_tensor),
                                     ptr(idx_tensor), stream()), "ball_query")
@@ -47,7 +48,8 @@ def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx
 
 
 def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, out_tensor):
-    require_cuda(points_tensor, idx_tensor, out_tensor)
+    require("group_points", (points_tensor, F32, b * c * n), (idx_tensor, I32, b * npoints * nsample),
+            (out_tensor, F32, b * c * npoints * nsample))
     with device_of(points_tensor):
         check(lib().ws3d_group_points(b, c, n, npoints, nsample, ptr(points_tensor), ptr(idx_tensor),
                                       ptr(out_tensor), stream()), "group_points")
@@ -55,7 +57,8 @@ def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, o
 
 
 def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_tensor, grad_points_tensor):
-    require_cuda(grad_out_tensor, idx_tensor, grad_points_tensor)
+    require("group_points_grad", (grad_out_tensor, F32, b * c * npoints * nsample), (idx_tensor, I32, b * npoints * nsample),
+            (grad_points_tensor, F32, b * c * n))
     with device_of(grad_out_tensor):
         check(lib().ws3d_group_points_grad(b, c, n, npoints, nsample, ptr(grad_out_tensor), ptr(idx_tensor),
                                            ptr(grad_points_tensor), stream()), "group_points_grad")
@@ -63,21 +66,34 @@ def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_te
 
 
 def three_nn_wrapper(b, n, m, unknown_tensor, known_tensor, dist2_tensor, idx_tensor):
-    require_cuda(unknown_tensor, known_tensor, dist2_tensor, idx_tensor)
+    require("three_nn", (unknown_tensor, F32, b * n * 3), (known_tensor, F32, b * m * 3), (dist2_tensor, F32, b * n * 3),
+            (idx_tensor, I32, b * n * 3))
     with device_of(unknown_tensor):
         check(lib().ws3d_three_nn(b, n, m, ptr(unknown_tensor), ptr(known_tensor), ptr(dist2_tensor),
                                   ptr(idx_tensor), stream()), "three_nn")
 
 
+def three_nn_weights(b, n, m, unknown, known, dist2, idx, weight):
+    """Extension: three_nn + the normalised inverse-distance weights of pointnet2_modules.py:139-144 in one launch.
+    dist2 (B,n,3) may be None."""
+    require("three_nn_weights", (unknown, F32, b * n * 3), (known, F32, b * m * 3), (dist2, F32, b * n * 3), (idx, I32, b * n * 3),
+            (weight, F32, b * n * 3))
+    with device_of(unknown):
+        check(lib().ws3d_three_nn_weights(b, n, m, ptr(unknown), ptr(known), ptr(dist2), ptr(idx), ptr(weight), stream()),
+              "three_nn_weights")
+
+
 def three_interpolate_wrapper(b, c, m, n, points_tensor, idx_tensor, weight_tensor, out_tensor):
-    require_cuda(points_tensor, idx_tensor, weight_tensor, out_tensor)
+    require("three_interpolate", (points_tensor, F32, b * c * m), (idx_tensor, I32, b * n * 3), (weight_tensor, F32, b * n * 3),
+            (out_tensor, F32, b * c * n))
     with device_of(points_tensor):
         check(lib().ws3d_three_interpolate(b, c, m, n, ptr(points_tensor), ptr(idx_tensor), ptr(weight_tensor),
                                            ptr(out_tensor), stream()), "three_interpolate")
 
 
 def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor):
-    require_cuda(grad_out_tensor, idx_tensor, weight_tensor, grad_points_tensor)
+    require("three_interpolate_grad", (grad_out_tensor, F32, b * c * n), (idx_tensor, I32, b * n * 3),
+            (weight_tensor, F32, b * n * 3), (grad_points_tensor, F32, b * c * m))
     with device_of(grad_out_tensor):
         check(lib().ws3d_three_interpolate_grad(b, c, n, m, ptr(grad_out_tensor), ptr(idx_tensor),
                                                 ptr(weight_tensor), ptr(grad_points_tensor), stream()),
@@ -86,56 +102,70 @@ def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weig
 
 # ---- extensions (no reference counterpart; used by ws3d_b200.pointnet2_utils) -------------------
 def furthest_point_sampling_gather(b, n, m, xyz, temp, idx, new_xyz):
-    require_cuda(xyz, temp, idx, new_xyz)
+    require("furthest_point_sampling_gather", (xyz, F32, b * n * 3), (temp, F32, b * n), (idx, I32, b * m), (new_xyz, F32, b * m * 3))
     with device_of(xyz):
         check(lib().ws3d_furthest_point_sampling_gather(b, n, m, ptr(xyz), ptr(temp), ptr(idx), ptr(new_xyz),
                                                         stream()), "furthest_point_sampling_gather")
 
 
 def ball_query2(b, n, m, radius0, nsample0, radius1, nsample1, new_xyz, xyz, idx0, idx1):
-    require_cuda(new_xyz, xyz, idx0, idx1)
+    require("ball_query2", (new_xyz, F32, b * m * 3), (xyz, F32, b * n * 3), (idx0, I32, b * m * nsample0), (idx1, I32, b * m * nsample1))
     with device_of(xyz):
         check(lib().ws3d_ball_query2(b, n, m, float(radius0), nsample0, float(radius1), nsample1, ptr(new_xyz),
                                      ptr(xyz), ptr(idx0), ptr(idx1), stream()), "ball_query2")
 
 
 def group_concat(b, n, m, c, nsample, use_xyz, xyz, new_xyz, features, idx, out):
-    require_cuda(xyz, new_xyz, features, idx, out)
+    require("group_concat", (xyz, F32, b * n * 3), (new_xyz, F32, b * m * 3), (features, F32, b * c * n), (idx, I32, b * m * nsample),
+            (out, F32, b * (c + (3 if use_xyz else 0)) * m * nsample))
     with device_of(out):
         check(lib().ws3d_group_concat(b, n, m, c, nsample, int(bool(use_xyz)), ptr(xyz), ptr(new_xyz), ptr(features),
                                       ptr(idx), ptr(out), stream()), "group_concat")
 
 
 def query_and_group(b, n, m, c, radius, nsample, use_xyz, xyz, new_xyz, features, out, idx_out):
-    require_cuda(xyz, new_xyz, features, out, idx_out)
+    require("query_and_group", (xyz, F32, b * n * 3), (new_xyz, F32, b * m * 3), (features, F32, b * c * n),
+            (out, F32, b * (c + (3 if use_xyz else 0)) * m * nsample), (idx_out, I32, b * m * nsample))
     with device_of(out):
         check(lib().ws3d_query_and_group(b, n, m, c, float(radius), nsample, int(bool(use_xyz)), ptr(xyz),
                                          ptr(new_xyz), ptr(features), ptr(out), ptr(idx_out), stream()),
               "query_and_group")
 
 
-def mlp_layer(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool):
+def mlp_layer(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool, out_ctot=None, out_coff=0):
     """One BN-folded shared-MLP layer on the tcgen05 tensor cores (see include/ws3d_ops.h).
-    `relu`: bit 0 = ReLU, bit 1 = round the output to TF32 (it feeds another layer)."""
-    require_cuda(w, shift, x1, x2, out)
+    `relu`: bit 0 = ReLU, bit 1 = round the output to TF32 (it feeds another layer).
+    `out_ctot` / `out_coff`: write channels [out_coff, out_coff + c_out) of an (B, out_ctot, .) tensor."""
+    ctot = c_out if out_ctot is None else int(out_ctot)
+    require("mlp_layer", (w, F32, c_out_pad * (c1 + c2)), (shift, F32, c_out_pad), (x1, F32, b * c1 * cols), (x2, F32, b * c2 * cols),
+            (out, F32, b * ctot * (cols // pool if pool else cols)))
     with device_of(out):
-        check(lib().ws3d_mlp_layer(b, c_out, c_out_pad, c1, c2, cols, ptr(w), ptr(shift), ptr(x1), ptr(x2), ptr(out),
-                                   int(relu), int(pool), stream()), "mlp_layer")
+        check(lib().ws3d_mlp_layer_into(b, c_out, c_out_pad, c1, c2, cols, ptr(w), ptr(shift), ptr(x1), ptr(x2), ptr(out),
+                                        ctot, int(out_coff), int(relu), int(pool), stream()), "mlp_layer")
+
+
+def split_pointcloud(pc, xyz, features):
+    """Extension: pc (B,N,3+C) -> xyz (B,N,3), features (B,C,N) or None in one launch (lib/net/pointnet2_msg.py:52-60)."""
+    b, n, c = pc.size(0), pc.size(1), pc.size(2) - 3
+    require("split_pointcloud", (pc, F32, None), (xyz, F32, b * n * 3), (features, F32, b * c * n))
+    if pc.dim() != 3 or c < 0 or (c > 0 and features is None):
+        raise RuntimeError("split_pointcloud: pc must be (B, N, 3 + C) with a features output when C > 0")
+    with device_of(pc):
+        check(lib().ws3d_split_pointcloud(b, n, c, ptr(pc), ptr(xyz), ptr(features), stream()), "split_pointcloud")
 
 
 # ---- iou3d_cuda -------------------------------------------------------------------------------
-def _check_boxes(*ts):
-    for t in ts:
-        if t is None:
-            continue
-        if not t.is_cuda:
-            raise RuntimeError("boxes must be a CUDAtensor ")
-        if not t.is_contiguous():
-            raise RuntimeError("boxes must be contiguous ")
+def _bev(what, boxes):
+    """(N, 5) float32 CUDA BEV boxes, the reference's CHECK_INPUT (iou3d.cpp:10-12) plus dtype / shape."""
+    require(what, (boxes, F32, None))
+    if boxes.dim() != 2 or boxes.size(1) != 5:
+        raise RuntimeError(f"{what}: boxes must be (N, 5) [x1, y1, x2, y2, ry]")
 
 
 def boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap):
-    _check_boxes(boxes_a, boxes_b, ans_overlap)
+    _bev("boxes_overlap_bev_gpu", boxes_a)
+    _bev("boxes_overlap_bev_gpu", boxes_b)
+    require("boxes_overlap_bev_gpu", (ans_overlap, F32, boxes_a.size(0) * boxes_b.size(0)))
     with device_of(boxes_a):
         check(lib().ws3d_boxes_overlap_bev(boxes_a.size(0), ptr(boxes_a), boxes_b.size(0), ptr(boxes_b),
                                            ptr(ans_overlap), stream()), "boxes_overlap_bev_gpu")
@@ -143,7 +173,9 @@ def boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap):
 
 
 def boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou):
-    _check_boxes(boxes_a, boxes_b, ans_iou)
+    _bev("boxes_iou_bev_gpu", boxes_a)
+    _bev("boxes_iou_bev_gpu", boxes_b)
+    require("boxes_iou_bev_gpu", (ans_iou, F32, boxes_a.size(0) * boxes_b.size(0)))
     with device_of(boxes_a):
         check(lib().ws3d_boxes_iou_bev(boxes_a.size(0), ptr(boxes_a), boxes_b.size(0), ptr(boxes_b), ptr(ans_iou),
                                        stream()), "boxes_iou_bev_gpu")
@@ -151,9 +183,9 @@ def boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou):
 
 
 def _nms_host(fn, name, boxes, keep, thresh):
-    _check_boxes(boxes)
-    if keep.is_cuda or keep.dtype != torch.int64 or not keep.is_contiguous():
-        raise RuntimeError("keep must be a contiguous CPU int64 tensor")
+    _bev(name, boxes)
+    if keep.is_cuda or keep.dtype != torch.int64 or not keep.is_contiguous() or keep.numel() < boxes.size(0):
+        raise RuntimeError("keep must be a contiguous CPU int64 tensor with one slot per box")
     with device_of(boxes):
         n = fn(ptr(boxes), boxes.size(0), float(thresh), ptr(keep), stream())
     if n < 0:
@@ -172,7 +204,7 @@ def nms_normal_gpu(boxes, keep, nms_overlap_thresh):
 
 def nms_device(boxes, thresh, rotated=True):
     """Extension: all-device NMS.  Returns (keep int64 CUDA (N), num_keep int32 CUDA (1)); no sync."""
-    _check_boxes(boxes)
+    _bev("nms", boxes)
     n = boxes.size(0)
     keep = torch.empty(n, dtype=torch.int64, device=boxes.device)
     num = torch.zeros(1, dtype=torch.int32, device=boxes.device)
@@ -184,7 +216,7 @@ def nms_device(boxes, thresh, rotated=True):
 
 def boxes_iou3d_aligned(boxes_a, boxes_b, iou2d, iou3d):
     """Extension: diagonal of boxes_iou3d_gpu for aligned (n,7) box pairs; outputs (n) each."""
-    _check_boxes(boxes_a, boxes_b, iou2d, iou3d)
+    require("boxes_iou3d_aligned", (boxes_a, F32, None), (boxes_b, F32, None), (iou2d, F32, boxes_a.size(0)), (iou3d, F32, boxes_a.size(0)))
     if boxes_a.shape != boxes_b.shape or boxes_a.dim() != 2 or boxes_a.size(1) != 7:
         raise RuntimeError("boxes_iou3d_aligned: boxes must both be (n, 7)")
     with device_of(boxes_a):
@@ -195,7 +227,7 @@ def boxes_iou3d_aligned(boxes_a, boxes_b, iou2d, iou3d):
 def radius_nms_device(centers, radius):
     """Extension: greedy radius NMS over (n,2) BEV centres sorted by descending score.
     Returns (keep int64 CUDA (n), num_keep int32 CUDA (1)); no sync."""
-    _check_boxes(centers)
+    require("radius_nms", (centers, F32, None))
     if centers.dim() != 2 or centers.size(1) != 2:
         raise RuntimeError("radius_nms: centers must be (n, 2)")
     n = centers.size(0)
@@ -208,9 +240,10 @@ def radius_nms_device(centers, radius):
 
 def cylinder_query(pts, centers, radius, idx, cnt, any_flag=None):
     """Extension: pts (n,3), centers (m,2) -> idx (m,cap) int32, cnt (m) int32, any_flag (n) uint8."""
-    _check_boxes(pts, centers, idx, cnt, any_flag)
-    if pts.dim() != 2 or pts.size(1) != 3 or centers.dim() != 2 or centers.size(1) != 2:
-        raise RuntimeError("cylinder_query: pts must be (n, 3) and centers (m, 2)")
+    require("cylinder_query", (pts, F32, None), (centers, F32, None))
+    if pts.dim() != 2 or pts.size(1) != 3 or centers.dim() != 2 or centers.size(1) != 2 or idx.dim() != 2:
+        raise RuntimeError("cylinder_query: pts must be (n, 3), centers (m, 2) and idx (m, cap)")
+    require("cylinder_query", (idx, I32, centers.size(0) * idx.size(1)), (cnt, I32, centers.size(0)), (any_flag, U8, pts.size(0)))
     with device_of(pts):
         check(lib().ws3d_cylinder_query(pts.size(0), centers.size(0), idx.size(1), float(radius), ptr(pts), ptr(centers),
                                         ptr(idx), ptr(cnt), ptr(any_flag), stream()), "cylinder_query")
@@ -218,9 +251,11 @@ def cylinder_query(pts, centers, radius, idx, cnt, any_flag=None):
 
 def gaussian_rpn_labels(pts, gt_boxes3d, num_gt, gauss_height, gauss_status, gauss_cov, fg_radius, cls_label, reg_label):
     """Extension: pts (B,n,3), gt_boxes3d (B,G,7), num_gt (B) int32 or None -> cls_label (B,n), reg_label (B,n,3)."""
-    _check_boxes(pts, gt_boxes3d, num_gt, cls_label, reg_label)
+    require("gaussian_rpn_labels", (pts, F32, None), (gt_boxes3d, F32, None))
     if pts.dim() != 3 or pts.size(2) != 3 or gt_boxes3d.dim() != 3 or gt_boxes3d.size(2) != 7 or gt_boxes3d.size(0) != pts.size(0):
         raise RuntimeError("gaussian_rpn_labels: pts must be (B, n, 3) and gt_boxes3d (B, G, 7)")
+    require("gaussian_rpn_labels", (num_gt, I32, pts.size(0)), (cls_label, F32, pts.size(0) * pts.size(1)),
+            (reg_label, F32, pts.size(0) * pts.size(1) * 3))
     with device_of(pts):
         check(lib().ws3d_gaussian_rpn_labels(pts.size(0), pts.size(1), gt_boxes3d.size(1), ptr(pts), ptr(gt_boxes3d), ptr(num_gt),
                                              float(gauss_height), float(gauss_status), float(gauss_cov), float(fg_radius),
@@ -231,7 +266,14 @@ def gaussian_rpn_labels(pts, gt_boxes3d, num_gt, gauss_height, gauss_status, gau
 def roipool3d_forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
     """Reference `forward` (roipool3d.cpp:48): xyz (B,N,3), boxes3d (B,M,7), pts_feature (B,N,C),
     pooled_features (B,M,S,3+C) and pooled_empty_flag (B,M) int32 zero-filled by the caller."""
-    _check_boxes(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag)
+    require("roipool3d forward", (xyz, F32, None), (boxes3d, F32, None), (pts_feature, F32, None), (pooled_features, F32, None),
+            (pooled_empty_flag, I32, None))
+    if (xyz.dim() != 3 or xyz.size(2) != 3 or boxes3d.dim() != 3 or boxes3d.size(2) != 7 or pts_feature.dim() != 3
+            or pooled_features.dim() != 4 or boxes3d.size(0) != xyz.size(0) or pts_feature.shape[:2] != xyz.shape[:2]
+            or pooled_features.shape[:2] != boxes3d.shape[:2] or pooled_features.size(3) != 3 + pts_feature.size(2)
+            or pooled_empty_flag.numel() < boxes3d.size(0) * boxes3d.size(1)):
+        raise RuntimeError("roipool3d forward: expected xyz (B,N,3), boxes3d (B,M,7), pts_feature (B,N,C), "
+                           "pooled_features (B,M,S,3+C), pooled_empty_flag (B,M)")
     with device_of(xyz):
         check(lib().ws3d_roipool3d(xyz.size(0), xyz.size(1), boxes3d.size(1), pts_feature.size(2),
                                    pooled_features.size(2), ptr(xyz), ptr(boxes3d), ptr(pts_feature),
@@ -264,7 +306,8 @@ def sa_mlp_fused_supported(c_feat, nsample, c1, c2, c3) -> bool:
 
 def sa_mlp_fused(b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, w, shift, out, out_ctot, out_coff):
     """Extension: grouping + 3 x (conv1x1 + BN + ReLU) + max-pool of one set-abstraction scale."""
-    require_cuda(xyz, new_xyz, features, idx, out, *w, *shift)
+    require("sa_mlp_fused", (xyz, F32, b * n * 3), (new_xyz, F32, b * m * 3), (features, F32, b * c_feat * n), (idx, I32, b * m * nsample),
+            (out, F32, b * out_ctot * m), *[(t, F32, None) for t in list(w) + list(shift)])
     with device_of(xyz):
         check(lib().ws3d_sa_mlp_fused(b, n, m, nsample, c_feat, ptr(xyz), ptr(new_xyz), ptr(features), ptr(idx),
                                       widths[0], widths[1], widths[2], ptr(w[0]), ptr(shift[0]), ptr(w[1]), ptr(shift[1]),
@@ -273,7 +316,8 @@ def sa_mlp_fused(b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, 
 
 def group_affine(b, n, m, c, nsample, P, xyz, new_xyz, wx, shift, idx, flags, out):
     """Extension: out[b,c,j,s] = act(P[b,c,i] + wx[c] . (xyz[b,i] - new_xyz[b,j]) + shift[c]), i = idx[b,j,s]; flags: 1 ReLU, 2 TF32."""
-    require_cuda(P, xyz, new_xyz, wx, shift, idx, out)
+    require("group_affine", (P, F32, b * c * n), (xyz, F32, b * n * 3), (new_xyz, F32, b * m * 3), (wx, F32, c * 3), (shift, F32, c),
+            (idx, I32, b * m * nsample), (out, F32, b * c * m * nsample))
     with device_of(P):
         check(lib().ws3d_group_affine(b, n, m, c, nsample, ptr(P), ptr(xyz), ptr(new_xyz), ptr(wx), ptr(shift), ptr(idx),
                                       int(flags), ptr(out), stream()), "group_affine")
@@ -281,7 +325,8 @@ def group_affine(b, n, m, c, nsample, P, xyz, new_xyz, wx, shift, idx, flags, ou
 
 def three_interpolate_affine(b, c, m, n, points, idx, weight, scale1, row1, shift, flags, out):
     """Extension: out = act(three_interpolate(points) + scale1[c] * row1[b, i] + shift[c]); flags: 1 ReLU, 2 TF32 rounding."""
-    require_cuda(points, idx, weight, scale1, row1, shift, out)
+    require("three_interpolate_affine", (points, F32, b * c * m), (idx, I32, b * n * 3), (weight, F32, b * n * 3), (scale1, F32, c),
+            (row1, F32, b * n), (shift, F32, c), (out, F32, b * c * n))
     with device_of(points):
         check(lib().ws3d_three_interpolate_affine(b, c, m, n, ptr(points), ptr(idx), ptr(weight), ptr(scale1), ptr(row1),
                                                   ptr(shift), int(flags), ptr(out), stream()), "three_interpolate_affine")
@@ -290,6 +335,21 @@ def three_interpolate_affine(b, c, m, n, points, idx, weight, scale1, row1, shif
 def set_workspace_arena(arena: int) -> int:
     """Scratch arena (0..7) for this thread's subsequent launches; returns the previous one (ws3d_ops.h)."""
     return int(lib().ws3d_set_workspace_arena(int(arena)))
+
+
+def num_arenas() -> int:
+    return int(lib().ws3d_num_arenas())
+
+
+def scratch_bytes(retired_only: bool = False) -> int:
+    """Bytes of cached scratch on the current device (ws3d_ops.h)."""
+    return int(lib().ws3d_scratch_bytes(int(bool(retired_only))))
+
+
+def release_scratch(everything: bool = False) -> None:
+    """Frees the retired scratch buffers (or every cached buffer) of the current device after a device synchronise.
+    Graphs captured while a freed buffer was live must not be replayed again (ws3d_ops.h)."""
+    check(lib().ws3d_release_scratch(int(bool(everything))), "release_scratch")
 
 
 def set_sm_budget(sms: int) -> int:

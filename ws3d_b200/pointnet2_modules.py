@@ -46,8 +46,8 @@ class _PointnetSAModuleBase(nn.Module):
             cache[k] = fused_mlp.FoldedMLP(self.mlps[k])
         return cache[k]
 
-    def _scale_inference(self, k, grouper, xyz, new_xyz, features, idx):
-        """One scale on the per-layer tensor-core path (inference): (B, c_last, npoint)."""
+    def _scale_inference(self, k, grouper, xyz, new_xyz, features, idx, out=None, out_coff=0):
+        """One scale on the per-layer tensor-core path (inference): (B, c_last, npoint), or its slot of `out`."""
         K = grouper.nsample
         if (features is not None and getattr(grouper, "use_xyz", False) and len(self.mlps[k]) >= 2 and features.is_contiguous()
                 and os.environ.get("WS3D_SA_PREMUL", "1") != "0"
@@ -58,10 +58,10 @@ class _PointnetSAModuleBase(nn.Module):
                 cache[k] = (fused_mlp.FoldedSAFirstLayer(self.mlps[k][0], features.shape[1]),
                             fused_mlp.FoldedMLP(torch.nn.Sequential(*list(self.mlps[k])[1:])))
             first, rest = cache[k]
-            return rest(first(xyz, new_xyz, features, idx, round_out=True), pool=K)
+            return rest(first(xyz, new_xyz, features, idx, round_out=True), pool=K, out=out, out_coff=out_coff)
         grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
         B, C, M, _ = grouped.shape
-        return self._folded(k)(grouped.view(B, C, M * K), pool=K)
+        return self._folded(k)(grouped.view(B, C, M * K), pool=K, out=out, out_coff=out_coff)
 
     def _scale_side_streams(self, xyz):
         """One extra CUDA stream per scale beyond the first (cached per module and device)."""
@@ -139,31 +139,35 @@ class _PointnetSAModuleBase(nn.Module):
         # inference, several scales: the scales are independent chains of small launches (group + three layers, each
         # well under one wave at the deeper levels), so they run side by side on per-scale streams
         side = None
-        if (fused and len(self.groupers) > 1 and xyz.is_cuda and self.npoint is not None
-                and all(fused_mlp.supported(new_xyz.shape[1] * g.nsample, g.nsample) for g in self.groupers)
-                and os.environ.get("WS3D_SCALE_STREAMS", "1") != "0"):
+        all_layers = (fused and xyz.is_cuda and self.npoint is not None
+                      and all(fused_mlp.supported(new_xyz.shape[1] * g.nsample, g.nsample) for g in self.groupers))
+        if all_layers:
+            # every scale's last layer writes its slot of the concatenated output (no torch.cat pass)
+            widths = [mlp[-1].conv.out_channels for mlp in self.mlps]
+            cat_out = torch.empty((xyz.shape[0], sum(widths), new_xyz.shape[1]), dtype=torch.float32, device=xyz.device)
+            offs = [sum(widths[:k]) for k in range(len(widths))]
+        if all_layers and len(self.groupers) > 1 and os.environ.get("WS3D_SCALE_STREAMS", "1") != "0":
             side = self._scale_side_streams(xyz)
             main = torch.cuda.current_stream(xyz.device)
             fork = torch.cuda.Event()
             fork.record(main)
+        joins = []
         for k, (grouper, mlp, idx) in enumerate(zip(self.groupers, self.mlps, indices)):
             if side is not None and k > 0:
                 st = side[k - 1]
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
-                    res = self._scale_inference(k, grouper, xyz, new_xyz, features, idx)
+                    self._scale_inference(k, grouper, xyz, new_xyz, features, idx, out=cat_out, out_coff=offs[k])
                     done = torch.cuda.Event()
                     done.record(st)
-                for t in (xyz, new_xyz, features, idx):
+                for t in (xyz, new_xyz, features, idx, cat_out):
                     if t is not None:
                         t.record_stream(st)
-                res.record_stream(main)
-                main.wait_event(done)   # (the join is only needed before the cat; waiting here keeps the code simple:
-                pooled.append(res)      #  scale 0 was launched first and is already running on `main`)
+                joins.append(done)
                 continue
-            if fused and self.npoint is not None and fused_mlp.supported(new_xyz.shape[1] * grouper.nsample, grouper.nsample):
+            if all_layers:
                 # inference: every layer is one tensor-core launch; the last one also max-pools over nsample
-                pooled.append(self._scale_inference(k, grouper, xyz, new_xyz, features, idx))
+                self._scale_inference(k, grouper, xyz, new_xyz, features, idx, out=cat_out, out_coff=offs[k])
                 continue
             grouped = grouper(xyz, new_xyz, features, idx=idx)  # (B, 3+C, npoint, nsample)
             B, C, M, K = grouped.shape
@@ -182,6 +186,10 @@ class _PointnetSAModuleBase(nn.Module):
             else:
                 raise NotImplementedError
             pooled.append(grouped.squeeze(-1).contiguous())
+        if all_layers:
+            for ev in joins:
+                main.wait_event(ev)
+            return new_xyz, cat_out
         return new_xyz, torch.cat(pooled, dim=1)
 
 
@@ -225,6 +233,8 @@ class PointnetFPModule(nn.Module):
     def interpolation_weights(unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """three_nn + inverse-distance weights (reference :139-144).  Depends on coordinates only, so a caller may
         compute it ahead of time (models.Pointnet2MSG does, on a side stream) and pass it as `nn=`."""
+        if unknown.is_cuda and unknown.is_contiguous() and known.is_contiguous():
+            return pointnet2_utils.three_nn_weights(unknown, known)   # one launch instead of six
         dist, idx = pointnet2_utils.three_nn(unknown, known)
         dist_recip = 1.0 / (dist + 1e-8)
         norm = torch.sum(dist_recip, dim=2, keepdim=True)

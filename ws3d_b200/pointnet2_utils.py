@@ -110,6 +110,20 @@ class _ThreeNN(Function):
 three_nn = _ThreeNN.apply
 
 
+def three_nn_weights(unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """three_nn and the interpolation weights of PointnetFPModule.forward (pointnet2_modules.py:139-144:
+    `1 / (dist + 1e-8)`, normalised over the three neighbours) from one launch.  Returns (idx (B,n,3) int32,
+    weight (B,n,3)); no gradient (the reference's three_nn has none and the weights are built from its output)."""
+    _f32c(unknown)
+    _f32c(known)
+    B, N, _ = unknown.shape
+    idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
+    weight = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
+    with torch.no_grad():
+        native.three_nn_weights(B, N, known.shape[1], unknown, known, None, idx, weight)
+    return idx, weight
+
+
 class _ThreeInterpolate(Function):
     """pointnet2_utils.py:108-153.  features (B,C,M), idx/weight (B,n,3) -> (B,C,n)."""
 
@@ -174,7 +188,7 @@ class _BallQuery(Function):
         _f32c(new_xyz)
         B, N, _ = xyz.shape
         npoint = new_xyz.shape[1]
-        idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)   # every row is written (ws3d_ops.h)
         native.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
         ctx.mark_non_differentiable(idx)
         return idx
@@ -194,8 +208,8 @@ def ball_query_pair(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
     _f32c(new_xyz)
     B, N, _ = xyz.shape
     npoint = new_xyz.shape[1]
-    idx0 = torch.zeros((B, npoint, nsamples[0]), dtype=torch.int32, device=xyz.device)
-    idx1 = torch.zeros((B, npoint, nsamples[1]), dtype=torch.int32, device=xyz.device)
+    idx0 = torch.empty((B, npoint, nsamples[0]), dtype=torch.int32, device=xyz.device)   # every row is written (ws3d_ops.h)
+    idx1 = torch.empty((B, npoint, nsamples[1]), dtype=torch.int32, device=xyz.device)
     with torch.no_grad():
         native.ball_query2(B, N, npoint, radii[0], nsamples[0], radii[1], nsamples[1], new_xyz, xyz, idx0, idx1)
     return idx0, idx1
