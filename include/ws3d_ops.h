@@ -298,6 +298,35 @@ int ws3d_gaussian_rpn_labels(int b, int n, int g_max, const float *pts, const fl
                              float gauss_cov, float fg_radius, float *cls_label, float *reg_label,
                              ws3d_stream_t stream);
 
+/* ---- loss-side box math and loader subsampling ---------------- */
+
+/* Replaces boxes3d_to_corners3d_torch (lib/utils/kitti_utils.py:104-131, ~15 eager torch kernels per call).
+ * boxes3d (N,7) [x, y(bottom), z, h, w, l, ry] -> corners (N,8,3); flip adds pi to ry (:113-114). */
+int ws3d_boxes3d_to_corners3d(int n, const float *boxes3d, int flip, float *corners, ws3d_stream_t stream);
+
+/* The corner distance of the Stage-2 corner loss (lib/net/train_functions.py:266-271): for aligned (N,7) box pairs,
+ * dist (N,8) = min(|P - G|, |P - G_flipped|) over the eight corners P of the predicted box, G of the ground truth and
+ * G_flipped of the ground truth turned by pi -- three corner computations, two norms and a min in one launch. */
+int ws3d_corner_distance(int n, const float *pred_boxes3d, const float *gt_boxes3d, float *dist, ws3d_stream_t stream);
+/* Its gradient with respect to the predicted boxes: grad_pred (N,7) from grad_dist (N,8) (the ground truth carries
+ * no gradient in the reference either).  Subgradients as torch's autograd takes them. */
+int ws3d_corner_distance_grad(int n, const float *pred_boxes3d, const float *gt_boxes3d, const float *grad_dist,
+                              float *grad_pred, ws3d_stream_t stream);
+
+/* The loader's subsampling to a fixed point count (lib/datasets/kitti_rcnn_dataset.py:424-452) on the device.
+ * pts (n,c) rows [x,y,z,features...], depth (n) (used when n > npoints).  The random draws are the HOST's, exactly
+ * those numpy makes there, so the result equals the reference's sample:
+ *   n > npoints : perm = np.random.permutation(n_near) (what np.random.choice(near_idxs, k, replace=False) draws; its
+ *                 first k = npoints - n_far entries are used), n_near = #(depth < near_depth);
+ *   n <= npoints: perm = np.random.permutation(n * ceil(npoints / n)) (first npoints entries are used);
+ *   order       = np.random.shuffle applied to arange(npoints).
+ * out (npoints,c) = pts[choice[order]] with `sub_last` subtracted from the last channel when c > 3 (the intensity shift
+ * of :444), choice (npoints) the selected source indices (may be NULL), status (1) int: 0, or 1 when n_near does not
+ * match the depths (nothing is written then). */
+int ws3d_subsample_points(int n, int c, int npoints, int n_near, float near_depth, float sub_last, const float *pts,
+                          const float *depth, const int *perm, const int *order, float *out, int *choice,
+                          int *status, ws3d_stream_t stream);
+
 /* ---- roipool3d_cuda -------------------------------------------------------- */
 
 /* Replaces roipool3dLauncher (lib/utils/roipool3d/src/roipool3d.cpp:12-13,

@@ -253,3 +253,46 @@ def gaussian_rpn_labels(pts_rect, gt_boxes3d, gauss_height=0.707, gauss_status=0
     lib().oracle_gaussian_rpn_labels(p.shape[0], b.shape[0], _p(p), _p(b), ctypes.c_float(gauss_height), ctypes.c_float(gauss_status),
                                      ctypes.c_double(gauss_cov), ctypes.c_float(fg_radius), _p(cls), _p(reg))
     return cls, reg
+
+
+# ---- SURVEY.md section 8 rows f2 (corner-loss box math) / f4 (loader subsampling) ----------------
+def boxes3d_to_corners3d(boxes3d, flip=False):
+    """kitti_utils.py:104-131: (n,7) -> (n,8,3)."""
+    b = _f(boxes3d).reshape(-1, 7)
+    out = np.zeros((b.shape[0], 8, 3), dtype=np.float32)
+    lib().oracle_boxes3d_to_corners3d(b.shape[0], _p(b), int(bool(flip)), _p(out))
+    return out
+
+
+def corner_distance(pred_boxes3d, gt_boxes3d):
+    """train_functions.py:266-271: aligned (n,7) pairs -> (n,8) min(|P - G|, |P - G_flipped|)."""
+    p, g = _f(pred_boxes3d).reshape(-1, 7), _f(gt_boxes3d).reshape(-1, 7)
+    out = np.zeros((p.shape[0], 8), dtype=np.float32)
+    lib().oracle_corner_distance(p.shape[0], _p(p), _p(g), _p(out))
+    return out
+
+
+def subsample_points(pts, depth, npoints, rng):
+    """kitti_rcnn_dataset.py:424-444, restated line by line with `rng` (a numpy RandomState) in place of the global
+    np.random: pts (n, 3 + C) rows [xyz, intensity...] -> (pts_input (npoints, 3 + C) with the last channel shifted by
+    -0.5 when C > 0, choice (npoints))."""
+    pts = _f(pts)
+    n = pts.shape[0]
+    if npoints < n:
+        pts_near_flag = np.asarray(depth, dtype=np.float32) < 40.0
+        far_idxs_choice = np.where(pts_near_flag == 0)[0]
+        near_idxs = np.where(pts_near_flag == 1)[0]
+        near_idxs_choice = rng.choice(near_idxs, npoints - len(far_idxs_choice), replace=False)
+        choice = np.concatenate((near_idxs_choice, far_idxs_choice), axis=0) if len(far_idxs_choice) > 0 else near_idxs_choice
+        rng.shuffle(choice)
+    else:
+        choice = np.arange(0, n, dtype=np.int32)
+        extra_choice = np.arange(0, n, dtype=np.int32)
+        while npoints > len(choice):
+            choice = np.concatenate((choice, extra_choice), axis=0)
+        choice = rng.choice(choice, npoints, replace=False)
+        rng.shuffle(choice)
+    out = pts[choice, :].copy()
+    if pts.shape[1] > 3:
+        out[:, -1] = out[:, -1] - np.float32(0.5)
+    return out, choice.astype(np.int32)

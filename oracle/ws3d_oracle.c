@@ -715,3 +715,46 @@ ORACLE_API void oracle_gaussian_rpn_labels(int n, int g, const float *pts, const
     }
   }
 }
+
+/* Row f2, loss-side box math.  lib/utils/kitti_utils.py:104-131 boxes3d_to_corners3d_torch for one box:
+ * x_corners = +-l/2, y_corners = 0 / -h, z_corners = +-w/2 (:117-119); R = [[cos,0,sin],[0,1,0],[-sin,0,cos]] (:122-126);
+ * corners_rotated = R x corners + centre (:128-129).  The float32 batched matmul accumulates k = 0,1,2 in order with
+ * FMAs from zero (its middle term multiplies an exact 0 or 1), then the centre is added with one rounding.  `flip`
+ * adds (float)pi to ry first (:113-114).  Host libm cosf / sinf against libdevice: last-ulp differences possible. */
+static void box_corners(const float *b, int flip, float *out /* 8 x 3 */) {
+  const float ry = flip ? b[6] + 3.14159265358979323846f : b[6];
+  const float cosa = cosf(ry), sina = sinf(ry);
+  const float hl = b[5] / 2.0f, hw = b[4] / 2.0f;
+  const float xs[8] = {hl, hl, -hl, -hl, hl, hl, -hl, -hl};
+  const float zs[8] = {hw, -hw, -hw, hw, hw, -hw, -hw, hw};
+  for (int k = 0; k < 8; ++k) {
+    const float yc = k < 4 ? 0.0f : -b[3];
+    out[3 * k] = fmaf(sina, zs[k], cosa * xs[k]) + b[0];
+    out[3 * k + 1] = yc + b[1];
+    out[3 * k + 2] = fmaf(cosa, zs[k], (-sina) * xs[k]) + b[2];
+  }
+}
+
+ORACLE_API void oracle_boxes3d_to_corners3d(int n, const float *boxes, int flip, float *corners) {
+  for (int i = 0; i < n; ++i) box_corners(boxes + (size_t)i * 7, flip, corners + (size_t)i * 24);
+}
+
+/* lib/net/train_functions.py:266-271: corner_dist = min(norm(pred_corner - gt_corner), norm(pred_corner - gt_flip_corner))
+ * per corner; torch.norm(dim=-1) of a 3-vector = sqrt((dx*dx + dy*dy) + dz*dz), one rounding per step. */
+ORACLE_API void oracle_corner_distance(int n, const float *pred, const float *gt, float *dist) {
+  for (int i = 0; i < n; ++i) {
+    float p[24], g[24], gf[24];
+    box_corners(pred + (size_t)i * 7, 0, p);
+    box_corners(gt + (size_t)i * 7, 0, g);
+    box_corners(gt + (size_t)i * 7, 1, gf);
+    for (int k = 0; k < 8; ++k) {
+      float d[2];
+      const float *q[2] = {g, gf};
+      for (int s = 0; s < 2; ++s) {
+        const float dx = p[3 * k] - q[s][3 * k], dy = p[3 * k + 1] - q[s][3 * k + 1], dz = p[3 * k + 2] - q[s][3 * k + 2];
+        d[s] = sqrtf((dx * dx + dy * dy) + dz * dz);
+      }
+      dist[(size_t)i * 8 + k] = d[0] < d[1] ? d[0] : d[1];
+    }
+  }
+}

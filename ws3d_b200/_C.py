@@ -58,6 +58,10 @@ _SIGNATURES = {
     "ws3d_radius_nms": [_vp, _i, _f, _vp, _vp, _vp, _vp],
     "ws3d_cylinder_query": [_i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_gaussian_rpn_labels": [_i, _i, _i, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp],
+    "ws3d_boxes3d_to_corners3d": [_i, _vp, _i, _vp, _vp],
+    "ws3d_corner_distance": [_i, _vp, _vp, _vp, _vp],
+    "ws3d_corner_distance_grad": [_i, _vp, _vp, _vp, _vp, _vp],
+    "ws3d_subsample_points": [_i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_roipool3d": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_pts_in_boxes3d_cpu": [_vp, _vp, _vp, _i, _i],
     "ws3d_roipool3d_cpu": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i],

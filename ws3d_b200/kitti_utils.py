@@ -1,4 +1,4 @@
-"""The two box helpers of lib/utils/kitti_utils.py that the hot-path wrappers depend on."""
+"""The box helpers of lib/utils/kitti_utils.py that the hot-path wrappers and the loss-side box math depend on."""
 import numpy as np
 import torch
 
@@ -16,3 +16,14 @@ def enlarge_box3d(boxes3d, extra_width):
     large[:, 3:6] += extra_width * 2
     large[:, 1] += extra_width
     return large
+
+
+def boxes3d_to_corners3d_torch(boxes3d: torch.Tensor, flip: bool = False) -> torch.Tensor:
+    """(N,7) [x,y,z,h,w,l,ry] -> (N,8,3) rotated corners (kitti_utils.py:104-131); one launch instead of ~15 eager
+    kernels.  Forward only, like every use of it outside the corner loss (train_functions.corner_distance has the
+    differentiable form)."""
+    from . import native
+    boxes = boxes3d.detach().contiguous().float()
+    corners = torch.empty((boxes.shape[0], 8, 3), dtype=torch.float32, device=boxes.device)
+    native.boxes3d_to_corners3d(boxes, flip, corners)
+    return corners

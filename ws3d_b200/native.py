@@ -262,6 +262,48 @@ def gaussian_rpn_labels(pts, gt_boxes3d, num_gt, gauss_height, gauss_status, gau
                                              ptr(cls_label), ptr(reg_label), stream()), "gaussian_rpn_labels")
 
 
+def boxes3d_to_corners3d(boxes3d, flip, corners):
+    """Extension: boxes3d (N,7) -> corners (N,8,3), kitti_utils.py:104-131."""
+    require("boxes3d_to_corners3d", (boxes3d, F32, None), (corners, F32, boxes3d.size(0) * 24))
+    if boxes3d.dim() != 2 or boxes3d.size(1) != 7:
+        raise RuntimeError("boxes3d_to_corners3d: boxes3d must be (N, 7)")
+    with device_of(boxes3d):
+        check(lib().ws3d_boxes3d_to_corners3d(boxes3d.size(0), ptr(boxes3d), int(bool(flip)), ptr(corners), stream()),
+              "boxes3d_to_corners3d")
+
+
+def corner_distance(pred, gt, dist):
+    """Extension: aligned (N,7) box pairs -> dist (N,8), train_functions.py:266-271."""
+    require("corner_distance", (pred, F32, None), (gt, F32, None), (dist, F32, pred.size(0) * 8))
+    if pred.dim() != 2 or pred.size(1) != 7 or pred.shape != gt.shape:
+        raise RuntimeError("corner_distance: boxes must both be (N, 7)")
+    with device_of(pred):
+        check(lib().ws3d_corner_distance(pred.size(0), ptr(pred), ptr(gt), ptr(dist), stream()), "corner_distance")
+
+
+def corner_distance_grad(pred, gt, grad_dist, grad_pred):
+    require("corner_distance_grad", (pred, F32, None), (gt, F32, None), (grad_dist, F32, pred.size(0) * 8),
+            (grad_pred, F32, pred.size(0) * 7))
+    if pred.dim() != 2 or pred.size(1) != 7 or pred.shape != gt.shape:
+        raise RuntimeError("corner_distance_grad: boxes must both be (N, 7)")
+    with device_of(pred):
+        check(lib().ws3d_corner_distance_grad(pred.size(0), ptr(pred), ptr(gt), ptr(grad_dist), ptr(grad_pred), stream()),
+              "corner_distance_grad")
+
+
+def subsample_points(pts, depth, npoints, n_near, near_depth, sub_last, perm, order, out, choice, status):
+    """Extension: kitti_rcnn_dataset.py:424-452 on the device with the host's random draws (ws3d_ops.h)."""
+    n, c = pts.size(0), pts.size(1)
+    need = n_near if n > npoints else npoints
+    require("subsample_points", (pts, F32, None), (depth, F32, n), (perm, I32, min(need, npoints) if n <= npoints else npoints - (n - n_near)),
+            (order, I32, npoints), (out, F32, npoints * c), (choice, I32, npoints), (status, I32, 1))
+    if pts.dim() != 2 or c < 3:
+        raise RuntimeError("subsample_points: pts must be (n, 3 + C)")
+    with device_of(pts):
+        check(lib().ws3d_subsample_points(n, c, int(npoints), int(n_near), float(near_depth), float(sub_last), ptr(pts), ptr(depth),
+                                          ptr(perm), ptr(order), ptr(out), ptr(choice), ptr(status), stream()), "subsample_points")
+
+
 # ---- roipool3d_cuda ---------------------------------------------------------------------------
 def roipool3d_forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag):
     """Reference `forward` (roipool3d.cpp:48): xyz (B,N,3), boxes3d (B,M,7), pts_feature (B,N,C),

@@ -10,9 +10,12 @@ import numpy as np
 CAR_SIZE = (1.52563191462, 1.62856739989, 3.88311640418)  # h, w, l (weaklyRPN.yaml:19)
 
 
-def make_scene(scene_id: int = 0, num_points: int = 16384, seed: int = 1234, uniform: bool = False) -> np.ndarray:
-    """-> (num_points, 4) float32 [x, y, z, intensity]."""
+def make_scene(scene_id: int = 0, num_points: int = 16384, seed: int = 1234, uniform: bool = False,
+               return_boxes: bool = False):
+    """-> (num_points, 4) float32 [x, y, z, intensity]; with `return_boxes` also the (n_cars, 7) ground-truth boxes
+    [x, y(bottom), z, h, w, l, ry] of the car clusters (empty for the uniform variant)."""
     rng = np.random.default_rng(seed + scene_id)
+    boxes = np.zeros((0, 7), np.float32)
     if uniform:
         xyz = np.stack([rng.uniform(-40, 40, num_points), rng.uniform(-1, 3, num_points),
                         rng.uniform(0, 70.4, num_points)], axis=1)
@@ -32,9 +35,25 @@ def make_scene(scene_id: int = 0, num_points: int = 16384, seed: int = 1234, uni
         c, s = np.cos(ry[owner]), np.sin(ry[owner])
         obj = np.stack([local[:, 0] * c + local[:, 2] * s, local[:, 1], -local[:, 0] * s + local[:, 2] * c], axis=1)
         xyz = np.concatenate([ground, obj + centres[owner]], axis=0)
+        # the clusters fill y in [centre - 1.0, centre + 0.7] (y points down): box bottom at centre + 0.7
+        boxes = np.concatenate([centres[:, 0:1], centres[:, 1:2] + 0.7, centres[:, 2:3],
+                                np.tile(np.asarray(CAR_SIZE)[None, :], (n_cars, 1)), ry[:, None]], axis=1).astype(np.float32)
     intensity = rng.uniform(0, 1, num_points) - 0.5
     pts = np.concatenate([xyz, intensity[:, None]], axis=1).astype(np.float32)
-    return pts[rng.permutation(num_points)]
+    pts = pts[rng.permutation(num_points)]
+    return (pts, boxes) if return_boxes else pts
+
+
+def make_gt_boxes(batch: int, num_points: int = 16384, first_scene: int = 0, seed: int = 1234, pad_to: int = 48):
+    """Ground-truth boxes of scenes [first_scene, first_scene + batch): (batch, pad_to, 7) float32 zero padded and the
+    per-scene counts (batch,) int32 -- the `gt_boxes3d` a loader would hand to the label generator."""
+    out = np.zeros((batch, pad_to, 7), np.float32)
+    cnt = np.zeros(batch, np.int32)
+    for i in range(batch):
+        _, bx = make_scene(first_scene + i, num_points, seed, return_boxes=True)   # (the RNG stream depends on num_points)
+        cnt[i] = min(len(bx), pad_to)
+        out[i, :cnt[i]] = bx[:cnt[i]]
+    return out, cnt
 
 
 def make_batch(batch: int, num_points: int = 16384, seed: int = 1234, first_scene: int = 0, uniform: bool = False):
