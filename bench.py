@@ -8,10 +8,18 @@ channels) per GPU.  Metric: set-abstraction path throughput in Mpoints/s = cloud
   python bench.py [--gpus N --steps K --warmup W]          this repo's CUDA path (one rank per GPU)
   python bench.py --impl reference ...                     the CPU path (oracle port, all host cores)
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same forward called
-with HOST (pinned) input, H2D copy and a D2H read of the per-cloud result checksum inside the timed
-region.  `roofline`: the dominant kernel of the step, timed live with CUDA events on the launching
-stream.  `cpu_baseline`: the oracle port on the host cores for a bounded sample of the workload.
+One JSON line on stdout (rank 0).
+  value        K batches through the streamed pipeline, inputs resident in HBM, between two device synchronisations:
+               pipeline fill and drain are INSIDE the timed region (exactly K coordinate phases and K feature phases).
+  e2e          the same K batches from pinned HOST memory: H2D copies and the D2H read of every step's per-cloud result
+               checksum inside the timed region (the API returns device tensors; the checksum is what is read back).
+  verify       every step's checksum against the plain (unpipelined) forward of the same batch, the last step's full
+               output tensor against it, and the FP32 path against the CPU oracle composition on one cloud.
+  roofline     the launch that dominates the feature phase (the phase that bounds the streamed step), timed live with
+               CUDA events; `fps` has the sampler's us/iteration; `sm_time_budget` the per-kernel SM-time shares from the
+               committed ncu capture.
+  oracle_gpu   the same modules on the REFERENCE's kernels recompiled for sm_100a (oracle/_ref), same process.
+  configs      BASELINE.json configs 1, 3, 4, 5;  cpu_baseline: the oracle port at 1 thread and on all host cores.
 """
 import argparse
 import json
@@ -33,17 +41,25 @@ NPTS = 16384
 BATCH = 16
 WORKLOAD = ("PointNet++-MSG backbone forward (4 SA + 4 FP, weaklyRPN.yaml shapes), batch 16 synthetic KITTI clouds 16384x4 per GPU "
             "(BASELINE configs[1])")
+DTYPE = "f32 ops / tf32 mlp"   # irregular ops are exact FP32 / int32; the shared MLPs run TF32 inputs with FP32 accumulation
 
 
-def measured_traffic(kernel, dims):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r1_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+def profile_json(name):
+    path = os.path.join(ROOT, "profiles", name)
     if not os.path.exists(path):
         return None
     with open(path) as f:
-        table = json.load(f)
+        return json.load(f)
+
+
+def measured_traffic(kernel, dims):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` captures."""
     key = kernel + ":" + ",".join(f"{k}={dims[k]}" for k in sorted(dims))
-    return table.get(key)
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        table = profile_json(name)
+        if table and key in table:
+            return table[key]
+    return None
 
 
 def measured_peaks():
@@ -51,8 +67,8 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1648.6)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -100,7 +116,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm (oracle port).  This is the only place besides tests/ and smoke() that touches oracle/.
+# CPU arm (oracle port).  Besides tests/ and smoke() this file is the only place that touches oracle/, and only in the
+# baseline / checker legs: cpu_baseline, --impl reference, oracle_gpu (the reference's kernels) and `verify`.
 def cpu_backbone_throughput(clouds, repeats=1, threads=None):
     import torch
 
@@ -122,6 +139,24 @@ def cpu_backbone_throughput(clouds, repeats=1, threads=None):
     return clouds * NPTS / best / 1e6, best, oracle.num_threads()
 
 
+def cpu_single_sa_layer(threads, repeats=2):
+    """Config 1 on the host: oracle FPS 16384 -> 4096 + ball query r = 0.8, K = 32 on one cloud."""
+    import oracle
+    from ws3d_b200 import synth
+    oracle.set_num_threads(threads)
+    pts = synth.make_batch(1, NPTS)
+    xyz = np.ascontiguousarray(pts[..., :3])
+    best, idx, bq = None, None, None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        idx = oracle.furthest_point_sample(xyz, 4096)
+        new_xyz = np.take_along_axis(xyz, idx[..., None].astype(np.int64), 1)
+        bq = oracle.ball_query(0.8, 32, xyz, new_xyz)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, idx, bq
+
+
 def run_reference_cpu(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,17 +169,19 @@ def run_reference_cpu(args):
     for _ in range(args.steps):
         _, dt, thr = cpu_backbone_throughput(clouds, threads=cores)
         times.append(dt)
+    v1, dt1, _ = cpu_backbone_throughput(1, threads=1)
     ms = float(np.mean(times)) * 1e3
     value = clouds * NPTS / (ms / 1e3) / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clouds_per_step": clouds,
+        "config": {"workload": WORKLOAD, "clouds_per_gpu": clouds, "points_per_cloud": NPTS,
                    "note": "CPU port of the reference algorithms (the reference has no CPU implementation of these ops); each "
                            "step is one pass over the GPU arm's 16-cloud batch (about 2.5 s on 16 cores)"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{clouds} clouds x {NPTS} points per step, oracle ops (OpenMP) + PyTorch CPU MLPs"},
+                         "sample": f"{clouds} clouds x {NPTS} points per step, oracle ops (OpenMP) + PyTorch CPU MLPs",
+                         "one_thread": {"value": round(v1, 4), "unit": UNIT, "sample": f"1 cloud, {dt1:.2f} s"}},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -152,6 +189,10 @@ def run_reference_cpu(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _sa_flops(b, m, k, c, c1, c2, c3, **kw):
+    return 2 * b * m * k * ((3 + c) * c1 + c1 * c2 + c2 * c3)
+
+
 ALG_BYTES = {
     # SURVEY.md section 8d, per launch; b = clouds in the launch
     "fps": lambda b, n, m, **k: b * (12 * n + 4 * m),
@@ -159,16 +200,25 @@ ALG_BYTES = {
     "group_concat": lambda b, n, m, c, k, **kw: b * (4 * m * k + 12 * n + 4 * c * n + 12 * m + 4 * (3 + c) * m * k),
     "three_nn": lambda b, n, m, **k: b * (12 * n + 12 * m + 24 * n),
     "three_interpolate": lambda b, c, m, n, **k: b * (4 * c * m + 24 * n + 4 * c * n),
+    "three_interpolate_affine": lambda b, c, m, n, **k: b * (4 * c * m + 24 * n + 4 * n + 4 * c * n),
+    # first layer's output gathered from the pre-multiplied source points: read P, coordinates, idx; write (c, m, k)
+    "group_affine": lambda b, n, m, c, k, **kw: b * (4 * c * n + 12 * n + 12 * m + 4 * m * k + 4 * c * m * k),
+    "split_pointcloud": lambda b, n, c, **k: b * 8 * (3 + c) * n,
     # one fused set-abstraction scale: indices + coordinates + features in, pooled features out (weights are L2-resident)
     "sa_mlp_fused": lambda b, n, m, k, c, c3, **kw: b * (4 * m * k + 12 * n + 12 * m + 4 * c * n + 4 * c3 * m),
     # one shared-MLP layer: read (c1+c2) x cols, write c_out x cols (or cols/pool), read the folded weights once
     "mlp_layer": lambda b, c_out, c_in, cols, pool, **k: 4 * (b * c_in * cols + b * c_out * (cols // pool if pool else cols)
                                                               + c_out * c_in),
 }
+ALG_FLOPS = {
+    "sa_mlp_fused": _sa_flops,
+    "mlp_layer": lambda b, c_out, c_in, cols, **k: 2 * b * c_out * c_in * cols,
+}
+COORDINATE_KERNELS = ("fps", "ball_query2", "three_nn", "split_pointcloud")   # run ahead on the coordinate streams
 
 
 class OpProfiler:
-    """CUDA-event timing of this repo's kernels inside the timed region (same stream)."""
+    """CUDA-event timing of this repo's launches (same stream), one event pair per launch."""
 
     def __init__(self, torch):
         self.torch = torch
@@ -179,10 +229,10 @@ class OpProfiler:
         prof = self
 
         def timed(name, fn, dims_fn):
-            def inner(*a):
+            def inner(*a, **kw):
                 s, e = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
                 s.record()
-                r = fn(*a)
+                r = fn(*a, **kw)
                 e.record()
                 prof.records.append((name, dims_fn(*a), s, e))
                 return r
@@ -193,11 +243,14 @@ class OpProfiler:
             "furthest_point_sampling_gather": ("fps", lambda b, n, m, *r: dict(b=b, n=n, m=m)),
             "ball_query2": ("ball_query2", lambda b, n, m, r0, k0, r1, k1, *r: dict(b=b, n=n, m=m, k0=k0, k1=k1)),
             "group_concat": ("group_concat", lambda b, n, m, c, k, *r: dict(b=b, n=n, m=m, c=c, k=k)),
-            "three_nn_wrapper": ("three_nn", lambda b, n, m, *r: dict(b=b, n=n, m=m)),
+            "group_affine": ("group_affine", lambda b, n, m, c, k, *r: dict(b=b, n=n, m=m, c=c, k=k)),
+            "three_nn_weights": ("three_nn", lambda b, n, m, *r: dict(b=b, n=n, m=m)),
             "three_interpolate_wrapper": ("three_interpolate", lambda b, c, m, n, *r: dict(b=b, c=c, m=m, n=n)),
+            "three_interpolate_affine": ("three_interpolate_affine", lambda b, c, m, n, *r: dict(b=b, c=c, m=m, n=n)),
+            "split_pointcloud": ("split_pointcloud", lambda pc, *r: dict(b=pc.shape[0], n=pc.shape[1], c=pc.shape[2] - 3)),
             "sa_mlp_fused": ("sa_mlp_fused", lambda b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, *r:
-                             dict(b=b, n=n, m=m, k=nsample, c=c_feat, c3=widths[2])),
-            "mlp_layer": ("mlp_layer", lambda b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool:
+                             dict(b=b, n=n, m=m, k=nsample, c=c_feat, c1=widths[0], c2=widths[1], c3=widths[2])),
+            "mlp_layer": ("mlp_layer", lambda b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool, *r:
                           dict(b=b, c_out=c_out, c_in=c1 + c2, cols=cols, pool=pool)),
         }
         for attr, (name, dims) in table.items():
@@ -214,14 +267,16 @@ class OpProfiler:
         for name, dims, s, e in self.records:
             ms = s.elapsed_time(e)
             key = (name, tuple(sorted(dims.items())))
-            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "bytes": ALG_BYTES[name](**dims)})
+            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "bytes": ALG_BYTES[name](**dims),
+                                     "flops": ALG_FLOPS[name](**dims) if name in ALG_FLOPS else 0})
             a["ms"] += ms
             a["launches"] += 1
         out = []
         for (name, dims), a in agg.items():
             avg = a["ms"] / a["launches"]
             out.append({"kernel": name, "dims": dict(dims), "avg_ms": avg, "ms_per_step": a["ms"] / steps,
-                        "alg_bytes": a["bytes"], "GBps": a["bytes"] / avg / 1e6})
+                        "alg_bytes": a["bytes"], "GBps": a["bytes"] / avg / 1e6, "flops": a["flops"],
+                        "TFLOPs": a["flops"] / avg / 1e9})
         out.sort(key=lambda r: -r["ms_per_step"])
         return out
 
@@ -230,7 +285,8 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from ws3d_b200 import _C, models, native, synth
+    from ws3d_b200 import _C, models, native, synth, workloads
+    from ws3d_b200.graphs import CudaGraphRunner, PipelinedBackboneRunner, StreamedBackboneRunner
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,49 +299,14 @@ def run_gpu(args):
     model = models.Pointnet2MSG(input_channels=1).to(dev).eval()
     # every rank works on its own clouds (scenes shard across GPUs; no data-path collective)
     host = torch.from_numpy(synth.make_batch(BATCH, NPTS, first_scene=rank * BATCH)).pin_memory()
+    host_b = torch.from_numpy(synth.make_batch(BATCH, NPTS, first_scene=(world + rank) * BATCH)).pin_memory()
+    hosts = [host, host_b]
     resident = host.to(dev)
-
-    def step_eager():
-        with torch.no_grad():
-            return model(resident)[1]
-
-    use_graph = os.environ.get("WS3D_CUDA_GRAPH", "1") != "0"
-    if use_graph:
-        # the forward (both streams) captured once, replayed per step: same kernels, no per-launch host work
-        from ws3d_b200.graphs import CudaGraphRunner
-        runner = CudaGraphRunner(lambda x: model(x)[1], resident)
-
-        def step_resident():
-            return runner(runner.static_in)
-
-        def step_e2e():
-            runner.static_in.copy_(host, non_blocking=True)   # H2D of this step's clouds (pinned source)
-            feats = runner(runner.static_in)
-            return feats.sum(dim=(1, 2)).cpu()                 # D2H read of the per-cloud checksum (synchronises)
-    else:
-        step_resident = step_eager
-
-        def step_e2e():
-            with torch.no_grad():
-                x = host.to(dev, non_blocking=True)
-                feats = model(x)[1]
-                return feats.sum(dim=(1, 2)).cpu()  # D2H read of the per-cloud checksum (synchronises)
-
-    # Software pipeline (ws3d_b200.graphs.PipelinedBackboneRunner): one replay = level-1 FPS of batch i+1 beside the
-    # rest of the forward pass of batch i.  A step still completes exactly one batch of 16 clouds.
-    pipelined = use_graph and args.inflight >= 2
-    if pipelined:
-        from ws3d_b200.graphs import PipelinedBackboneRunner
-        native.set_sm_budget(args.sm_budget)
-        host_b = torch.from_numpy(synth.make_batch(BATCH, NPTS, first_scene=(world + rank) * BATCH)).pin_memory()
-        hosts = [host, host_b]
-        pr = PipelinedBackboneRunner(model, resident)
-        pr.stage[0].copy_(host)
-        pr.stage[1].copy_(host_b)
-        pr.prefetch(pr.stage[0])
-
-        def step_pipe():
-            return pr.step()
+    residents = [resident, host_b.to(dev)]
+    steps, warm = args.steps, max(args.warmup, 3)
+    look = max(1, args.inflight - 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_small = torch.empty(160 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def sync_all():
         torch.cuda.synchronize()
@@ -293,18 +314,29 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    def max_ms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def timed_region(step_fn, steps, profile):
-        prof = None
-        if profile:
-            prof = OpProfiler(torch)
-            prof.wrap(native)
-        launches0 = _C.launch_count()
+    def step_eager(x=None):
+        with torch.no_grad():
+            return model(resident if x is None else x)[1]
+
+    # ---- the plain forward: what every pipelined result is checked against
+    with torch.no_grad():
+        plain = [model(r)[1].clone() for r in residents]
+        plain_sums = [p.sum(dim=(1, 2)) for p in plain]
+    torch.cuda.synchronize()
+
+    # ---- one batch in flight: the two-stream forward captured once, replayed per step
+    runner = CudaGraphRunner(lambda x: model(x)[1], resident)
+
+    def timed_per_step(step_fn, n):
         total = 0.0
         sync_all()
-        t_wall = time.perf_counter()
-        for _ in range(steps):
+        for _ in range(n):
             flush.fill_(0)  # L2 flush between timed iterations (outside the event pair)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -313,136 +345,110 @@ def run_gpu(args):
             e.synchronize()
             total += s.elapsed_time(e)
         sync_all()
-        wall = time.perf_counter() - t_wall
-        launches = _C.launch_count() - launches0
-        if prof:
-            prof.unwrap()
-        t = torch.tensor([total], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, prof, wall
+        return max_ms(total)
 
-    def timed_stream_e2e(steps):
-        """K pipelined steps from pinned HOST batches, one event pair round all of them: per step an H2D copy of the
-        batch after next (copy stream, overlapping the running step), one replay, a checksum kernel and an async
-        D2H read of it; the host only ever waits for the PREVIOUS step's result.  L2 is flushed in-stream."""
-        pinned = [torch.empty(BATCH, dtype=torch.float32).pin_memory() for _ in range(2)]
-        read_ev = [None, None]
-        results = []
-        pr.prefetch(hosts[0])
-        pr.stage_next(hosts[1])
-        sync_all()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for j in range(steps):
-            flush_small.fill_(0)
-            out = pr.step()                       # completes batch j (samples batch j+1 meanwhile)
-            pr.stage_next(hosts[j % 2])           # H2D of batch j+2, waits only for the replay that read that buffer
-            if read_ev[j % 2] is not None:        # result of step j-2 must have been consumed before its buffer is reused
-                read_ev[j % 2].synchronize()
-                results.append(float(pinned[j % 2][0]))
-            pinned[j % 2].copy_(out.sum(dim=(1, 2)), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            read_ev[j % 2] = ev
-        for k in ((steps) % 2, (steps + 1) % 2):
-            if read_ev[k] is not None:
-                read_ev[k].synchronize()
-                results.append(float(pinned[k][0]))
-        e.record()
-        e.synchronize()
-        sync_all()
-        t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        assert len(results) == steps
-        return float(t.item())
+    def step_single():
+        return runner(runner.static_in)
 
-    flush_small = torch.empty(160 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-        step_e2e()
-        step_eager()
-        if pipelined:
-            step_pipe()
-    if pipelined:
-        timed_stream_e2e(max(args.warmup, 3))
-    sync_all()
+    def step_single_e2e():
+        runner.static_in.copy_(host, non_blocking=True)
+        return runner(runner.static_in).sum(dim=(1, 2)).cpu()
 
+    for _ in range(warm):
+        step_single()
+        step_single_e2e()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.__enter__()
-    ms_total, launches, _, _ = timed_region(step_resident, args.steps, profile=False)
-    if use_graph:   # replays do not pass through the C ABI: count the kernels of one eager step instead
-        l0 = _C.launch_count()
-        step_eager()
-        torch.cuda.synchronize()
-        launches = (_C.launch_count() - l0) * args.steps
-    ms_e2e, _, _, _ = timed_region(step_e2e, args.steps, profile=False)
-    ms_single, ms_single_e2e = ms_total, ms_e2e
-    if pipelined:
+    ms_single = timed_per_step(step_single, steps)
+    ms_single_e2e = timed_per_step(step_single_e2e, steps)
+    single_ok = bool(torch.equal(runner(runner.static_in), plain[0]))
+    l0 = _C.launch_count()
+    step_eager()
+    torch.cuda.synchronize()
+    launches_per_step = _C.launch_count() - l0
+
+    # ---- two batches in flight: level-1 FPS of batch i+1 beside the rest of batch i (one replay per step)
+    native.set_sm_budget(args.sm_budget)
+    two = None
+    if args.inflight >= 2:
+        pr = PipelinedBackboneRunner(model, resident)
+        pr.stage[0].copy_(host)
+        pr.stage[1].copy_(host_b)
         pr.prefetch(pr.stage[0])
-        ms_total, _, _, _ = timed_region(step_pipe, args.steps, profile=False)
-        ms_e2e = timed_stream_e2e(args.steps)
-    ms_two, ms_two_e2e = ms_total, ms_e2e
-    deep = pipelined and args.inflight >= 3
-    if deep:
-        # The coordinate phase (FPS levels in throughput mode, ball queries, stencils) runs `inflight - 1` batches ahead
-        # on its own streams beside the feature phase (ws3d_b200.graphs.StreamedBackboneRunner).  K steps, one event pair.
-        from ws3d_b200.graphs import StreamedBackboneRunner
-        look = args.inflight - 1
-        sr = StreamedBackboneRunner(model, resident, lookahead=look, feature_streams=args.feature_streams)
+        for _ in range(warm):
+            pr.step()
+        pr.prefetch(pr.stage[0])
+        ms_two = timed_per_step(pr.step, steps)
+        two = {"ms_per_step": round(ms_two / steps, 4), "Mpoints_per_s": round(world * BATCH * NPTS / (ms_two / steps / 1e3) / 1e6, 3),
+               "note": "PipelinedBackboneRunner: FPS of batch i+1 inside the same replay as the rest of batch i; per-step event pairs, "
+                       "L2 flushed between steps"}
+        del pr
 
-        def flush_stream(runner, j):   # the stream the feature phase of step j will run on
-            fs = runner.feature_streams
-            return torch.cuda.current_stream(dev) if fs is None else fs[runner.tail % len(fs)]
-        residents = [resident, host_b.to(dev)]
+    # ---- the headline: coordinate phases `look` batches ahead of the feature phases (StreamedBackboneRunner)
+    sr = StreamedBackboneRunner(model, resident, lookahead=look, feature_streams=args.feature_streams)
 
-        def timed_streamed(sr, steps, from_host):
-            src = hosts if from_host else residents
-            pinned = [torch.empty(BATCH, dtype=torch.float32).pin_memory() for _ in range(2)]
-            read_ev = [None, None]
-            for j in range(look):
-                sr.submit(src[j % 2])
-            sync_all()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            sr.fork()
+    def timed_streamed(runner_, n, from_host, check):
+        """Exactly n batches between two device synchronisations: s.record -> the first `look` submits (pipeline fill) ->
+        n x (L2 flush, feature phase of batch j, checksum, submit of batch j + look while j + look < n) -> every stream
+        joined -> e.record.  n coordinate phases and n feature phases are issued and finished inside the region."""
+        src = hosts if from_host else residents
+        sums = torch.zeros((n, BATCH), dtype=torch.float32, device=dev)
+        pinned = torch.zeros((n, BATCH), dtype=torch.float32).pin_memory() if from_host else None
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        runner_.fork()
+        for j in range(min(look, n)):
+            runner_.submit(src[j % 2])
 
-            def consume(j):
-                def fn(out):
-                    if read_ev[j % 2] is not None:            # the pinned slot of step j-2 has been read by now
-                        read_ev[j % 2].synchronize()
-                    pinned[j % 2].copy_(out.sum(dim=(1, 2)), non_blocking=True)   # per-cloud checksum -> async D2H
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    read_ev[j % 2] = ev
-                return fn
+        def consume(j):
+            def fn(out):
+                feats = out[0] if isinstance(out, (tuple, list)) else out
+                torch.sum(feats, dim=(1, 2), out=sums[j])          # per-cloud checksum of this step's result
+                if from_host:
+                    pinned[j].copy_(sums[j], non_blocking=True)   # D2H read of the result, ordered after the step
+            return fn
 
-            for j in range(steps):
-                # (the runner alternates consecutive feature phases between its `feature_streams` internal streams)
-                with torch.cuda.stream(flush_stream(sr, j)):
-                    flush_small.fill_(0)                      # in-stream L2 flush, inside the timed region
-                sr.complete(consume(j) if from_host else None)    # feature phase of batch j (+ result read-back)
-                sr.submit(src[(j + look) % 2])                # staging copy + coordinate phase of batch j + look (own stream)
-            sr.join()
-            e.record()
-            e.synchronize()
-            for _ in range(look):                         # drain the batches sampled ahead
-                sr.complete()
-            sync_all()
-            t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
+        for j in range(n):
+            fs = runner_.feature_streams
+            st = torch.cuda.current_stream(dev) if fs is None else fs[runner_.tail % len(fs)]
+            with torch.cuda.stream(st):
+                flush_small.fill_(0)                              # in-stream L2 flush, inside the timed region
+            runner_.complete(consume(j))
+            if j + look < n:
+                runner_.submit(src[(j + look) % 2])
+        runner_.join()
+        e.record()
+        e.synchronize()
+        sync_all()
+        ms = max_ms(s.elapsed_time(e))
+        ok = None
+        if check is not None:
+            got = pinned.to(dev) if from_host else sums
+            ok = all(bool(torch.equal(got[j], check[j % 2])) for j in range(n))
+        return ms, ok
 
-        timed_streamed(sr, max(args.warmup, 3), False)
-        timed_streamed(sr, max(args.warmup, 3), True)
-        ms_total = timed_streamed(sr, args.steps, False)
-        ms_e2e = timed_streamed(sr, args.steps, True)
-    # the same K steps once more with a CUDA-event pair round every launch of this library (per-kernel durations
-    # for the roofline entries; kept out of `value` because ~600 extra event records per step cost host time)
-    def step_eager_two_phase():   # what the streamed pipeline runs, serially: coordinate phase (throughput FPS), feature phase
+    timed_streamed(sr, warm + look, False, None)
+    timed_streamed(sr, warm + look, True, None)
+    ms_total, ok_resident = timed_streamed(sr, steps, False, plain_sums)
+    last = sr.outputs[(sr.tail - 1) % sr.nbuf]
+    ok_full = bool(torch.equal(last, plain[(steps - 1) % 2]))
+    ms_e2e, ok_host = timed_streamed(sr, steps, True, plain_sums)
+    long_steps = max(steps, 200)
+    if long_steps != steps:   # converged figure: fill / drain amortised over >= 200 batches (same closed accounting)
+        ms_long, ok_long = timed_streamed(sr, long_steps, False, plain_sums)
+        ms_long_e2e, ok_long_e2e = timed_streamed(sr, long_steps, True, plain_sums)
+    else:
+        ms_long, ok_long, ms_long_e2e, ok_long_e2e = ms_total, ok_resident, ms_e2e, ok_host
+    verify = {"streamed_checksums_equal_plain_forward": bool(ok_resident and ok_host and ok_long and ok_long_e2e),
+              "streamed_last_output_equals_plain_forward": ok_full, "graph_replay_equals_plain_forward": single_ok,
+              "steps_checked": 2 * steps + (2 * long_steps if long_steps != steps else 0)}
+    if not (verify["streamed_checksums_equal_plain_forward"] and ok_full and single_ok):
+        raise SystemExit("bench.py: the pipelined forward differs from the plain forward: " + json.dumps(verify))
+
+    # ---- the same batches once more, eagerly and serially, with a CUDA-event pair round every launch of this library
+    def step_eager_two_phase():   # what the streamed pipeline runs: coordinate phase (throughput FPS), feature phase
         with torch.no_grad():
             prev = native.set_fps_mode(1)
             try:
@@ -451,133 +457,336 @@ def run_gpu(args):
                 native.set_fps_mode(prev)
             return model.feature_phase(resident, plan)[1]
 
-    if deep:
-        for _ in range(2):
-            step_eager_two_phase()
-    ms_prof, _, prof, _ = timed_region(step_eager_two_phase if deep else step_eager, args.steps, profile=True)
-    # Stage-1 RPN = backbone + the two per-point heads (lib/net/rpn.py:67-81): scenes/s for the metric's second half
+    for _ in range(2):
+        step_eager_two_phase()
+    prof_steps = min(steps, 20)
+    prof = OpProfiler(torch)
+    prof.wrap(native)
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(prof_steps):
+        step_eager_two_phase()
+    t1.record()
+    t1.synchronize()
+    prof.unwrap()
+    ms_prof = t0.elapsed_time(t1)
+    kernels = prof.summarize(prof_steps)
+
+    # ---- Stage-1 RPN = backbone + the two per-point heads (lib/net/rpn.py:67-81), same pipeline
     rpn = models.RPN().to(dev).eval()
     rpn.backbone_net = model
 
-    def rpn_heads(pc, first=None):
-        o = rpn(pc, first_samples=first)
-        return o["rpn_cls"], o["rpn_reg"]
+    def rpn_heads_plan(pc, plan):
+        o = rpn(pc, plan=plan)
+        return o["backbone_features"], o["rpn_cls"], o["rpn_reg"]
 
-    if pipelined:
-        rpn_pr = PipelinedBackboneRunner(model, resident, fn=rpn_heads)
-        rpn_pr.stage[0].copy_(host)
-        rpn_pr.stage[1].copy_(host_b)
-        rpn_pr.prefetch(rpn_pr.stage[0])
-
-        def step_rpn():
-            return rpn_pr.step()
-    elif use_graph:
-        rpn_runner = CudaGraphRunner(rpn_heads, resident)
-
-        def step_rpn():
-            return rpn_runner(rpn_runner.static_in)
-    else:
-        def step_rpn():
-            with torch.no_grad():
-                return rpn(resident)["rpn_cls"]
-
-    for _ in range(3):
-        step_rpn()
-    ms_rpn, _, _, _ = timed_region(step_rpn, args.steps, profile=False)
-    if deep:
-        def rpn_heads_plan(pc, plan):
-            o = rpn(pc, plan=plan)
-            return o["rpn_cls"], o["rpn_reg"]
-
-        rpn_sr = StreamedBackboneRunner(model, resident, fn=rpn_heads_plan, lookahead=look, feature_streams=args.feature_streams)
-        timed_streamed(rpn_sr, 3, False)
-        ms_rpn = timed_streamed(rpn_sr, args.steps, False)
+    rpn_sr = StreamedBackboneRunner(model, resident, fn=rpn_heads_plan, lookahead=look, feature_streams=args.feature_streams)
+    timed_streamed(rpn_sr, warm + look, False, None)
+    ms_rpn, ok_rpn = timed_streamed(rpn_sr, steps, False, plain_sums)
+    ms_rpn_long, _ = timed_streamed(rpn_sr, long_steps, False, plain_sums) if long_steps != steps else (ms_rpn, None)
+    verify["rpn_backbone_checksums_equal_plain_forward"] = bool(ok_rpn)
+    del rpn_sr
     if sampler:
         sampler.__exit__(None, None, None)
 
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = world * BATCH * NPTS / (ms_step / 1e3) / 1e6
-    e2e_value = world * BATCH * NPTS / (ms_e2e / args.steps / 1e3) / 1e6
-    peak, peak_src = measured_peaks()
-    roof = None
-    kernels = []
-    if prof:
-        kernels = prof.summarize(args.steps)
-        top = kernels[0]
-        roof = {"bound": "hbm", "kernel": top["kernel"], "dims": top["dims"], "achieved": round(top["GBps"], 3), "peak": peak,
-                "unit": "GB/s", "frac": round(top["GBps"] / peak, 6), "traffic": measured_traffic(top["kernel"], top["dims"]),
-                "peak_source": peak_src, "alg_bytes": int(top["alg_bytes"]),
-                "avg_launch_ms": round(top["avg_ms"], 4), "share_of_step": round(top["ms_per_step"] / (ms_prof / args.steps), 4),
-                "profiled_ms_per_step": round(ms_prof / args.steps, 4),
-                "note": ("FPS is a latency chain of m-1 dependent iterations (SURVEY.md 8d): its HBM fraction is reported for the "
-                         "record; us/iteration is the meaningful figure.  In the pipelined modes it runs beside the feature "
-                         "phase of other batches (throughput mode: one SM per cloud), so its share of the SERIAL profile pass "
-                         "below is not its share of the timed step" if top["kernel"] == "fps" else "")}
-        if top["kernel"] == "fps":
-            roof["us_per_iteration"] = round(top["avg_ms"] * 1e3 / (top["dims"]["m"] - 1), 4)
+    e2e_value = world * BATCH * NPTS / (ms_e2e / steps / 1e3) / 1e6
+    peak, peak_tf, peak_src = measured_peaks()
+    tf32_peak = peak_tf / 2   # TF32 issues at half the BF16 rate on the 5th-generation tensor cores
 
+    feature = [k for k in kernels if k["kernel"] not in COORDINATE_KERNELS]
+    top = feature[0]
+    feature_ms = sum(k["ms_per_step"] for k in feature)
+    coord_ms = sum(k["ms_per_step"] for k in kernels if k["kernel"] in COORDINATE_KERNELS)
+    tensor_bound = top["flops"] > 0 and top["TFLOPs"] / tf32_peak > top["GBps"] / peak
+    roof = {"bound": "tensor" if tensor_bound else "hbm", "kernel": top["kernel"], "dims": top["dims"],
+            "achieved": round(top["TFLOPs"] if tensor_bound else top["GBps"], 3), "peak": tf32_peak if tensor_bound else peak,
+            "unit": "TFLOP/s" if tensor_bound else "GB/s",
+            "frac": round((top["TFLOPs"] / tf32_peak) if tensor_bound else (top["GBps"] / peak), 6),
+            "traffic": measured_traffic(top["kernel"], top["dims"]), "peak_source": peak_src + ("; TF32 = BF16 / 2" if tensor_bound else ""),
+            "alg_bytes": int(top["alg_bytes"]), "alg_flops": int(top["flops"]), "avg_launch_ms": round(top["avg_ms"], 4),
+            "hbm": {"achieved_GBps": round(top["GBps"], 2), "frac": round(top["GBps"] / peak, 5)},
+            "tensor": {"achieved_TFLOPs": round(top["TFLOPs"], 2), "frac_of_tf32_peak": round(top["TFLOPs"] / tf32_peak, 5)},
+            "share_of_feature_phase": round(top["ms_per_step"] / feature_ms, 4),
+            "feature_phase_serial_ms": round(feature_ms, 4), "coordinate_phase_serial_ms": round(coord_ms, 4),
+            "profiled_ms_per_step": round(ms_prof / prof_steps, 4),
+            "note": ("the streamed step is bounded by the feature phase (the coordinate phases run `look` batches ahead on their own "
+                     "streams, one SM per cloud); this is its longest launch in the serial profile pass.  Whole step: "
+                     f"{sum(k['alg_bytes'] * k['ms_per_step'] / k['avg_ms'] for k in kernels) / 1e9:.2f} GB algorithmic per batch = "
+                     f"{sum(k['alg_bytes'] * k['ms_per_step'] / k['avg_ms'] for k in kernels) / (ms_long / long_steps) / 1e6 / peak:.3f} "
+                     "of the HBM peak at the converged step time")}
+    fps_rec = None
+    fps_k = [k for k in kernels if k["kernel"] == "fps"]
+    if fps_k:
+        f0 = max(fps_k, key=lambda k: k["avg_ms"])
+        fps_rec = {"dims": f0["dims"], "avg_launch_ms": round(f0["avg_ms"], 4), "us_per_iteration": round(f0["avg_ms"] * 1e3 / (f0["dims"]["m"] - 1), 4),
+                   "target_us_per_iteration": [0.25, 0.4], "sms": f0["dims"]["b"], "mode": "throughput (one SM per cloud)",
+                   "hbm_frac": round(f0["GBps"] / peak, 6),
+                   "note": "latency chain of m-1 dependent iterations (SURVEY.md 8d): not HBM-bound; runs beside the feature phases"}
+
+    line = None
     if rank == 0:
-        cores = len(os.sched_getaffinity(0))
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            v, dt, thr = cpu_backbone_throughput(BATCH, repeats=2, threads=cores)
-            cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"the full batch ({BATCH} clouds x {NPTS} points), best of 2 passes ({dt:.1f} s each): oracle ops "
-                             f"(OpenMP, {thr} threads) + PyTorch CPU MLPs"}
         line = {
-            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points_per_cloud": NPTS, "l2": ("flushed before every step, in-stream and inside the timed region (160 MiB write > 126 MB L2)" if deep else
-                              "flushed between timed iterations (256 MiB write, outside the per-step event pair)"),
-                       "mlp": ("tcgen05 TF32, FP32 accumulate: SA1 / SA2 one fused kernel per scale (grouping + 3 layers + max-pool in "
-                               "tensor memory), other layers one launch per conv1x1+BN+ReLU[+max-pool]"
-                               if torch.backends.cudnn.allow_tf32 else "PyTorch/cuDNN fp32 (TF32 off)"),
-                       "launch": ("two CUDA graph replays per step (coordinate phase of batch i+N-1, feature phase of batch i)" if deep
-                                  else "one CUDA graph replay per step" if use_graph else "eager launches"),
-                       "pipeline": ((f"{args.inflight} batches in flight: the coordinate phase (4 FPS levels in throughput mode = one "
-                                     f"SM per cloud, ball queries, interpolation stencils) runs {args.inflight - 1} batches ahead on "
-                                     f"its own streams beside the graph-replayed feature phases, which alternate between "
-                                     f"{args.feature_streams} stream(s); one batch of 16 clouds completes per step; K steps under "
-                                     "one event pair, L2 flushed in-stream") if deep else
-                                    ("2 batches in flight: each replay runs level-1 FPS of batch i+1 (high-priority stream) beside "
-                                     "the rest of the forward pass of batch i; one batch of 16 clouds completes per step")
-                                    if pipelined else "none (one batch in flight)"),
-                       "sm_budget_persistent_kernels": args.sm_budget if pipelined else 0,
-                       "streams": "two CUDA streams (FPS chain + interpolation stencils run ahead of grouping / MLPs)"
-                                  if os.environ.get("WS3D_TWO_STREAMS", "1") != "0" else "single stream",
-                       "sharding": "scenes per rank, no data-path collective"},
+            "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points_per_cloud": NPTS,
+                       "timed_region": "exactly K batches between two device synchronisations; pipeline fill (the first "
+                                       f"{look} coordinate phases) and drain are inside it; every stream joined before the end event",
+                       "l2": "flushed before every step, in-stream and inside the timed region (160 MiB write > 126 MB L2)",
+                       "mlp": "tcgen05 TF32 inputs, FP32 accumulate (the class cuDNN uses for the reference's convolutions by default): "
+                              "SA1 / SA2 one fused kernel per scale, other layers one launch per conv1x1+BN+ReLU[+max-pool]; "
+                              "`fp32_exact` has the FP32 figure",
+                       "launch": "two CUDA graph replays per step (coordinate phase of batch i+N-1, feature phase of batch i)",
+                       "pipeline": f"{args.inflight} batches in flight, feature phases alternate between {args.feature_streams} stream(s)",
+                       "sm_budget_persistent_kernels": args.sm_budget, "sharding": "scenes per rank, no data-path collective"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4) * world,
-                    "d2h_bytes_per_step": BATCH * 4 * world, "ms_per_step": round(ms_e2e / args.steps, 4),
-                    "note": ("pinned host clouds -> H2D (copy stream) -> pipelined forward -> per-cloud feature checksum -> async D2H, "
-                             "K steps streamed under one event pair, L2 flushed in-stream every step" if pipelined else
-                             "pinned host cloud -> H2D -> backbone forward -> per-cloud feature checksum -> D2H")},
-            "two_in_flight": ({"ms_per_step": round(ms_two / args.steps, 4),
-                               "Mpoints_per_s": round(world * BATCH * NPTS / (ms_two / args.steps / 1e3) / 1e6, 3),
-                               "e2e_Mpoints_per_s": round(world * BATCH * NPTS / (ms_two_e2e / args.steps / 1e3) / 1e6, 3),
-                               "note": "PipelinedBackboneRunner: FPS of batch i+1 inside the same replay as the rest of batch i"}
-                              if deep else None),
-            "single_batch_latency": {"ms": round(ms_single / args.steps, 4),
-                                     "Mpoints_per_s": round(world * BATCH * NPTS / (ms_single / args.steps / 1e3) / 1e6, 3),
-                                     "e2e_ms": round(ms_single_e2e / args.steps, 4),
-                                     "note": "one batch in flight (graph replay of the two-stream forward), same timing method"},
-            "gpu_launches": int(launches),
-            "rpn": {"scenes_per_s": round(world * BATCH / (ms_rpn / args.steps / 1e3), 1), "ms_per_step": round(ms_rpn / args.steps, 4),
-                    "note": "Stage-1 RPN forward (backbone + cls/reg heads, lib/net/rpn.py:67-81), same batch, inputs resident"
-                            + (", same software pipeline as `value`" if pipelined else "")},
+                    "d2h_bytes_per_step": BATCH * 4 * world, "ms_per_step": round(ms_e2e / steps, 4),
+                    "note": "pinned host clouds -> H2D (coordinate stream) -> pipelined forward -> per-cloud feature checksum -> D2H, "
+                            "same closed K-batch region.  The API returns DEVICE tensors (134 MB of per-point features per batch, "
+                            "consumed by the heads / Stage 2 on the GPU); the 64-byte checksum is what a caller reads back"},
+            "steady_state": {"steps": long_steps, "ms_per_step": round(ms_long / long_steps, 4),
+                             "Mpoints_per_s": round(world * BATCH * NPTS / (ms_long / long_steps / 1e3) / 1e6, 3),
+                             "e2e_Mpoints_per_s": round(world * BATCH * NPTS / (ms_long_e2e / long_steps / 1e3) / 1e6, 3),
+                             "note": "same closed accounting over >= 200 batches: fill / drain amortised"},
+            "verify": verify,
+            "two_in_flight": two,
+            "single_batch_latency": {"ms": round(ms_single / steps, 4),
+                                     "Mpoints_per_s": round(world * BATCH * NPTS / (ms_single / steps / 1e3) / 1e6, 3),
+                                     "e2e_ms": round(ms_single_e2e / steps, 4),
+                                     "note": "one batch in flight (graph replay of the two-stream forward), per-step event pairs"},
+            "gpu_launches": int(launches_per_step * steps),
+            "rpn": {"scenes_per_s": round(world * BATCH / (ms_rpn / steps / 1e3), 1), "ms_per_step": round(ms_rpn / steps, 4),
+                    "steady_state_scenes_per_s": round(world * BATCH / (ms_rpn_long / long_steps / 1e3), 1),
+                    "note": "Stage-1 RPN forward (backbone + cls/reg heads as one chain, lib/net/rpn.py:67-81), same pipeline and accounting"},
             "clocks": sampler.summary() if sampler else None,
+            "roofline": roof, "fps": fps_rec,
+            "sm_time_budget": profile_json("r2_sm_budget.json"),
+            "kernels": [{"kernel": k["kernel"], "dims": k["dims"], "avg_ms": round(k["avg_ms"], 4),
+                         "ms_per_step": round(k["ms_per_step"], 4), "GBps": round(k["GBps"], 2),
+                         "frac": round(k["GBps"] / peak, 5), "TFLOPs": round(k["TFLOPs"], 2)} for k in kernels],
         }
-        if roof:
-            line["roofline"] = roof
-            line["kernels"] = [{"kernel": k["kernel"], "dims": k["dims"], "avg_ms": round(k["avg_ms"], 4),
-                                "ms_per_step": round(k["ms_per_step"], 4), "GBps": round(k["GBps"], 2),
-                                "frac": round(k["GBps"] / peak, 5)} for k in kernels]
-        if cpu:
-            line["cpu_baseline"] = cpu
+    del sr, runner
+    torch.cuda.synchronize()
+
+    # ---- BASELINE.json configs 3 and 5 run on every rank (they shard); 1, 4 and the baselines on rank 0 of a 1-GPU run
+    configs = {}
+    if not args.no_configs:
+        configs["3"] = bench_training(args, torch, dist, dev, world, rank, workloads, max_ms)
+        st2 = workloads.stage2_stack(dev, rank, scenes=1, flush=flush, iters=10)
+        ms5 = max_ms(st2["ms"])
+        configs["5"] = {"workload": "Stage-2 SA stack, 512 pooled proposals per scene x 512 points x 128 ch, 1 scene per GPU, forward",
+                        "ms_per_step": round(ms5, 4), "proposals_per_s": round(world * st2["proposals_per_gpu"] / ms5 * 1e3, 1), "n_gpus": world}
+        if world == 1:
+            configs["1"] = bench_config1(torch, dev, flush, workloads)
+            configs["4"] = bench_config4(torch, dev, flush, workloads, peak)
+    if rank == 0:
+        line["configs"] = configs
+        if world == 1 and not args.no_cpu_baseline:
+            line["fp32_exact"] = bench_fp32_exact(torch, model, residents, plain, flush, dev)
+            line["oracle_gpu"] = bench_oracle_gpu(torch, model, residents, flush, dev, ms_single / steps, ms_long / long_steps)
+            cores = len(os.sched_getaffinity(0))
+            v, dt, thr = cpu_backbone_throughput(BATCH, repeats=2, threads=cores)
+            v1, dt1, _ = cpu_backbone_throughput(1, repeats=1, threads=1)
+            line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"the full batch ({BATCH} clouds x {NPTS} points), best of 2 passes ({dt:.1f} s each): oracle "
+                                              f"ops (OpenMP, {thr} threads) + PyTorch CPU MLPs",
+                                    "one_thread": {"value": round(v1, 4), "unit": UNIT, "cores": 1,
+                                                   "sample": f"1 cloud x {NPTS} points, one pass ({dt1:.1f} s), 1 thread"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_training(args, torch, dist, dev, world, rank, workloads, max_ms):
+    """Config 3: Stage-1 RPN training step.  Weak scaling (32 scenes per GPU) and strong scaling (global batch 32);
+    with world > 1 the gradient all-reduce (NCCL) is inside the step; its share = 1 - t(no_sync) / t(sync)."""
+    out = {"workload": "Stage-1 RPN training step (forward in training mode, Gaussian labels on the GPU, get_rpn_loss, backward, Adam), "
+                       "synthetic scenes 16384 x 4"}
+    for tag, per_gpu in (("weak_32_per_gpu", 32), ("strong_global_32", max(1, 32 // world))):
+        if tag.startswith("strong") and world == 1:
+            continue
+        step = workloads.RpnTrainStep(per_gpu, dev, world, rank, graph=True)
+        n = max(3, min(args.steps, 8))
+
+        def timed(sync_grads):
+            for _ in range(2):
+                step(sync_grads)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(n):
+                loss = step(sync_grads)
+            e.record()
+            e.synchronize()
+            return max_ms(s.elapsed_time(e)) / n, float(loss)
+
+        ms, loss = timed(True)
+        rec = {"scenes_per_gpu": per_gpu, "n_gpus": world, "ms_per_step": round(ms, 3), "scenes_per_s": round(world * per_gpu / ms * 1e3, 1),
+               "final_loss": round(loss, 4), "steps": n, "launch": "one CUDA graph replay per step" if step.graphed else "eager (DDP)",
+               "mlp": train_mlp_description()}
+        if world > 1:
+            ms_ns, _ = timed(False)
+            rec["allreduce"] = {"bytes": step.param_bytes, "ms_per_step_without": round(ms_ns, 3),
+                                "share_of_step": round(max(0.0, 1.0 - ms_ns / ms), 4),
+                                "note": "DDP gradient all-reduce over NCCL / NVLink, overlapped with backward; share = 1 - t(no_sync) / t(sync)"}
+        out[tag] = rec
+        del step
+        torch.cuda.synchronize()
+    return out
+
+
+def train_mlp_description():
+    try:
+        from ws3d_b200 import train_mlp
+        return train_mlp.DESCRIPTION
+    except Exception:
+        return "PyTorch / cuDNN shared MLPs on channels-last activations (batch statistics, autograd) over this repo's ops and gradient kernels"
+
+
+def bench_config1(torch, dev, flush, workloads):
+    """Config 1: one SA layer's irregular ops on one cloud; GPU beside the CPU port at 1 thread and on all cores."""
+    cores = len(os.sched_getaffinity(0))
+    g = workloads.single_sa_layer(dev, flush)
+    _, idx, bq = g.pop("tensors")
+    t1, idx1, bq1 = cpu_single_sa_layer(1)
+    tn, _, _ = cpu_single_sa_layer(cores)
+    parity = bool(np.array_equal(idx.cpu().numpy(), idx1) and np.array_equal(bq.cpu().numpy(), bq1))
+    if not parity:
+        raise SystemExit("bench.py: config 1 indices differ from the oracle")
+    return {"workload": "single SA layer: FPS 16384 -> 4096 + ball_query r=0.8 K=32 on one synthetic 16384x4 cloud (BASELINE configs[0])",
+            "gpu": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in g.items()},
+            "cpu_port": {"one_thread": {"ms": round(t1 * 1e3, 2), "Mpoints_per_s": round(NPTS / t1 / 1e6, 4)},
+                         "all_cores": {"cores": cores, "ms": round(tn * 1e3, 2), "Mpoints_per_s": round(NPTS / tn / 1e6, 4)},
+                         "note": "FPS is serial per cloud: with one cloud only the ball query uses more than one core"},
+            "indices_equal_oracle": parity}
+
+
+def bench_config4(torch, dev, flush, workloads, peak):
+    """Config 4: BEV IoU + NMS on 16384 boxes, roipool3d 16384 boxes x 16384 points; CPU port on bounded subsets."""
+    import oracle
+    r = workloads.iou_nms_roipool(dev, flush)
+    sc = r.pop("scene")
+    out = {"workload": "roipool3d + iou3d NMS: 16384 proposals x 16384 points, one scene (BASELINE configs[3])"}
+    for k, v in r.items():
+        if isinstance(v, dict):
+            v = {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+            if "GBps" in v:
+                v["hbm_frac"] = round(v["GBps"] / peak, 4)
+        out[k] = v
+    cores = len(os.sched_getaffinity(0))
+    oracle.set_num_threads(cores)
+    sub = 2048
+    bev = sc["bev"][sc["scores"].sort(descending=True)[1]][:sub].cpu().numpy()
+    t0 = time.perf_counter()
+    oracle.nms(bev, 0.85)
+    t_nms = time.perf_counter() - t0
+    xyz = sc["xyz"][0].cpu().numpy()
+    t0 = time.perf_counter()
+    oracle.roipool3d_cpu(xyz, sc["boxes3d"][0, :256].cpu().numpy(), sc["features"][0, :, :1].cpu().numpy(), 512)
+    t_roi = time.perf_counter() - t0
+    out["cpu_port"] = {"cores": cores, "nms_2048_boxes_ms": round(t_nms * 1e3, 2),
+                       "nms_16384_boxes_extrapolated_ms": round(t_nms * 1e3 * (16384 / sub) ** 2, 1),
+                       "roipool3d_256_boxes_C1_ms": round(t_roi * 1e3, 2),
+                       "roipool3d_16384_boxes_C1_extrapolated_ms": round(t_roi * 1e3 * 16384 / 256, 1),
+                       "note": "bounded subsets (full size is O(1e11) operations on the host); NMS scales with boxes^2, roipool with boxes"}
+    return out
+
+
+def bench_fp32_exact(torch, model, residents, plain, flush, dev):
+    """The FP32-exact figure beside the TF32 headline: TF32 off -> the modules take the PyTorch FP32 MLP path over the
+    same ops.  Checked against the CPU oracle composition on one cloud (allclose 2e-4)."""
+    from oracle import cpu_backbone
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            for _ in range(2):
+                out32 = model(residents[0])[1]
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                flush.fill_(0)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out32 = model(residents[0])[1]
+                e.record()
+                e.synchronize()
+                ts.append(s.elapsed_time(e))
+        ms = float(np.median(ts))
+        from ws3d_b200 import models as _models
+        cpu_model = _models.Pointnet2MSG(input_channels=1).eval()
+        cpu_model.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+        want = cpu_backbone.backbone_forward(cpu_model, residents[0][:1].cpu().numpy())[1]
+        got = out32[:1].cpu().numpy()
+        scale = float(np.abs(want).max())
+        err = float(np.abs(got - want).max())
+        ok = bool(np.allclose(got, want, rtol=2e-4, atol=2e-4 * scale))
+        tf32_err = float((plain[0] - out32).abs().max()) / float(out32.abs().max())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    if not ok:
+        raise SystemExit(f"bench.py: the FP32 path differs from the CPU oracle composition (max abs {err}, scale {scale})")
+    return {"ms_per_step": round(ms, 4), "Mpoints_per_s": round(BATCH * NPTS / ms / 1e3, 3), "mlp": "PyTorch / cuDNN FP32 (allow_tf32 = False), one batch in flight, eager",
+            "allclose_to_cpu_oracle_2e-4": ok, "max_abs_err_vs_cpu_oracle": err, "output_scale": scale,
+            "tf32_headline_vs_fp32_max_rel_err": round(tf32_err, 6)}
+
+
+def bench_oracle_gpu(torch, model, residents, flush, dev, ms_single, ms_streamed):
+    """the same PyTorch modules over the REFERENCE's kernels (oracle/_ref, recompiled for sm_100a)
+    in the reference's unfused sequencing -- one batch in flight, and best effort with several batches on their own streams."""
+    try:
+        from oracle.ref_backbone import RefOps, load_ref, ref_forward
+        if load_ref("pointnet2_cuda") is None:
+            return {"unavailable": "oracle/_ref/pointnet2_cuda.so is not built (oracle/build_ref.sh needs /root/reference)"}
+        ops = RefOps()
+    except Exception as ex:   # noqa: BLE001
+        return {"unavailable": f"{type(ex).__name__}: {ex}"}
+    with torch.no_grad():
+        for _ in range(2):
+            ref_forward(model, ops, residents[0])
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            flush.fill_(0)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = ref_forward(model, ops, residents[0])[1]
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms_one = float(np.median(ts))
+        # best effort: 4 batches side by side on 4 streams, 2 rounds
+        streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        main = torch.cuda.current_stream(dev)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for st in streams:
+            st.wait_stream(main)
+        for r in range(2):
+            for k, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    ref_forward(model, ops, residents[(r + k) % 2])
+        for st in streams:
+            main.wait_stream(st)
+        e.record()
+        e.synchronize()
+        ms_multi = s.elapsed_time(e) / 8
+    return {"impl": "reference kernels (pointnet2_lib/pointnet2/src/*.cu, unmodified, -gencode sm_100a) under the same PyTorch modules, cuDNN TF32 MLPs",
+            "one_in_flight": {"ms_per_step": round(ms_one, 3), "Mpoints_per_s": round(BATCH * NPTS / ms_one / 1e3, 3)},
+            "four_streams": {"ms_per_step": round(ms_multi, 3), "Mpoints_per_s": round(BATCH * NPTS / ms_multi / 1e3, 3)},
+            "speedup_one_in_flight": round(ms_one / ms_single, 2), "speedup_best_vs_best": round(min(ms_one, ms_multi) / ms_streamed, 2),
+            "note": "speedup_one_in_flight = reference one-in-flight / this repo's single-batch latency; speedup_best_vs_best = the "
+                    "reference arm's better figure / this repo's converged streamed step"}
 
 
 def main():
@@ -586,16 +795,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side legs (cpu_baseline, fp32_exact, oracle_gpu)")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE.json configs 1, 3, 4, 5")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "6")),
-                    help=">= 3: coordinate phase (FPS, ball queries, stencils) N-1 batches ahead of the feature phase "
-                         "(StreamedBackboneRunner); 2: level-1 FPS of the next batch beside the current batch; 1: no pipeline")
+                    help="batches in flight: the coordinate phase (FPS, ball queries, stencils) runs N-1 batches ahead of the feature phase")
     ap.add_argument("--feature-streams", type=int, default=int(os.environ.get("WS3D_FEATURE_STREAMS", "2")),
-                    help="streams the feature phases of consecutive batches alternate between (streamed pipeline)")
+                    help="streams the feature phases of consecutive batches alternate between")
     ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "100")),
-                    help="SMs a persistent MLP kernel spreads over in the pipelined modes (0 = all 148; the coordinate phases of the "
-                         "batches ahead hold 3-5 x 16 SMs, so full-width grids would queue behind them: 185.4 / 186.8 / 187.6 Mpoints/s "
-                         "at 0 / 72 / 100)")
+                    help="SMs a persistent MLP kernel spreads over in the pipelined modes (0 = all)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_cpu(args)

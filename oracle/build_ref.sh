@@ -67,3 +67,6 @@ g++ -shared "$OBJ"/{pointnet2_api,sampling,ball_query,group_points,interpolate,s
 g++ -shared "$OBJ"/{iou3d,iou3d_kernel}.o $LIBS -o "$OUT/iou3d_cuda.so"
 g++ -shared "$OBJ"/{roipool3d,roipool3d_kernel}.o $LIBS -o "$OUT/roipool3d_cuda.so"
 echo "build_ref: wrote $OUT/{pointnet2_cuda,iou3d_cuda,roipool3d_cuda}.so"
+
+# --- the reference's Python op wrappers as one archive next to the extensions they bind (see oracle/stage_refpy.py)
+$PY "$HERE/stage_refpy.py" "$REF" "$OUT/refpy.zip"

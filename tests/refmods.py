@@ -1,30 +1,70 @@
 """Loaders for the checkers used by the tests: the reference's own extension modules built into
 oracle/_ref/ (TEST INFRASTRUCTURE, see oracle/build_ref.sh) under private names, so they never
-shadow the product's drop-in modules."""
-import importlib.machinery
-import importlib.util
+shadow the product's drop-in modules.  On a machine with a CUDA device a missing oracle/_ref is a
+test FAILURE (require_ref), not a silent downgrade to oracle-only checks."""
 import os
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-_cache = {}
+import pytest
+
+from oracle.ref_backbone import REF_DIR, load_ref  # noqa: F401
 
 
 def have_ref(name: str) -> bool:
     return os.path.exists(os.path.join(REF_DIR, name + ".so"))
 
 
-def load_ref(name: str):
-    """name in {pointnet2_cuda, iou3d_cuda, roipool3d_cuda}; returns the module or None."""
-    if name in _cache:
-        return _cache[name]
-    path = os.path.join(REF_DIR, name + ".so")
-    mod = None
-    if os.path.exists(path):
-        import torch  # noqa: F401  (the extension links against libtorch)
-        loader = importlib.machinery.ExtensionFileLoader(name, path)
-        spec = importlib.util.spec_from_loader(name, loader)
-        mod = importlib.util.module_from_spec(spec)
-        loader.exec_module(mod)
-    _cache[name] = mod
+def require_ref(name: str):
+    """The reference extension `name`, or a hard test failure: the parity claim against the reference's own kernels
+    must not evaporate because oracle/_ref did not travel to the GPU box."""
+    mod = load_ref(name)
+    if mod is None:
+        pytest.fail(f"oracle/_ref/{name}.so is missing: run oracle/build_ref.sh where /root/reference exists "
+                    "(it is git-ignored but travels with the gpurun snapshot)")
     return mod
+
+
+REFPY_ZIP = os.path.join(REF_DIR, "refpy.zip")
+_REF_PACKAGES = ("pointnet2_lib", "lib")
+
+
+def load_reference_python(natives: dict):
+    """The reference's own Python op wrappers (oracle/_ref/refpy.zip: pointnet2_utils / pointnet2_modules / pytorch_utils /
+    iou3d_utils / roipool3d_utils, UNMODIFIED) imported with `natives` = {"pointnet2_cuda": mod, "iou3d_cuda": mod,
+    "roipool3d_cuda": mod} as the extension modules they bind at import time.  Every call returns a FRESH set of module
+    objects, so the same files can be loaded once over the product's drop-ins and once over the reference extensions."""
+    import sys
+    import types
+    if not os.path.exists(REFPY_ZIP):
+        return None
+
+    def purge():
+        for name in list(sys.modules):
+            if name.split(".")[0] in _REF_PACKAGES:
+                del sys.modules[name]
+
+    saved = {k: sys.modules.get(k) for k in natives}
+    purge()
+    sys.modules.update(natives)
+    sys.path.insert(0, REFPY_ZIP)
+    try:
+        import lib.utils.iou3d.iou3d_utils as iou3d_utils
+        import lib.utils.roipool3d.roipool3d_utils as roipool3d_utils
+        import pointnet2_lib.pointnet2.pointnet2_modules as pointnet2_modules
+        import pointnet2_lib.pointnet2.pointnet2_utils as pointnet2_utils
+    finally:
+        sys.path.remove(REFPY_ZIP)
+        purge()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return types.SimpleNamespace(pointnet2_utils=pointnet2_utils, pointnet2_modules=pointnet2_modules, iou3d_utils=iou3d_utils,
+                                 roipool3d_utils=roipool3d_utils)
+
+
+def require_reference_python(natives: dict):
+    ns = load_reference_python(natives)
+    if ns is None:
+        pytest.fail("oracle/_ref/refpy.zip is missing: run oracle/build_ref.sh where /root/reference exists")
+    return ns

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import oracle
-from refmods import load_ref
+from refmods import require_ref
 
 pytestmark = pytest.mark.gpu
 dev = "cuda:0"
@@ -42,7 +42,7 @@ def test_overlap_and_iou_matrices(na, nb, spread, mode):
     ov = torch.zeros((na, nb), device=dev)
     native.boxes_overlap_bev_gpu(ta, tb, ov)
     iou = iou3d_utils.boxes_iou_bev(ta, tb)
-    ref = load_ref("iou3d_cuda")
+    ref = require_ref("iou3d_cuda")
     if ref is not None:
         rov, riou = torch.zeros_like(ov), torch.zeros_like(iou)
         ref.boxes_overlap_bev_gpu(ta, tb, rov)
@@ -84,7 +84,7 @@ def test_rotated_nms_keep_list(n, spread, thresh, mode):
     kbuf = torch.zeros(n, dtype=torch.int64)
     num = native.nms_gpu(sorted_boxes, kbuf, thresh)
     assert torch.equal(order[kbuf[:num].to(dev)], keep)
-    ref = load_ref("iou3d_cuda")
+    ref = require_ref("iou3d_cuda")
     if ref is not None:
         rbuf = torch.zeros(n, dtype=torch.int64)
         rnum = ref.nms_gpu(sorted_boxes, rbuf, thresh)
@@ -111,7 +111,7 @@ def test_normal_nms_keep_list(n, thresh):
     sorted_boxes = tb[order].contiguous()
     exp = oracle.nms_normal(sorted_boxes.cpu().numpy(), thresh)
     np.testing.assert_array_equal(keep.cpu().numpy(), order.cpu().numpy()[exp])   # no trig: bit-exact vs the CPU oracle
-    ref = load_ref("iou3d_cuda")
+    ref = require_ref("iou3d_cuda")
     if ref is not None:
         rbuf = torch.zeros(n, dtype=torch.int64)
         rnum = ref.nms_normal_gpu(sorted_boxes, rbuf, thresh)
@@ -133,3 +133,24 @@ def test_boxes_iou3d_gpu_matches_reference_formula():
     exp3d = ov * oh / np.clip(va + vb - ov * oh, 1e-7, None)
     np.testing.assert_allclose(iou3d.cpu().numpy(), exp3d, rtol=1e-4, atol=1e-5)
     assert iou2d.shape == (300, 200)
+
+
+def test_nms_config4_size_equals_reference_kernels():
+    """BASELINE configs[3] size: 16384 rotated boxes, both thresholds of weaklyRPN.yaml -- keep lists equal to the
+    reference's nms_gpu / nms_normal_gpu, and the all-device variant equal to the reference-signature one."""
+    from ws3d_b200 import native, synth
+    scene = synth.make_scene(0)
+    boxes3d = synth.make_boxes(scene[:, :3], 16384)
+    bev = torch.from_numpy(synth.boxes3d_to_bev(boxes3d)).to(dev)
+    scores = torch.from_numpy(np.random.default_rng(7).random(16384).astype(np.float32)).to(dev)
+    sb = bev[scores.sort(descending=True)[1]].contiguous()
+    ref = require_ref("iou3d_cuda")
+    for th in (0.85, 0.1):
+        for mine, theirs in ((native.nms_gpu, ref.nms_gpu), (native.nms_normal_gpu, ref.nms_normal_gpu)):
+            kb, rb = torch.zeros(16384, dtype=torch.int64), torch.zeros(16384, dtype=torch.int64)
+            num, rnum = mine(sb, kb, th), theirs(sb, rb, th)
+            assert num == rnum and torch.equal(kb[:num], rb[:rnum]), (th, mine.__name__)
+        keep, cnt = native.nms_device(sb, th)
+        kb = torch.zeros(16384, dtype=torch.int64)
+        num = native.nms_gpu(sb, kb, th)
+        assert int(cnt.item()) == num and torch.equal(keep[:num].cpu(), kb[:num])

@@ -215,3 +215,135 @@ def test_fps_modes_are_bit_identical():
         outs.append((idx.clone(), nx.clone()))
     for idx, nx in outs[1:]:
         assert torch.equal(idx, outs[0][0]) and torch.equal(nx, outs[0][1])
+
+
+def test_streamed_runner_at_bench_config_equals_plain_forward():
+    """The HEADLINE configuration of bench.py -- full weaklyRPN.yaml network, 16 clouds x 16384 points, 6 batches in
+    flight (lookahead 5), two feature streams, persistent kernels capped at 100 SMs, TF32 MLPs -- returns exactly the
+    plain forward's tensor for every batch of a stream of 12 batches (two alternating inputs, host and resident)."""
+    from ws3d_b200 import models, native, synth
+    from ws3d_b200.graphs import StreamedBackboneRunner
+    torch.backends.cudnn.allow_tf32 = True           # (the autouse fixture restores the previous value)
+    torch.manual_seed(0)
+    model = models.Pointnet2MSG(input_channels=1).to(dev).eval()
+    _randomize_bn(model, 11)
+    hosts = [torch.from_numpy(synth.make_batch(16, 16384, first_scene=16 * k)).pin_memory() for k in range(2)]
+    with torch.no_grad():
+        want = [model(h.to(dev))[1].clone() for h in hosts]
+    prev = native.set_sm_budget(100)
+    try:
+        runner = StreamedBackboneRunner(model, hosts[0].to(dev), lookahead=5, feature_streams=2)
+        n = 12
+        for j in range(5):
+            runner.submit(hosts[j % 2])
+        runner.fork()
+        bad = []
+        for j in range(n):
+            ok = runner.complete(consume=lambda o, j=j: torch.equal(o, want[j % 2]))
+            if not ok:
+                bad.append(j)
+            if j + 5 < n:
+                runner.submit(hosts[(j + 5) % 2] if j % 3 else hosts[(j + 5) % 2].to(dev))
+        runner.join()
+        torch.cuda.synchronize()
+        assert not bad, f"batches {bad} differ from the plain forward"
+    finally:
+        native.set_sm_budget(prev)
+
+
+def test_full_config_fp32_forward_matches_cpu_oracle_composition():
+    """The full-size network (weaklyRPN.yaml shapes) on one 16384-point cloud, FP32 MLPs, against the CPU composition of
+    oracle ops: sampled coordinates exact, features allclose(2e-4)."""
+    from ws3d_b200 import models, synth
+    torch.manual_seed(0)
+    cpu_model = models.Pointnet2MSG(input_channels=1).eval()
+    _randomize_bn(cpu_model, 2)
+    gpu_model = copy.deepcopy(cpu_model).to(dev).eval()
+    pts = synth.make_batch(1, 16384, first_scene=40)
+    with torch.no_grad():
+        gx, gf = gpu_model(torch.from_numpy(pts).to(dev))
+    cx, cf = cpu_backbone.backbone_forward(cpu_model, pts)
+    np.testing.assert_array_equal(gx.cpu().numpy(), cx)
+    scale = float(np.abs(cf).max())
+    np.testing.assert_allclose(gf.cpu().numpy(), cf, rtol=2e-4, atol=2e-4 * scale)
+
+
+def test_three_nn_weights_equals_torch_formula():
+    """ws3d_three_nn_weights: idx equal to three_nn's, weights equal to the five torch kernels of
+    pointnet2_modules.py:139-144 (every step is one IEEE float32 operation; torch's 3-term sum may associate
+    differently, hence one ulp of slack)."""
+    from ws3d_b200 import pointnet2_utils, synth
+    for n, m in ((16384, 4096), (1024, 256), (256, 64), (300, 2)):
+        pts = torch.from_numpy(synth.make_batch(2, n, first_scene=3)).to(dev)
+        unknown = pts[..., :3].contiguous()
+        known = unknown[:, torch.randperm(n, generator=torch.Generator().manual_seed(n))[:m].to(dev)].contiguous()
+        dist, idx = pointnet2_utils.three_nn(unknown, known)
+        recip = 1.0 / (dist + 1e-8)
+        want = recip / torch.sum(recip, dim=2, keepdim=True)
+        idx2, weight = pointnet2_utils.three_nn_weights(unknown, known)
+        assert torch.equal(idx, idx2)
+        torch.testing.assert_close(weight, want, rtol=3e-7, atol=1e-9)
+        exact = float((weight == want).float().mean())
+        assert exact > 0.5, exact     # the same arithmetic up to the association of the 3-term sum
+
+
+def test_ball_query_writes_every_row_of_uninitialised_output():
+    """Rows of centres without any neighbour are zero-filled by the kernels (the reference relies on the caller's
+    zero fill): every path -- cell grid, shared-memory scan, generic -- on garbage-filled idx buffers."""
+    import oracle
+    from ws3d_b200 import native, synth
+    for n, m in ((16384, 512), (1024, 128), (20000, 64)):
+        pts = synth.make_batch(2, n, first_scene=9)
+        xyz = np.ascontiguousarray(pts[..., :3])
+        new_xyz = xyz[:, :m].copy()
+        new_xyz[:, ::3] += 500.0                       # every third centre is far from every point
+        new_xyz[0, 1] = np.nan
+        tx, tn = torch.from_numpy(xyz).to(dev), torch.from_numpy(new_xyz).to(dev)
+        idx = torch.full((2, m, 16), -7, dtype=torch.int32, device=dev)
+        native.ball_query_wrapper(2, n, m, 0.5, 16, tn, tx, idx)
+        np.testing.assert_array_equal(idx.cpu().numpy(), oracle.ball_query(0.5, 16, xyz, new_xyz))
+        i0 = torch.full((2, m, 16), -7, dtype=torch.int32, device=dev)
+        i1 = torch.full((2, m, 32), -7, dtype=torch.int32, device=dev)
+        native.ball_query2(2, n, m, 0.5, 16, 1.0, 32, tn, tx, i0, i1)
+        np.testing.assert_array_equal(i0.cpu().numpy(), oracle.ball_query(0.5, 16, xyz, new_xyz))
+        np.testing.assert_array_equal(i1.cpu().numpy(), oracle.ball_query(1.0, 32, xyz, new_xyz))
+        assert int((i0[:, ::3] != 0).sum()) == 0
+
+
+def test_rpn_fused_heads_equal_separate_heads():
+    """models.RPN in inference: both heads as one chain of two launches (stacked / block-diagonal weights) against the
+    per-head tensor-core path and the PyTorch modules."""
+    from ws3d_b200 import fused_mlp, models
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(3)
+    rpn = models.RPN().to(dev).eval()
+    _randomize_bn(rpn, 4)
+    feats = torch.randn(2, 128, 4096, device=dev)
+    with torch.no_grad():
+        both = fused_mlp.FoldedHeads([rpn.rpn_cls_layer, rpn.rpn_reg_layer])(feats)
+        cls_sep = rpn._head("rpn_cls_layer", feats)
+        reg_sep = rpn._head("rpn_reg_layer", feats)
+        cls_pt, reg_pt = rpn.rpn_cls_layer(feats), rpn.rpn_reg_layer(feats)
+    torch.testing.assert_close(both[:, :1], cls_sep, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(both[:, 1:], reg_sep, rtol=1e-6, atol=1e-6)
+    assert float((both[:, :1] - cls_pt).abs().max()) < 3e-3 * float(cls_pt.abs().max())
+    assert float((both[:, 1:] - reg_pt).abs().max()) < 3e-3 * max(1e-3, float(reg_pt.abs().max()))
+
+
+def test_scratch_release_frees_retired_buffers():
+    from ws3d_b200 import native, pointnet2_utils, synth
+    torch.cuda.synchronize()
+    native.release_scratch(everything=True)
+    assert native.scratch_bytes() == 0
+    for n in (4096, 16384):      # the second call outgrows the first call's cell-grid scratch
+        xyz = torch.from_numpy(np.ascontiguousarray(synth.make_batch(4, n)[..., :3])).to(dev)
+        pointnet2_utils.ball_query(0.5, 16, xyz, xyz[:, :256].contiguous())
+    assert native.scratch_bytes(retired_only=True) > 0
+    live = native.scratch_bytes() - native.scratch_bytes(retired_only=True)
+    native.release_scratch()
+    assert native.scratch_bytes(retired_only=True) == 0 and native.scratch_bytes() == live
+    native.release_scratch(everything=True)
+    assert native.scratch_bytes() == 0
+    xyz = torch.from_numpy(np.ascontiguousarray(synth.make_batch(1, 4096)[..., :3])).to(dev)
+    pointnet2_utils.ball_query(0.5, 16, xyz, xyz[:, :64].contiguous())       # the library re-allocates on demand
+    torch.cuda.synchronize()

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import oracle
-from refmods import load_ref
+from refmods import require_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -62,7 +62,7 @@ def test_fps_matches_oracle_and_reference(b, n, m, kind):
     idx3, new_xyz = pointnet2_utils.sample_and_gather(x, m)
     np.testing.assert_array_equal(idx3.cpu().numpy(), exp_idx)
     np.testing.assert_array_equal(new_xyz.cpu().numpy(), np.take_along_axis(xyz, exp_idx[..., None].astype(np.int64), 1))
-    ref = load_ref("pointnet2_cuda")
+    ref = require_ref("pointnet2_cuda")
     if ref is not None:
         rtemp = torch.full((b, n), 1e10, device=dev)
         ridx = torch.empty((b, m), dtype=torch.int32, device=dev)
@@ -127,7 +127,7 @@ def test_ball_query_matches_oracle_and_reference(b, n, m, r, k, kind):
     x, q = _t(xyz), _t(new_xyz)
     idx = pointnet2_utils.ball_query(r, k, x, q)
     np.testing.assert_array_equal(idx.cpu().numpy(), exp)
-    ref = load_ref("pointnet2_cuda")
+    ref = require_ref("pointnet2_cuda")
     if ref is not None:
         ridx = torch.zeros((b, m, k), dtype=torch.int32, device=dev)
         ref.ball_query_wrapper(b, n, m, r, k, q, x, ridx)
@@ -179,7 +179,7 @@ def test_ball_query_cell_grid_edge_cases(kind):
     np.testing.assert_array_equal(i1.cpu().numpy(), exp)
     with np.errstate(invalid="ignore", over="ignore"):
         np.testing.assert_array_equal(i0.cpu().numpy(), oracle.ball_query(r * 0.5, 16, xyz, new_xyz))
-    ref = load_ref("pointnet2_cuda")
+    ref = require_ref("pointnet2_cuda")
     if ref is not None:
         ridx = torch.zeros((b, m, k), dtype=torch.int32, device=dev)
         ref.ball_query_wrapper(b, n, m, r, k, q, x, ridx)
@@ -217,7 +217,7 @@ def test_group_and_gather(b, c, n, m, k):
     g1 = rng.normal(size=out1.shape).astype(np.float32)
     out1.backward(_t(g1))
     np.testing.assert_allclose(f2.grad.cpu().numpy(), oracle.gather_operation_grad(g1, idx1, n), rtol=1e-5, atol=1e-5)
-    ref = load_ref("pointnet2_cuda")
+    ref = require_ref("pointnet2_cuda")
     if ref is not None:
         r = torch.empty_like(out)
         ref.group_points_wrapper(b, c, n, m, k, f.detach(), i, r)
@@ -241,7 +241,7 @@ def test_three_nn(b, n, m):
     dist, idx2 = pointnet2_utils.three_nn(u, k)
     np.testing.assert_array_equal(idx2.cpu().numpy(), idx)
     np.testing.assert_allclose(dist.cpu().numpy(), np.sqrt(d2), rtol=1e-6)
-    ref = load_ref("pointnet2_cuda")
+    ref = require_ref("pointnet2_cuda")
     if ref is not None:
         rd2, ridx = torch.empty_like(gd2), torch.empty_like(gidx)
         ref.three_nn_wrapper(b, n, m, u, k, rd2, ridx)
@@ -290,7 +290,7 @@ def test_three_nn_cell_grid_edge_cases(kind):
     native.three_nn_wrapper(b, n, m, u, k, gd2, gidx)
     np.testing.assert_array_equal(gidx.cpu().numpy(), idx)
     np.testing.assert_array_equal(gd2.cpu().numpy(), d2)
-    ref = load_ref("pointnet2_cuda")
+    ref = require_ref("pointnet2_cuda")
     if ref is not None:
         rd2, ridx = torch.empty_like(gd2), torch.empty_like(gidx)
         ref.three_nn_wrapper(b, n, m, u, k, rd2, ridx)
@@ -311,7 +311,7 @@ def test_three_interpolate(b, c, m, n):
     g = rng.normal(size=out.shape).astype(np.float32)
     out.backward(_t(g))
     np.testing.assert_allclose(f.grad.cpu().numpy(), oracle.three_interpolate_grad(g, idx, w, m), rtol=1e-4, atol=1e-5)
-    ref = load_ref("pointnet2_cuda")
+    ref = require_ref("pointnet2_cuda")
     if ref is not None:
         r = torch.empty_like(out)
         ref.three_interpolate_wrapper(b, c, m, n, f.detach(), _t(idx), _t(w), r)

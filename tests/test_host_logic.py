@@ -159,3 +159,50 @@ def test_premultiplied_first_layers_fold_the_same_function_on_cpu():
     pre = torch.einsum("oc,bcm->bom", ff.wa[:ff.c_out, :C], known)
     got_fp = torch.relu(interp(pre) + ff.scale1[None, :, None] * skip + ff.shift[None, :, None])
     assert float((got_fp - want_fp).abs().max()) < 2e-3 * float(want_fp.abs().max())
+
+
+def test_boundary_rejects_wrong_dtypes_and_short_buffers():
+    """the ctypes boundary passes raw pointers, so dtype and size are enforced before the call --
+    int64 indices or float64 / half features raise RuntimeError as the reference's pybind `tensor.data<T>()` does."""
+    import pytest
+    import torch
+
+    from ws3d_b200 import _C
+    f32, i32 = torch.float32, torch.int32
+    ok = torch.zeros(8, dtype=f32)
+    assert _C.require("t", (ok, f32, 8), (None, i32, 4), cuda=False)
+    with pytest.raises(RuntimeError, match="must be torch.int32"):
+        _C.require("t", (torch.zeros(8, dtype=torch.int64), i32, None), cuda=False)
+    with pytest.raises(RuntimeError, match="must be torch.float32"):
+        _C.require("t", (torch.zeros(8, dtype=torch.float64), f32, None), cuda=False)
+    with pytest.raises(RuntimeError, match="must be torch.float32"):
+        _C.require("t", (torch.zeros(8, dtype=torch.float16), f32, None), cuda=False)
+    with pytest.raises(RuntimeError, match="need 9"):
+        _C.require("t", (ok, f32, 9), cuda=False)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        _C.require("t", (torch.zeros(4, 4)[:, 0], f32, None), cuda=False)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        _C.require("t", (ok, f32, None))
+
+
+def test_native_wrappers_validate_before_touching_the_library():
+    """Every wrapper of the reference's function tables raises on an int64 idx / CPU tensor without a launch."""
+    import pytest
+    import torch
+
+    from ws3d_b200 import native
+    x = torch.zeros(1, 16, 3)
+    with pytest.raises(RuntimeError):
+        native.furthest_point_sampling_wrapper(1, 16, 4, x, torch.zeros(1, 16), torch.zeros(1, 4, dtype=torch.int32))   # CPU tensors
+    with pytest.raises(RuntimeError):
+        native.boxes_iou_bev_gpu(torch.zeros(4, 7), torch.zeros(4, 5), torch.zeros(4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        native.nms_gpu(torch.zeros(4, 5), torch.zeros(4, dtype=torch.int64), 0.5)
+
+
+def test_streamed_runner_rejects_more_buffer_sets_than_scratch_arenas():
+    import inspect
+
+    from ws3d_b200 import graphs
+    src = inspect.getsource(graphs.StreamedBackboneRunner.__init__)
+    assert "num_arenas" in src and "raise ValueError" in src
