@@ -23,6 +23,9 @@ dev = "cuda:0"
 quick = "--quick" in sys.argv
 
 
+problems = []
+
+
 def main():
     torch.manual_seed(0)
     # ---- irregular ops at sizes that select each kernel variant
@@ -30,10 +33,15 @@ def main():
         pts = torch.from_numpy(synth.make_batch(2, n)).to(dev)
         xyz = pts[..., :3].contiguous()
         feat = pts[..., 3:].transpose(1, 2).contiguous()
+        ref_idx = None
         for mode in (0, 1, 2):
             prev = native.set_fps_mode(mode)
             idx, new_xyz = pointnet2_utils.sample_and_gather(xyz, m)
             native.set_fps_mode(prev)
+            if ref_idx is None:
+                ref_idx = idx.clone()
+            elif not torch.equal(idx, ref_idx):
+                problems.append(f"FPS mode {mode} differs from mode 0 at n={n} m={m}: {int((idx != ref_idx).sum())} indices")
         i0, i1 = pointnet2_utils.ball_query_pair((0.5, 1.0), (16, 32), xyz, new_xyz)
         g = pointnet2_utils.group_concat(xyz, new_xyz, feat, i1, True)
         nn_idx, w = pointnet2_utils.three_nn_weights(xyz, new_xyz)
@@ -45,6 +53,17 @@ def main():
     batches = [torch.from_numpy(synth.make_batch(2, 4096, first_scene=5 * k)).to(dev) for k in range(4)]
     with torch.no_grad():
         want = [model(b)[1].clone() for b in batches]
+        again = [model(b)[1].clone() for b in batches]
+        prev = native.set_fps_mode(1)
+        plans = [model.coordinate_phase(b) for b in batches]
+        native.set_fps_mode(prev)
+        two_phase = [model.feature_phase(b, p)[1].clone() for b, p in zip(batches, plans)]
+    torch.cuda.synchronize()
+    for k in range(4):
+        if not torch.equal(want[k], again[k]):
+            problems.append(f"plain forward of batch {k} is not reproducible: max diff {float((want[k] - again[k]).abs().max())}")
+        if not torch.equal(want[k], two_phase[k]):
+            problems.append(f"eager two-phase forward of batch {k} differs from the plain forward: {float((want[k] - two_phase[k]).abs().max())}")
     runner = StreamedBackboneRunner(model, batches[0], lookahead=2, feature_streams=2)
     runner.submit(batches[0])
     runner.submit(batches[1])
@@ -55,7 +74,9 @@ def main():
             runner.submit(batches[k + 2])
         runner.join()
         torch.cuda.synchronize()
-        assert torch.equal(got, want[k]), f"streamed batch {k} differs"
+        if not torch.equal(got, want[k]):
+            problems.append(f"streamed batch {k} differs from the plain forward: max diff {float((got - want[k]).abs().max())}, "
+                            f"{int((got != want[k]).sum())} of {got.numel()} values")
     rpn = models.RPN().to(dev).eval()
     with torch.no_grad():
         rpn(torch.from_numpy(synth.make_batch(1, 16384 if not quick else 4096)).to(dev))
@@ -83,6 +104,11 @@ def main():
     _, _, status = data_utils.subsample_points(torch.from_numpy(scene).to(dev), depth, 8192, perm, order, n_near)
     torch.cuda.synchronize()
     assert int(status.item()) == 0
+    if problems:
+        print("sanitize workload: RESULT MISMATCHES under the tool:")
+        for p in problems:
+            print("  -", p)
+        sys.exit(3)
     print("sanitize workload ok")
 
 

@@ -18,6 +18,21 @@
 // against h/2, l/2, w/2, which are exact in float, so float comparisons give identical results.
 // The rotation uses the reference build's FMA shape: x_rot = fma(dx,cos,-rn(dz*sin)),
 // z_rot = fma(dz,cos,rn(dx*sin)).
+//
+// Two-kernel path (clouds of 1024..65536 points, S <= 1024: every WS3D call):
+//   select  -- the points are binned into a uniform cell grid (cell_grid.cuh, shared with ball_query / three_nn); one warp
+//              per box visits only the cells under the box's padded axis-aligned bound (a car-sized box: ~300 candidate
+//              points instead of 16384), applies the reference predicate, orders the hits by original index (the
+//              reference keeps the first S in index order) and writes the S source indices -- wrap-around duplicates
+//              `k % cnt` expanded -- to an L2-resident scratch (B, M, S).  Boxes with more hits than the buffer holds
+//              take the exact early-exit scan in index order (it ends quickly precisely because the box is dense).
+//   write   -- ALL warps stream the (B, M, S, 3+C) tensor: a box's block is S*(3+C) contiguous floats that starts on a
+//              16-byte boundary, so every thread assembles four consecutive floats (crossing row ends where needed) and
+//              issues one 16-byte streaming store; a warp instruction writes 512 contiguous bytes whatever 3+C is.
+// The one-kernel scan below remains for shapes outside that range.
+#include <stdlib.h>
+
+#include "cell_grid.cuh"
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -139,6 +154,223 @@ __global__ void __launch_bounds__(kMaxWarps * 32) roipool3d_kernel(RoiParams prm
   }
 }
 
+// ---- two-kernel path ------------------------------------------------------------------------------
+constexpr int kSelWarps = 8;
+constexpr int kSelCap = 1024;     // buffered hits per warp (4 KB of shared memory each)
+
+struct BoxGeom { float cx, cy, cz, hh, hw, hl, cosa, sina; };
+
+__device__ __forceinline__ BoxGeom box_geom(const float *__restrict__ bx) {
+  BoxGeom g;
+  const float bot = __ldg(bx + 1), h = __ldg(bx + 3), w = __ldg(bx + 4), l = __ldg(bx + 5), ang = __ldg(bx + 6);
+  g.cx = __ldg(bx); g.cz = __ldg(bx + 2);
+  g.cy = (float)((double)bot - (double)h / 2.0);  // roipool3d_kernel.cu:18
+  g.hh = __fmul_rn(h, 0.5f); g.hw = __fmul_rn(w, 0.5f); g.hl = __fmul_rn(l, 0.5f);
+  g.cosa = cosf(ang); g.sina = sinf(ang);
+  return g;
+}
+// pt_in_box3d (roipool3d_kernel.cu:14-28) with the reference build's FMA shape
+__device__ __forceinline__ bool in_box(const BoxGeom &g, float x, float y, float z) {
+  const float dx = __fsub_rn(x, g.cx), dz = __fsub_rn(z, g.cz);
+  const bool pre = !(fabsf(dx) > 10.0f) && !(fabsf(__fsub_rn(y, g.cy)) > g.hh) && !(fabsf(dz) > 10.0f);
+  const float x_rot = __fmaf_rn(dx, g.cosa, -__fmul_rn(dz, g.sina));
+  const float z_rot = __fmaf_rn(dz, g.cosa, __fmul_rn(dx, g.sina));
+  return pre && (x_rot >= -g.hl) && (x_rot <= g.hl) && (z_rot >= -g.hw) && (z_rot <= g.hw);
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32) roipool_select_kernel(int n, int m, int S, const float *__restrict__ xyz,
+                                                                        const float *__restrict__ boxes3d,
+                                                                        const GridHdr *__restrict__ hdrs,
+                                                                        const int *__restrict__ cell_start,
+                                                                        const float4 *__restrict__ sorted,
+                                                                        int *__restrict__ sel_out, int *__restrict__ empty_flag) {
+  __shared__ int s_hits[kSelWarps][kSelCap];
+  __shared__ int s_row_start[kSelWarps][32], s_row_pref[kSelWarps][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t cloud = blockIdx.y;
+  const GridHdr h = hdrs[cloud];
+  const int *cstart = cell_start + cloud * (size_t)(kMaxCells + 1);
+  const float4 *spts = sorted + cloud * (size_t)n;
+  const float *pts = xyz + cloud * (size_t)n * 3;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int *hits = s_hits[warp];
+
+  for (int j = blockIdx.x * kSelWarps + warp; j < m; j += gridDim.x * kSelWarps) {
+    const BoxGeom g = box_geom(boxes3d + (cloud * (size_t)m + j) * 7);
+    int *sel = sel_out + (cloud * (size_t)m + j) * (size_t)S;
+    // Padded axis-aligned bound of the points that can pass the predicate: |dx| <= hl|cos| + hw|sin| (and <= 10),
+    // |dz| <= hl|sin| + hw|cos| (and <= 10), |y - cy| <= hh, each widened against the rounding of the float predicate.
+    // cell_axis is monotone and is what binned the points, so the cell range of the bound covers them exactly.
+    const float ex = fminf(fabsf(g.cosa) * g.hl + fabsf(g.sina) * g.hw, 10.0f) * 1.0001f + 1e-3f;
+    const float ez = fminf(fabsf(g.sina) * g.hl + fabsf(g.cosa) * g.hw, 10.0f) * 1.0001f + 1e-3f;
+    const float ey = g.hh * 1.0001f + 1e-3f;
+    int cnt = 0;
+    bool overflow = false;
+    // a NaN anywhere in the bound: no point can pass the predicate (every comparison with NaN is false)
+    if (ex == ex && ez == ez && ey == ey && g.cx == g.cx && g.cy == g.cy && g.cz == g.cz && h.ncell > 0 && h.inv > 0.f) {
+      const int x0 = cell_axis(g.cx - ex, h.ox, h.inv, h.dx), x1 = cell_axis(g.cx + ex, h.ox, h.inv, h.dx);
+      const int y0 = cell_axis(g.cy - ey, h.oy, h.inv, h.dy), y1 = cell_axis(g.cy + ey, h.oy, h.inv, h.dy);
+      const int z0 = cell_axis(g.cz - ez, h.oz, h.inv, h.dz), z1 = cell_axis(g.cz + ez, h.oz, h.inv, h.dz);
+      const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+      for (int r0 = 0; r0 < nrows && !overflow; r0 += 32) {
+        // up to 32 (y, z) rows of cells at a time: each is one contiguous run of `sorted` (x is the fastest cell axis)
+        const int r = r0 + lane;
+        int start = 0, len = 0;
+        if (r < nrows) {
+          const int rowbase = ((z0 + r / ny) * h.dy + (y0 + r % ny)) * h.dx;
+          start = __ldg(cstart + rowbase + x0);
+          len = __ldg(cstart + rowbase + x1 + 1) - start;
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        __syncwarp();
+        s_row_start[warp][lane] = start;
+        s_row_pref[warp][lane + 1] = incl;
+        if (lane == 0) s_row_pref[warp][0] = 0;
+        __syncwarp();
+        const int total = s_row_pref[warp][32];
+        for (int c0 = 0; c0 < total; c0 += 32) {
+          const int c = c0 + lane;
+          bool in = false;
+          int k = 0;
+          if (c < total) {
+            int lo = 0;                                  // largest row with pref[row] <= c (5-step binary search)
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1)
+              if (s_row_pref[warp][lo + step] <= c) lo += step;
+            const float4 p = __ldg(spts + s_row_start[warp][lo] + (c - s_row_pref[warp][lo]));
+            in = in_box(g, p.x, p.y, p.z);
+            k = __float_as_int(p.w);
+          }
+          const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, in);
+          const int pos = cnt + __popc(ballot & lt_mask);
+          if (in && pos < kSelCap) hits[pos] = k;
+          cnt += __popc(ballot);
+        }
+        if (cnt > kSelCap) overflow = true;
+      }
+    }
+    __syncwarp();
+    if (overflow) {
+      // dense box: exact early-exit scan over the original order (ends after ~S / density points)
+      cnt = 0;
+      for (int base = 0; base < n && cnt < S; base += 32) {
+        const int k = base + lane;
+        bool in = false;
+        if (k < n) in = in_box(g, __ldg(pts + (size_t)k * 3), __ldg(pts + (size_t)k * 3 + 1), __ldg(pts + (size_t)k * 3 + 2));
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, in);
+        const int pos = cnt + __popc(ballot & lt_mask);
+        if (in && pos < S) sel[pos] = k;
+        cnt += __popc(ballot);
+      }
+      __syncwarp();
+      const int have = min(cnt, S);
+      for (int k = have + lane; k < S; k += 32) sel[k] = sel[k % have];   // (have >= 1: the box overflowed the buffer)
+    } else if (cnt > 0) {
+      // rank of every hit among the hits = its slot in index order; the first S are the reference's selection
+      const int have = min(cnt, S);
+      for (int h0 = 0; h0 < cnt; h0 += 32) {
+        const int hh = h0 + lane;
+        const int mine = hh < cnt ? hits[hh] : 0x7FFFFFFF;
+        int rank = 0;
+        for (int t = 0; t < cnt; ++t) rank += (hits[t] < mine) ? 1 : 0;
+        if (hh < cnt && rank < S) sel[rank] = mine;
+      }
+      __syncwarp();
+      for (int k = have + lane; k < S; k += 32) sel[k] = sel[k % have];   // wrap-around duplicates (roipool3d_kernel.cu:150-158)
+    }
+    if (lane == 0 && cnt == 0) {
+      empty_flag[cloud * (size_t)m + j] = 1;   // roipool3d_kernel.cu:146-148; non-empty boxes leave the caller's fill alone
+      sel[0] = -1;                             // tells the write kernel to skip the box (its rows keep the caller's zeros)
+    }
+    __syncwarp();
+  }
+}
+
+// One CTA per (box, cloud): the box's S*(3+C) output floats as float4 stores.
+constexpr int kWrThreads = 256;
+template <bool kVec>
+__global__ void __launch_bounds__(kWrThreads) roipool_write_kernel(int n, int m, int c, int S, const float *__restrict__ xyz,
+                                                                    const float *__restrict__ feat,
+                                                                    const int *__restrict__ sel_in,
+                                                                    float *__restrict__ pooled) {
+  const size_t cloud = blockIdx.y;
+  const int j = blockIdx.x;
+  const int row_len = 3 + c;
+  const int *sel = sel_in + (cloud * (size_t)m + j) * (size_t)S;
+  if (__ldg(sel) < 0) return;                           // empty box: its rows keep the caller's zero fill (roipool3d_kernel.cu:146-148)
+  const float *pts = xyz + cloud * (size_t)n * 3;
+  const float *fts = feat + cloud * (size_t)n * c;
+  float *dst = pooled + (cloud * (size_t)m + j) * (size_t)S * row_len;
+  const int total = S * row_len;
+  if (kVec) {
+    // element e = 4 * v: row k = e / row_len, column t = e % row_len, advanced incrementally (no division in the loop)
+    const int stride = 4 * kWrThreads;
+    const int dk = stride / row_len, dt = stride - dk * row_len;
+    int e = 4 * (int)threadIdx.x;
+    int k = e / row_len, t = e - k * row_len;
+    for (; e < total; e += stride) {
+      float v[4];
+      int kk = k, tt = t;
+      int src = __ldg(sel + kk);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] = tt < 3 ? __ldg(pts + (size_t)src * 3 + tt) : __ldg(fts + (size_t)src * c + (tt - 3));
+        if (++tt == row_len) { tt = 0; ++kk; if (q < 3 && kk < S) src = __ldg(sel + kk); }
+      }
+      __stcs(reinterpret_cast<float4 *>(dst + e), make_float4(v[0], v[1], v[2], v[3]));
+      k += dk; t += dt;
+      if (t >= row_len) { t -= row_len; ++k; }
+    }
+  } else {
+    for (int e = threadIdx.x; e < total; e += kWrThreads) {
+      const int k = e / row_len, t = e - k * row_len;
+      const int src = __ldg(sel + k);
+      __stcs(dst + e, t < 3 ? __ldg(pts + (size_t)src * 3 + t) : __ldg(fts + (size_t)src * c + (t - 3)));
+    }
+  }
+}
+
+bool roipool_grid_applicable(int batch, int n, int m, int s) {
+  static const int enabled = []() { const char *e = getenv("WS3D_ROIPOOL_GRID"); return (e && *e) ? atoi(e) : 1; }();
+  return enabled && n >= 1024 && n <= 65536 && s >= 1 && s <= kSelCap && m >= 1 && m <= 0x7FFFFFFF / kWrThreads && batch <= 65535;
+}
+
+int roipool_grid(int batch, int n, int m, int c, int s, const float *xyz, const float *boxes3d, const float *feat, float *pooled,
+                 int *flag, cudaStream_t stream) {
+  const size_t hdr_bytes = ((size_t)batch * sizeof(GridHdr) + 255) & ~(size_t)255;
+  const size_t start_bytes = ((size_t)batch * (kMaxCells + 1) * sizeof(int) + 255) & ~(size_t)255;
+  const size_t sorted_bytes = ((size_t)batch * n * sizeof(float4) + 255) & ~(size_t)255;
+  const size_t sel_bytes = (size_t)batch * m * s * sizeof(int);
+  char *ws = (char *)scratch(hdr_bytes + start_bytes + sorted_bytes + sel_bytes, 1);
+  if (!ws) return (int)cudaErrorMemoryAllocation;
+  GridHdr *hdrs = (GridHdr *)ws;
+  int *cell_start = (int *)(ws + hdr_bytes);
+  float4 *sorted = (float4 *)(ws + hdr_bytes + start_bytes);
+  int *sel = (int *)(ws + hdr_bytes + start_bytes + sorted_bytes);
+  cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxCells * (int)sizeof(int));
+  if (e != cudaSuccess) { set_error("roipool3d grid: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  grid_build_kernel<<<batch, 1024, kMaxCells * sizeof(int), stream>>>(n, 0.f, kMaxCells, xyz, hdrs, cell_start, sorted);
+  int rc = check_launch("roipool3d (grid build)");
+  if (rc) return rc;
+  int gx = ceil_div(m, kSelWarps);
+  const int cap = ceil_div(8 * num_sms(), batch);
+  if (gx > cap) gx = cap;
+  roipool_select_kernel<<<dim3((unsigned)gx, (unsigned)batch), kSelWarps * 32, 0, stream>>>(n, m, s, xyz, boxes3d, hdrs, cell_start,
+                                                                                          sorted, sel, flag);
+  rc = check_launch("roipool3d (select)");
+  if (rc) return rc;
+  const bool vec = ((size_t)s * (3 + c)) % 4 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 15u) == 0;
+  const dim3 grid((unsigned)m, (unsigned)batch);
+  if (vec) roipool_write_kernel<true><<<grid, kWrThreads, 0, stream>>>(n, m, c, s, xyz, feat, sel, pooled);
+  else roipool_write_kernel<false><<<grid, kWrThreads, 0, stream>>>(n, m, c, s, xyz, feat, sel, pooled);
+  return check_launch("roipool3d (write)");
+}
+
 int roipool_dispatch(int batch, int n, int m, int c, int s, const float *xyz, const float *boxes3d, const float *feat,
                      float *pooled, int *flag, cudaStream_t stream) {
   const char *what = "roipool3d";
@@ -146,6 +378,7 @@ int roipool_dispatch(int batch, int n, int m, int c, int s, const float *xyz, co
   if (batch == 0 || m == 0) return 0;
   if (!boxes3d || !flag || (n > 0 && !xyz) || (s > 0 && !pooled) || (n > 0 && c > 0 && !feat)) return fail_arg(what);
   if (batch > 65535) return fail_arg(what);
+  if (roipool_grid_applicable(batch, n, m, s)) return roipool_grid(batch, n, m, c, s, xyz, boxes3d, feat, pooled, flag, stream);
   RoiParams prm;
   prm.n = n; prm.m = m; prm.c = c; prm.s = s;
   prm.xyz = xyz; prm.boxes3d = boxes3d; prm.feat = feat; prm.pooled = pooled; prm.empty_flag = flag;
