@@ -204,6 +204,39 @@ int ws3d_mlp_layer_into(int b, int c_out, int c_out_pad, int c1, int c2, int col
                         const float *shift, const float *x1, const float *x2, float *out, int out_ctot,
                         int out_coff, int relu, int pool, ws3d_stream_t stream);
 
+/* ---- training-mode shared MLP (BASELINE config 3) -------------------
+ * conv1x1 -> BatchNorm(batch statistics) -> ReLU [-> max-pool over nsample], forward and backward, replacing the cuDNN
+ * conv / BN / ReLU / max-pool kernels and their autograd mirrors behind pytorch_utils.py:5-32 and
+ * pointnet2_modules.py:40-44 in training.  All activations are (B, C, cols) channel-major float32; cols % 4 == 0. */
+
+/* Forward GEMM with statistics: y (B,c_out,cols) = W [x1 ; x2] (weights laid out as for ws3d_mlp_layer, zero_shift = c_out_pad
+ * zeros) on the tcgen05 tensor cores, and stats[0..c_out) += sum_y, stats[c_out..2c_out) += sum_y^2 (double, caller zeroes). */
+int ws3d_mlp_layer_stats(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *zero_shift,
+                         const float *x1, const float *x2, float *y, double *stats, ws3d_stream_t stream);
+/* Batch statistics -> per-channel affine: scale = gamma * invstd, shift = beta - mean * scale (gamma / beta may be NULL = 1 / 0);
+ * running_mean / running_var (may be NULL) updated as torch.nn.BatchNorm does (momentum, unbiased variance). count = B * cols. */
+int ws3d_bn_finalize(int c, double count, const double *stats, const float *gamma, const float *beta, float eps, float momentum,
+                     float *running_mean, float *running_var, float *scale, float *shift, float *mean, float *invstd,
+                     ws3d_stream_t stream);
+/* z = act(y * scale[c] + shift[c]); flags: 1 ReLU, 2 round z to TF32.  pool > 0 (power of two in [4,128] dividing cols):
+ * z is (B,c,cols/pool) = max over every run of `pool` columns and arg (B,c,cols/pool) uint8 its first arg-max. */
+int ws3d_bn_relu_apply(int b, int c, int cols, int pool, const float *y, const float *scale, const float *shift, int flags,
+                       float *z, unsigned char *arg, ws3d_stream_t stream);
+/* Backward reductions: sums[0..c) += sum dA, sums[c..2c) += sum dA * xhat (double, caller zeroes), dA = dz where the
+ * activation passed, xhat = (y - mean) * invstd; dz is (B,c,cols) or, with pool > 0, (B,c,cols/pool) routed through arg. */
+int ws3d_bn_relu_bwd_reduce(int b, int c, int cols, int pool, const float *y, const float *dz, const unsigned char *arg,
+                            const float *scale, const float *shift, const float *mean, const float *invstd, int flags,
+                            double *sums, ws3d_stream_t stream);
+/* dy (B,c,cols) = scale * (dA - sums[c] / count - xhat * sums[C + c] / count), rounded to TF32; count <= 0: dy = scale * dA
+ * (a layer without batch norm).  dgamma = sums[c..2c), dbeta = sums[0..c). */
+int ws3d_bn_relu_bwd_apply(int b, int c, int cols, int pool, const float *y, const float *dz, const unsigned char *arg,
+                           const float *scale, const float *shift, const float *mean, const float *invstd, int flags,
+                           const double *sums, double count, float *dy, ws3d_stream_t stream);
+/* Weight gradient on the tensor cores: dw (c_out x c_in, row stride ldw floats) += sum_b dy[b] (c_out x cols) x[b]^T; TF32
+ * operands, FP32 accumulation, split over the contraction axis with FP32 atomics (caller zeroes dw). */
+int ws3d_mlp_wgrad(int b, int c_out, int c_in, int cols, const float *dy, const float *x, float *dw, int ldw,
+                   ws3d_stream_t stream);
+
 /* Extension: the `_break_up_pc` step of lib/net/pointnet2_msg.py:52-60 in one launch:
  * pc (B,N,3+C) -> xyz (B,N,3) and features (B,C,N) (channel-major; NULL when C == 0). */
 int ws3d_split_pointcloud(int b, int n, int c, const float *pc, float *xyz, float *features,

@@ -1,0 +1,230 @@
+"""Training-mode shared MLP on this library's kernels (csrc/train_mlp.cu, ws3d_b200/train_mlp.py) against PyTorch:
+the elementwise / reduction kernels against torch formulas and autograd in FP32, the tensor-core GEMMs against float64
+products of the TF32-truncated operands, whole layers and the whole RPN training step against the PyTorch modules."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda:0"
+
+
+def _tf32(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)      # what the tensor core reads
+
+
+@pytest.mark.parametrize("B,C,cols,pool", [(3, 37, 512, 0), (2, 16, 4096, 16), (2, 130, 2048, 32), (1, 5, 256, 4), (2, 8, 1024, 128),
+                                           (1, 3, 100, 0)])
+def test_bn_relu_apply_matches_torch(B, C, cols, pool):
+    from ws3d_b200 import native
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    y = torch.randn(B, C, cols, generator=g).to(dev)
+    scale = (torch.rand(C, generator=g) + 0.5).to(dev)
+    shift = (torch.randn(C, generator=g) * 0.3).to(dev)
+    for relu in (1, 0):
+        want = y * scale[None, :, None] + shift[None, :, None]
+        if relu:
+            want = want.clamp_min(0)
+        if pool:
+            z = torch.empty(B, C, cols // pool, device=dev)
+            arg = torch.empty(B, C, cols // pool, dtype=torch.uint8, device=dev)
+            native.bn_relu_apply(B, C, cols, pool, y, scale, shift, relu, z, arg)
+            wv, wi = want.view(B, C, cols // pool, pool).max(dim=3)
+            torch.testing.assert_close(z, wv, rtol=1e-6, atol=1e-6)
+            # the arg-max selects the maximum, and it is the first one wherever the maximum is not tied to rounding
+            got_v = want.view(B, C, cols // pool, pool).gather(3, arg.long().unsqueeze(-1)).squeeze(-1)
+            torch.testing.assert_close(got_v, wv, rtol=1e-6, atol=1e-6)
+            first = (want.view(B, C, cols // pool, pool) == wv.unsqueeze(-1)).float().argmax(dim=3)
+            assert float((first == arg.long()).float().mean()) > 0.999
+            if relu:   # all-zero groups (every pre-activation negative): the first column, like F.max_pool2d
+                allzero = wv == 0
+                assert bool((arg[allzero] == 0).all())
+        else:
+            z = torch.empty_like(y)
+            native.bn_relu_apply(B, C, cols, 0, y, scale, shift, relu, z, None)
+            torch.testing.assert_close(z, want, rtol=1e-6, atol=1e-6)
+            native.bn_relu_apply(B, C, cols, 0, y, scale, shift, relu | 2, z, None)
+            assert bool(((z.view(torch.int32) & 0x1FFF) == 0).all())                  # rounded to TF32
+            torch.testing.assert_close(z, want, rtol=6e-4, atol=1e-6)
+
+
+def test_mlp_layer_stats_gemm_and_statistics():
+    from ws3d_b200 import native
+    g = torch.Generator().manual_seed(5)
+    for B, c_out, c1, c2, cols in ((2, 64, 99, 0, 2048), (3, 196, 128, 0, 1000), (2, 128, 256, 1, 4096), (1, 16, 4, 0, 512)):
+        c_out_pad, k1, k2 = -(-c_out // 128) * 128, -(-c1 // 32) * 32, (-(-c2 // 32) * 32 if c2 else 0)
+        w = torch.randn(c_out, c1 + c2, generator=g) * 0.2
+        wp = torch.zeros(c_out_pad, k1 + k2)
+        wp[:c_out, :c1] = w[:, :c1]
+        if c2:
+            wp[:c_out, k1:k1 + c2] = w[:, c1:]
+        x1 = torch.randn(B, c1, cols, generator=g).to(dev)
+        x2 = torch.randn(B, c2, cols, generator=g).to(dev) if c2 else None
+        y = torch.empty(B, c_out, cols, device=dev)
+        stats = torch.zeros(2 * c_out, dtype=torch.float64, device=dev)
+        native.mlp_layer_stats(B, c_out, c_out_pad, c1, c2, cols, wp.to(dev), torch.zeros(c_out_pad, device=dev), x1, x2, y, stats)
+        x = x1 if x2 is None else torch.cat([x1, x2], dim=1)
+        want = torch.einsum("oc,bce->boe", _tf32(w.to(dev)).double(), _tf32(x).double())
+        assert float((y.double() - want).abs().max()) < 1e-4 * float(want.abs().max())
+        torch.testing.assert_close(stats[:c_out], y.double().sum(dim=(0, 2)), rtol=1e-6, atol=1e-3)
+        torch.testing.assert_close(stats[c_out:], (y.double() ** 2).sum(dim=(0, 2)), rtol=1e-6, atol=1e-3)
+
+
+def test_bn_finalize_matches_torch_batch_norm_bookkeeping():
+    from ws3d_b200 import native
+    g = torch.Generator().manual_seed(2)
+    B, C, cols = 3, 21, 640
+    y = (torch.randn(B, C, cols, generator=g) * 2 + 0.5).to(dev)
+    bn = torch.nn.BatchNorm1d(C).to(dev).train()
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.2)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    want = bn(y)
+    stats = torch.cat([y.double().sum(dim=(0, 2)), (y.double() ** 2).sum(dim=(0, 2))])
+    scale, shift, mean, invstd = (torch.empty(C, device=dev) for _ in range(4))
+    native.bn_finalize(C, B * cols, stats, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, rm, rv, scale, shift, mean, invstd)
+    torch.testing.assert_close(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv, bn.running_var, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(y * scale[None, :, None] + shift[None, :, None], want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,cols,pool,has_bn", [(3, 37, 512, 0, True), (2, 16, 2048, 16, True), (2, 70, 1024, 32, True), (2, 9, 256, 0, False),
+                                                  (1, 6, 512, 64, True)])
+def test_bn_relu_backward_kernels_match_autograd(B, C, cols, pool, has_bn):
+    from ws3d_b200 import native
+    g = torch.Generator().manual_seed(C)
+    y = torch.randn(B, C, cols, generator=g).to(dev).requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(dev).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.3).to(dev).requires_grad_(True)
+    if has_bn:
+        a = F.batch_norm(y, None, None, gamma, beta, training=True, eps=1e-5)
+    else:
+        a = y + beta[None, :, None]
+    z = F.relu(a)
+    if pool:
+        z = z.view(B, C, cols // pool, pool).max(dim=3)[0]
+    dz = torch.randn(z.shape, generator=g).to(dev)
+    (z * dz).sum().backward()
+    with torch.no_grad():
+        yd = y.detach()
+        if has_bn:
+            mean = yd.mean(dim=(0, 2))
+            invstd = 1.0 / torch.sqrt(yd.var(dim=(0, 2), unbiased=False) + 1e-5)
+            scale = gamma.detach() * invstd
+            shift = beta.detach() - mean * scale
+        else:
+            mean, invstd, scale, shift = torch.zeros(C, device=dev), torch.ones(C, device=dev), torch.ones(C, device=dev), beta.detach().clone()
+        arg = None
+        if pool:
+            zz = torch.empty(B, C, cols // pool, device=dev)
+            arg = torch.empty(B, C, cols // pool, dtype=torch.uint8, device=dev)
+            native.bn_relu_apply(B, C, cols, pool, yd, scale, shift, 1, zz, arg)
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        native.bn_relu_bwd_reduce(B, C, cols, pool, yd, dz, arg, scale, shift, mean, invstd, 1, sums)
+        dy = torch.empty_like(yd)
+        native.bn_relu_bwd_apply(B, C, cols, pool, yd, dz, arg, scale, shift, mean, invstd, 1, sums, B * cols if has_bn else 0, dy)
+    ref = y.grad
+    assert float((dy - ref).abs().max()) < 1e-3 * max(1e-3, float(ref.abs().max())), float((dy - ref).abs().max())   # dy is TF32-rounded
+    torch.testing.assert_close(sums[:C].float(), beta.grad, rtol=1e-4, atol=1e-4)
+    if has_bn:
+        torch.testing.assert_close(sums[C:].float(), gamma.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,c_out,c_in,cols", [(2, 64, 99, 2048), (3, 196, 128, 1000), (1, 1, 128, 16384), (2, 16, 4, 4096), (2, 512, 515, 512),
+                                               (16, 128, 96, 100)])
+def test_mlp_wgrad_matches_float64_product(B, c_out, c_in, cols):
+    from ws3d_b200 import native
+    g = torch.Generator().manual_seed(c_out + c_in)
+    dy = _tf32(torch.randn(B, c_out, cols, generator=g).to(dev))
+    x = torch.randn(B, c_in, cols, generator=g).to(dev)
+    ld = c_in + 5
+    dw = torch.zeros(c_out, ld, device=dev)
+    native.mlp_wgrad(B, c_out, c_in, cols, dy, x, dw, ld, 3)
+    want = torch.einsum("boe,bce->oc", dy.double(), _tf32(x).double())
+    scale = float(want.abs().max())
+    assert float((dw[:, 3:3 + c_in].double() - want).abs().max()) < 2e-4 * scale
+    assert float(dw[:, :3].abs().max()) == 0 and float(dw[:, 3 + c_in:].abs().max()) == 0       # nothing outside the block
+    native.mlp_wgrad(B, c_out, c_in, cols, dy, x, dw, ld, 3)                                      # accumulates
+    assert float((dw[:, 3:3 + c_in].double() - 2 * want).abs().max()) < 4e-4 * scale
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(1e-6, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("spec,cols,pool,two_inputs", [([99, 64, 96, 128], 1024 * 32, 32, False), ([4, 16, 16, 32], 4096 * 16, 16, False),
+                                                       ([257, 128, 128], 16384, 0, True), ([768, 512, 512], 1024, 0, True)])
+def test_shared_mlp_train_matches_pytorch_modules(spec, cols, pool, two_inputs):
+    """Forward, running statistics and every gradient of a SharedMLP in training mode: this library's layer kernels
+    against the PyTorch modules (cuDNN TF32 convolutions, native BatchNorm / ReLU / max-pool, autograd)."""
+    import copy
+
+    from ws3d_b200 import pytorch_utils as pt_utils
+    from ws3d_b200 import train_mlp
+    torch.manual_seed(7)
+    B = 2
+    mine = pt_utils.SharedMLP(list(spec), bn=True).to(dev).train()
+    for m in mine.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    ref = copy.deepcopy(mine)
+    c2 = 1 if spec[0] == 257 else (256 if two_inputs else 0)
+    c1 = spec[0] - c2
+    x1 = torch.randn(B, c1, cols, device=dev)
+    x2 = torch.randn(B, c2, cols, device=dev) if c2 else None
+    a1, a2 = x1.clone().requires_grad_(True), (x2.clone().requires_grad_(True) if c2 else None)
+    b1, b2 = x1.clone().requires_grad_(True), (x2.clone().requires_grad_(True) if c2 else None)
+    assert train_mlp.enabled_for(mine, a1, pool)
+    out = train_mlp.shared_mlp_train(mine, a1, a2, pool=pool)
+    xin = b1 if b2 is None else torch.cat([b1, b2], dim=1)
+    K = pool if pool else 1
+    y = ref(xin.view(B, spec[0], cols // K, K))
+    want = F.max_pool2d(y, kernel_size=[1, K]).squeeze(-1) if pool else y.view(B, spec[-1], cols)
+    assert _rel(out, want) < 2e-2, _rel(out, want)
+    gout = torch.randn_like(want)
+    (out * gout).sum().backward()
+    (want * gout).sum().backward()
+    assert _rel(a1.grad, b1.grad) < 4e-2, ("dx1", _rel(a1.grad, b1.grad))
+    if c2:
+        assert _rel(a2.grad, b2.grad) < 4e-2, ("dx2", _rel(a2.grad, b2.grad))
+    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert _rel(p.grad, q.grad) < 4e-2, (n, _rel(p.grad, q.grad))
+    for (n, p), (_, q) in zip(mine.named_buffers(), ref.named_buffers()):
+        torch.testing.assert_close(p.float(), q.float(), rtol=2e-3, atol=2e-3, msg=n)
+
+
+def test_rpn_training_step_on_own_kernels_matches_pytorch_path():
+    """The whole Stage-1 training forward / backward (labels on the GPU, get_rpn_loss) with WS3D_TRAIN_MLP=1 against the
+    same step on the PyTorch MLPs: loss and gradients agree to TF32 tolerance; every parameter receives a gradient."""
+    import copy
+
+    from ws3d_b200 import label_utils, models, synth, train_functions
+    torch.manual_seed(0)
+    net = models.RPN().to(dev).train()
+    ref = copy.deepcopy(net)
+    pts = torch.from_numpy(synth.make_batch(2, 16384)).to(dev)
+    gt, cnt = synth.make_gt_boxes(2)
+    cls_label, reg_label = label_utils.generate_gaussian_training_labels(pts[..., :3].contiguous(), torch.from_numpy(gt).to(dev),
+                                                                         torch.from_numpy(cnt).to(dev))
+    losses = []
+    for model, flag in ((net, "1"), (ref, "0")):
+        os.environ["WS3D_TRAIN_MLP"] = flag
+        try:
+            torch.manual_seed(3)           # dropout masks
+            out = model({"pts_input": pts})
+            loss, _ = train_functions.get_rpn_loss(out["rpn_cls"], out["rpn_reg"], cls_label, reg_label)
+            loss.backward()
+            losses.append(float(loss))
+        finally:
+            os.environ.pop("WS3D_TRAIN_MLP", None)
+    assert abs(losses[0] - losses[1]) < 2e-2 * abs(losses[1]), losses
+    worst = 0.0
+    for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        if float(q.grad.abs().max()) > 1e-6:
+            worst = max(worst, _rel(p.grad, q.grad))
+    assert worst < 0.15, worst       # 32 chained TF32 layers with batch statistics, atomics in the irregular gradients

@@ -44,6 +44,12 @@ _SIGNATURES = {
     "ws3d_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_mlp_layer": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "ws3d_mlp_layer_into": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "ws3d_mlp_layer_stats": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ws3d_bn_finalize": [_i, ctypes.c_double, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ws3d_bn_relu_apply": [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "ws3d_bn_relu_bwd_reduce": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
+    "ws3d_bn_relu_bwd_apply": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, ctypes.c_double, _vp, _vp],
+    "ws3d_mlp_wgrad": [_i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "ws3d_split_pointcloud": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_sa_mlp_fused_supported": [_i, _i, _i, _i, _i],
     "ws3d_sa_mlp_fused": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
@@ -132,7 +138,7 @@ def require_cuda(*tensors, what: str = "ws3d_b200"):
     return True
 
 
-F32, I32, I64, U8 = torch.float32, torch.int32, torch.int64, torch.uint8
+F32, F64, I32, I64, U8 = torch.float32, torch.float64, torch.int32, torch.int64, torch.uint8
 
 
 def require(what: str, *specs, cuda: bool = True):

@@ -42,6 +42,7 @@ struct MlpParams {
   const float *shift;  // (c_out_padded)
   float *out;
   int out_ctot, out_coff;   // out is (B, out_ctot, cols or cols / pool); this layer writes channels [out_coff, out_coff + c_out)
+  double *stats;            // training: [sum(c_out) | sum of squares(c_out)] of the RAW accumulator, added per tile; or null
   int n_col_tiles, n_m_tiles, n_tiles;   // tile = (cloud, 128-channel block, NT-column block), column block fastest
 };
 
@@ -274,9 +275,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
       float *stage = reinterpret_cast<float *>(s_raw + (stage_base - smem_u32(s_raw)) + kStages * kStageBytes) + quarter * (32 * 36);
       const int co_base = m0 + ((quarter * 32) & (rows_per_copy - 1));
       const int srow = lane >> 3, scol = (lane & 7) * 4;
+      float st_sum = 0.f, st_sq = 0.f;
       for (int c = cbeg; c < cend && col0 + c < prm.cols; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(trow + (uint32_t)c, r);
+        if (prm.stats) {   // columns beyond the row are zero-filled by TMA: they add nothing
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float a = __uint_as_float(r[t]);
+            st_sum += a;
+            st_sq = fmaf(a, a, st_sq);
+          }
+        }
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
           float v = __uint_as_float(r[t]) + shift;
@@ -298,6 +308,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
           }
         }
         __syncwarp();
+      }
+      if (prm.stats && live) {
+        atomicAdd(prm.stats + co, (double)st_sum);
+        atomicAdd(prm.stats + prm.c_out + co, (double)st_sq);
       }
     } else if (warp_live) {
       const int ns = prm.pool;                  // power of two dividing the warp's column share
@@ -365,10 +379,11 @@ using namespace ws3d;
 // out: (B, c_out, cols) or, when pool > 0, (B, c_out, cols / pool) with the max over each run of `pool` columns.
 // out_ctot / out_coff: the layer writes channels [out_coff, out_coff + c_out) of an (B, out_ctot, .) tensor (the slot of one
 //    scale in the concatenated multi-scale output of pointnet2_modules.py:55: no torch.cat pass).
-WS3D_API int ws3d_mlp_layer_into(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *shift,
-                                 const float *x1, const float *x2, float *out, int out_ctot, int out_coff, int relu, int pool,
-                                 ws3d_stream_t stream) {
+static int mlp_layer_impl(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *shift,
+                          const float *x1, const float *x2, float *out, int out_ctot, int out_coff, int relu, int pool,
+                          double *stats, ws3d_stream_t stream) {
   const char *what = "mlp_layer";
+  if (stats && pool != 0) return fail_arg("mlp_layer (statistics are taken on unpooled layers)");
   if (out_coff < 0 || out_coff + c_out > out_ctot) return fail_arg("mlp_layer (output channel slot)");
   if (b < 0 || c_out <= 0 || c1 <= 0 || c2 < 0 || cols < 0 || c_out_pad % kTileM || c_out_pad < c_out) return fail_arg(what);
   if (b == 0 || cols == 0) return 0;
@@ -392,6 +407,7 @@ WS3D_API int ws3d_mlp_layer_into(int b, int c_out, int c_out_pad, int c1, int c2
   MlpParams prm;
   prm.c_out = c_out; prm.cols = cols; prm.pool = pool; prm.flags = relu; prm.shift = shift; prm.out = out;
   prm.out_ctot = out_ctot; prm.out_coff = out_coff;
+  prm.stats = stats;
   prm.nk1 = ceil_div(c1, kChunkK);
   prm.nk2 = c2 > 0 ? ceil_div(c2, kChunkK) : 0;
   prm.n_m_tiles = c_out_pad / kTileM;
@@ -442,7 +458,21 @@ WS3D_API int ws3d_mlp_layer_into(int b, int c_out, int c_out_pad, int c1, int c2
   return check_launch(what);
 }
 
+WS3D_API int ws3d_mlp_layer_into(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *shift,
+                                 const float *x1, const float *x2, float *out, int out_ctot, int out_coff, int relu, int pool,
+                                 ws3d_stream_t stream) {
+  return mlp_layer_impl(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, out_ctot, out_coff, relu, pool, nullptr, stream);
+}
+
 WS3D_API int ws3d_mlp_layer(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *shift,
                             const float *x1, const float *x2, float *out, int relu, int pool, ws3d_stream_t stream) {
-  return ws3d_mlp_layer_into(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, c_out, 0, relu, pool, stream);
+  return mlp_layer_impl(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, c_out, 0, relu, pool, nullptr, stream);
+}
+
+// Training forward: y (B, c_out, cols) = W [x1 ; x2] (raw accumulator: no shift, no activation) and the per-channel
+// sum / sum of squares of y added into stats (2 * c_out doubles, zeroed by the caller) from the epilogue.
+WS3D_API int ws3d_mlp_layer_stats(int b, int c_out, int c_out_pad, int c1, int c2, int cols, const float *w, const float *zero_shift,
+                                  const float *x1, const float *x2, float *y, double *stats, ws3d_stream_t stream) {
+  if (!stats) return fail_arg("mlp_layer_stats (null pointer)");
+  return mlp_layer_impl(b, c_out, c_out_pad, c1, c2, cols, w, zero_shift, x1, x2, y, c_out, 0, 0, 0, stats, stream);
 }

@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import fused_mlp
 from . import pointnet2_utils
+from . import train_mlp
 from . import pytorch_utils as pt_utils
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
 
@@ -210,6 +211,8 @@ class RPN(nn.Module):
             if name not in cache:
                 cache[name] = fused_mlp.FoldedMLP(nn.Sequential(*[m for m in seq if not isinstance(m, nn.Dropout)]))
             return cache[name](x)
+        if x.dim() == 3 and train_mlp.enabled_for(seq, x):
+            return train_mlp.shared_mlp_train(seq, x.contiguous())     # training: this library's layer kernels + torch's dropout
         return seq(x)
 
     def forward(self, input_data, first_samples: Optional[torch.Tensor] = None, plan: Optional[dict] = None):

@@ -10,7 +10,7 @@ the reference module names so the reference's Python wrappers run on top unmodif
 import torch
 
 from . import _C
-from ._C import F32, I32, I64, U8, check, device_of, lib, ptr, require, stream
+from ._C import F32, F64, I32, I64, U8, check, device_of, lib, ptr, require, stream
 
 
 # ---- pointnet2_cuda ---------------------------------------------------------------------------
@@ -142,6 +142,58 @@ def mlp_layer(b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, po
     with device_of(out):
         check(lib().ws3d_mlp_layer_into(b, c_out, c_out_pad, c1, c2, cols, ptr(w), ptr(shift), ptr(x1), ptr(x2), ptr(out),
                                         ctot, int(out_coff), int(relu), int(pool), stream()), "mlp_layer")
+
+
+# ---- training-mode shared MLP (see include/ws3d_ops.h) -------------------------------------------------
+def mlp_layer_stats(b, c_out, c_out_pad, c1, c2, cols, w, zero_shift, x1, x2, y, stats):
+    require("mlp_layer_stats", (w, F32, c_out_pad * (c1 + c2)), (zero_shift, F32, c_out_pad), (x1, F32, b * c1 * cols),
+            (x2, F32, b * c2 * cols), (y, F32, b * c_out * cols), (stats, F64, 2 * c_out))
+    with device_of(y):
+        check(lib().ws3d_mlp_layer_stats(b, c_out, c_out_pad, c1, c2, cols, ptr(w), ptr(zero_shift), ptr(x1), ptr(x2), ptr(y), ptr(stats),
+                                         stream()), "mlp_layer_stats")
+
+
+def bn_finalize(c, count, stats, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd):
+    require("bn_finalize", (stats, F64, 2 * c), (gamma, F32, c), (beta, F32, c), (running_mean, F32, c), (running_var, F32, c),
+            (scale, F32, c), (shift, F32, c), (mean, F32, c), (invstd, F32, c))
+    with device_of(stats):
+        check(lib().ws3d_bn_finalize(c, float(count), ptr(stats), ptr(gamma), ptr(beta), float(eps), float(momentum), ptr(running_mean),
+                                     ptr(running_var), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), stream()), "bn_finalize")
+
+
+def bn_relu_apply(b, c, cols, pool, y, scale, shift, flags, z, arg):
+    require("bn_relu_apply", (y, F32, b * c * cols), (scale, F32, c), (shift, F32, c), (z, F32, b * c * (cols // pool if pool else cols)),
+            (arg, U8, b * c * (cols // pool) if pool else None))
+    with device_of(y):
+        check(lib().ws3d_bn_relu_apply(b, c, cols, pool, ptr(y), ptr(scale), ptr(shift), int(flags), ptr(z), ptr(arg), stream()),
+              "bn_relu_apply")
+
+
+def bn_relu_bwd_reduce(b, c, cols, pool, y, dz, arg, scale, shift, mean, invstd, flags, sums):
+    require("bn_relu_bwd_reduce", (y, F32, b * c * cols), (dz, F32, b * c * (cols // pool if pool else cols)),
+            (arg, U8, b * c * (cols // pool) if pool else None), (scale, F32, c), (shift, F32, c), (mean, F32, c), (invstd, F32, c),
+            (sums, F64, 2 * c))
+    with device_of(y):
+        check(lib().ws3d_bn_relu_bwd_reduce(b, c, cols, pool, ptr(y), ptr(dz), ptr(arg), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                                            int(flags), ptr(sums), stream()), "bn_relu_bwd_reduce")
+
+
+def bn_relu_bwd_apply(b, c, cols, pool, y, dz, arg, scale, shift, mean, invstd, flags, sums, count, dy):
+    require("bn_relu_bwd_apply", (y, F32, b * c * cols), (dz, F32, b * c * (cols // pool if pool else cols)),
+            (arg, U8, b * c * (cols // pool) if pool else None), (scale, F32, c), (shift, F32, c), (mean, F32, c), (invstd, F32, c),
+            (sums, F64, 2 * c), (dy, F32, b * c * cols))
+    with device_of(y):
+        check(lib().ws3d_bn_relu_bwd_apply(b, c, cols, pool, ptr(y), ptr(dz), ptr(arg), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                                           int(flags), ptr(sums), float(count), ptr(dy), stream()), "bn_relu_bwd_apply")
+
+
+def mlp_wgrad(b, c_out, c_in, cols, dy, x, dw, ldw, dw_offset=0):
+    """dw[:, dw_offset : dw_offset + c_in] += sum_b dy[b] x[b]^T for a (c_out, ldw) row-major dw."""
+    require("mlp_wgrad", (dy, F32, b * c_out * cols), (x, F32, b * c_in * cols), (dw, F32, (c_out - 1) * ldw + dw_offset + c_in))
+    from ctypes import c_void_p
+    with device_of(dy):
+        check(lib().ws3d_mlp_wgrad(b, c_out, c_in, cols, ptr(dy), ptr(x), c_void_p(dw.data_ptr() + 4 * int(dw_offset)), int(ldw), stream()),
+              "mlp_wgrad")
 
 
 def split_pointcloud(pc, xyz, features):

@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from . import fused_mlp
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
+from . import train_mlp
 
 
 def _train_channels_last(x: torch.Tensor) -> bool:
@@ -112,13 +113,17 @@ class _PointnetSAModuleBase(nn.Module):
                 out = torch.empty((xyz.shape[0], sum(widths), new_xyz.shape[1]), dtype=torch.float32, device=xyz.device)
                 streams = self._scale_side_streams(xyz) if os.environ.get("WS3D_SCALE_STREAMS", "1") != "0" else None
                 main = torch.cuda.current_stream(xyz.device)
+                for k, mlp in enumerate(self.mlps):
+                    # folded weights are built (small kernels on the CURRENT stream) BEFORE the fork event is recorded: a
+                    # side stream that waits for the fork then also waits for its weights.  (Found by compute-sanitizer:
+                    # building them after the fork left the first call of a scale on a side stream unordered against it.)
+                    if k not in cache:
+                        cache[k] = fused_mlp.FusedSAScale(mlp)
                 if streams:
                     fork = torch.cuda.Event()
                     fork.record(main)
                 off, joins = 0, []
                 for k, (mlp, idx) in enumerate(zip(self.mlps, indices)):
-                    if k not in cache:
-                        cache[k] = fused_mlp.FusedSAScale(mlp)
                     if streams and k > 0:
                         st = streams[k - 1]
                         st.wait_event(fork)
@@ -174,8 +179,13 @@ class _PointnetSAModuleBase(nn.Module):
             if fused and fused_mlp.supported(M * K, K):   # GroupAll
                 pooled.append(self._folded(k)(grouped.view(B, C, M * K), pool=K))
                 continue
+            if self.pool_method == 'max_pool' and grouped.dim() == 4 and train_mlp.enabled_for(mlp, grouped, K):
+                # training: every layer (GEMM + batch-statistics BatchNorm + ReLU, the last one with the max-pool) and its
+                # backward on this library's kernels, on the channel-major tensor the grouping kernel has just written
+                pooled.append(train_mlp.shared_mlp_train(mlp, grouped.view(B, C, M * K), pool=K))
+                continue
             if _train_channels_last(grouped):
-                # training: NHWC activations -- the 1x1 convolutions become plain GEMMs and BatchNorm reduces over the
+                # training on the PyTorch path (WS3D_TRAIN_MLP=0): NHWC activations -- the 1x1 convolutions become plain GEMMs and BatchNorm reduces over the
                 # contiguous channel vectors instead of cuDNN's one-thread-block-per-channel NCHW kernels
                 grouped = grouped.contiguous(memory_format=torch.channels_last)
             grouped = mlp(grouped)
@@ -272,6 +282,9 @@ class PointnetFPModule(nn.Module):
                 folded = self.__dict__["_folded_mlp"] = fused_mlp.FoldedMLP(self.mlp, first_split=split)
             skip = None if unknow_feats is None else unknow_feats.contiguous()
             return folded(interpolated, skip)
+        if interpolated.dim() == 3 and train_mlp.enabled_for(self.mlp, interpolated):
+            # training: the skip features are the second input of the first layer (no torch.cat), see train_mlp
+            return train_mlp.shared_mlp_train(self.mlp, interpolated.contiguous(), unknow_feats)
         new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
         new_features = new_features.unsqueeze(-1)
         if _train_channels_last(new_features):
