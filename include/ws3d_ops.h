@@ -261,6 +261,17 @@ int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float 
                       int c3, const float *w1, const float *shift1, const float *w2,
                       const float *shift2, const float *w3, const float *shift3, float *out,
                       int out_ctot, int out_coff, ws3d_stream_t stream);
+/* Same, gathering the grouped points from POINT-MAJOR rows (B, n, ld) = [x, y, z, features[0..c_feat), zeros] (ld % 4 == 0,
+ * 16-byte aligned; e.g. the (B,N,4) input cloud itself for the first level): one contiguous row per grouped point instead
+ * of 3 + c_feat scattered 4-byte reads of a channel-major tensor.  out_pm (B, m, ld_pm) or NULL: this scale's pooled
+ * channels also written in that layout at columns [3 + out_coff, 3 + out_coff + c3) for the next level; the scale called
+ * with pm_xyz != 0 also writes the centre coordinates (columns 0..2) and zeroes columns [3 + out_ctot, ld_pm).
+ * Results are bit-identical to ws3d_sa_mlp_fused on the equivalent channel-major inputs. */
+int ws3d_sa_mlp_fused_rows(int b, int n, int m, int nsample, int c_feat, const float *rows, int ld,
+                           const float *new_xyz, const int *idx, int c1, int c2, int c3, const float *w1,
+                           const float *shift1, const float *w2, const float *shift2, const float *w3,
+                           const float *shift3, float *out, int out_ctot, int out_coff, float *out_pm, int ld_pm,
+                           int pm_xyz, ws3d_stream_t stream);
 
 /* ---- iou3d_cuda ------------------------------------------------------------ */
 

@@ -347,3 +347,43 @@ def test_scratch_release_frees_retired_buffers():
     xyz = torch.from_numpy(np.ascontiguousarray(synth.make_batch(1, 4096)[..., :3])).to(dev)
     pointnet2_utils.ball_query(0.5, 16, xyz, xyz[:, :64].contiguous())       # the library re-allocates on demand
     torch.cuda.synchronize()
+
+
+def test_fused_sa_point_major_rows_path_is_bit_identical():
+    """The fused SA kernels gathering from point-major rows (the (B,N,4) cloud itself at level 1, the previous level's
+    point-major output at level 2) give exactly the channel-major gather's result, and the emitted rows are
+    [centre xyz | pooled channels of both scales | zeros]."""
+    import os
+
+    from ws3d_b200 import models, synth
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(0)
+    model = models.Pointnet2MSG(input_channels=1).to(dev).eval()
+    _randomize_bn(model, 6)
+    pts = torch.from_numpy(synth.make_batch(3, 16384, first_scene=21)).to(dev)
+    with torch.no_grad():
+        os.environ["WS3D_SA_ROWS"] = "0"
+        try:
+            want = model(pts)[1].clone()
+        finally:
+            os.environ.pop("WS3D_SA_ROWS", None)
+        got = model(pts)[1]
+        assert torch.equal(got, want)
+        xyz, feat = model._break_up_pc(pts)
+        sa1 = model.SA_modules[0]
+        nx, nf, rows = sa1(xyz, feat, rows=pts, want_rows=True)
+        assert rows is not None and rows.shape == (3, 4096, 104)
+        assert torch.equal(rows[..., :3], nx)
+        assert torch.equal(rows[..., 3:99], nf.transpose(1, 2))
+        assert float(rows[..., 99:].abs().max()) == 0.0
+        nx2, nf2 = model.SA_modules[1](nx, nf, rows=rows)
+        nx2b, nf2b = model.SA_modules[1](nx, nf)
+        assert torch.equal(nx2, nx2b) and torch.equal(nf2, nf2b)
+        # a ragged shape: centres per cloud not a multiple of the tile, cloud rows wider than the operand
+        pts5 = torch.cat([pts[:, :5000], torch.zeros(3, 5000, 4, device=dev)], dim=2).contiguous()      # (3, 5000, 8): ld = 8 > 3 + 1
+        sa = models.Pointnet2MSG(input_channels=1).SA_modules[0].to(dev).eval()
+        sa.npoint = 1000
+        x5, f5 = pts5[..., :3].contiguous(), pts5[..., 3:4].transpose(1, 2).contiguous()
+        a = sa(x5, f5)
+        b = sa(x5, f5, rows=pts5, want_rows=True)
+        assert torch.equal(a[1], b[1]) and torch.equal(b[2][..., 3:99], b[1].transpose(1, 2))

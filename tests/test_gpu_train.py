@@ -152,7 +152,15 @@ def test_mlp_wgrad_matches_float64_product(B, c_out, c_in, cols):
 
 
 def _rel(a, b):
-    return float((a - b).abs().max()) / max(1e-6, float(b.abs().max()))
+    return float((a.detach() - b.detach()).abs().max()) / max(1e-6, float(b.detach().abs().max()))
+
+
+def _rel_l2(a, b):
+    """Relative Frobenius error.  Gradients are compared in this norm: a ReLU mask or a max-pool arg-max that flips on a
+    near-tie (TF32 rounding differs between the two implementations) moves single elements by O(1) of a term, which a
+    max-norm comparison would report although both results are correct gradients of their own forward pass."""
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm()) / max(1e-12, float(b.norm()))
 
 
 @pytest.mark.parametrize("spec,cols,pool,two_inputs", [([99, 64, 96, 128], 1024 * 32, 32, False), ([4, 16, 16, 32], 4096 * 16, 16, False),
@@ -188,11 +196,11 @@ def test_shared_mlp_train_matches_pytorch_modules(spec, cols, pool, two_inputs):
     gout = torch.randn_like(want)
     (out * gout).sum().backward()
     (want * gout).sum().backward()
-    assert _rel(a1.grad, b1.grad) < 4e-2, ("dx1", _rel(a1.grad, b1.grad))
+    assert _rel_l2(a1.grad, b1.grad) < 3e-2, ("dx1", _rel_l2(a1.grad, b1.grad))
     if c2:
-        assert _rel(a2.grad, b2.grad) < 4e-2, ("dx2", _rel(a2.grad, b2.grad))
+        assert _rel_l2(a2.grad, b2.grad) < 3e-2, ("dx2", _rel_l2(a2.grad, b2.grad))
     for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
-        assert _rel(p.grad, q.grad) < 4e-2, (n, _rel(p.grad, q.grad))
+        assert _rel_l2(p.grad, q.grad) < 3e-2, (n, _rel_l2(p.grad, q.grad))
     for (n, p), (_, q) in zip(mine.named_buffers(), ref.named_buffers()):
         torch.testing.assert_close(p.float(), q.float(), rtol=2e-3, atol=2e-3, msg=n)
 
@@ -226,5 +234,5 @@ def test_rpn_training_step_on_own_kernels_matches_pytorch_path():
     for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
         if float(q.grad.abs().max()) > 1e-6:
-            worst = max(worst, _rel(p.grad, q.grad))
+            worst = max(worst, _rel_l2(p.grad, q.grad))
     assert worst < 0.15, worst       # 32 chained TF32 layers with batch statistics, atomics in the irregular gradients

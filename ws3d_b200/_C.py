@@ -53,6 +53,7 @@ _SIGNATURES = {
     "ws3d_split_pointcloud": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_sa_mlp_fused_supported": [_i, _i, _i, _i, _i],
     "ws3d_sa_mlp_fused": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "ws3d_sa_mlp_fused_rows": [_i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp],
     "ws3d_boxes_overlap_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "ws3d_boxes_iou_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "ws3d_nms_workspace_bytes": [_i],

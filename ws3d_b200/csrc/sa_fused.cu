@@ -46,6 +46,15 @@ struct SaFusedParams {
   const float *shift1, *shift2, *shift3;   // padded to n1 / n2 / n3
   float *out;
   int out_ctot, out_coff;        // out is (B, out_ctot, m); this scale writes channels [out_coff, out_coff + c3)
+  // Point-major operand rows (optional): rows (B, n, ld) = [x, y, z, features..., zero padding], ld % 4 == 0, so that a
+  // thread gathers its grouped point with ld / 4 16-byte loads of ONE contiguous row instead of 3 + c_feat 4-byte loads
+  // that each touch their own 32-byte sector of a channel-major tensor (at SA2 the channel-major gather moves 1.7 GB
+  // of sectors through L2 for 0.2 GB of data).  out_pm (B, m, ld_pm) receives this scale's pooled channels in the same
+  // layout for the NEXT level; the scale with pm_xyz set also writes the centre coordinates and the zero padding.
+  const float *rows;
+  int ld;
+  float *out_pm;
+  int ld_pm, pm_xyz;
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
@@ -215,7 +224,39 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
     if (tile + (int)gridDim.x < prm.n_tiles) p_next = load_idx(tile + (int)gridDim.x);
     // ---- gather: [xyz[idx] - centre ; features[:, idx]] along this thread's TMEM lane.  Rows beyond the cloud
     // (last tile only) recompute point 0 against centre 0: finite values that never reach an output.
-    {
+    if (prm.rows) {
+      // point-major source: the whole operand row is one contiguous run of ld floats
+      const int j = valid ? flat >> lg_ns : 0;
+      const float4 *rp = reinterpret_cast<const float4 *>(prm.rows + ((size_t)cloud * n + p) * prm.ld);
+      const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
+      const float cx = __ldg(pc), cy = __ldg(pc + 1), cz = __ldg(pc + 2);
+      for (int c0 = 0; c0 < prm.k0; c0 += kBatch) {
+        uint32_t v[kBatch];
+#pragma unroll
+        for (int t = 0; t < kBatch; t += 4) {
+          if (c0 + t < prm.ld) {                      // CTA-uniform; columns beyond the row are zero (k0 may exceed ld)
+            const float4 q = __ldg(rp + ((c0 + t) >> 2));
+            v[t] = __float_as_uint(q.x); v[t + 1] = __float_as_uint(q.y); v[t + 2] = __float_as_uint(q.z); v[t + 3] = __float_as_uint(q.w);
+          } else {
+            v[t] = v[t + 1] = v[t + 2] = v[t + 3] = 0u;
+          }
+        }
+        if (c0 == 0) {
+          v[0] = round_tf32(__fsub_rn(__uint_as_float(v[0]), cx));
+          v[1] = round_tf32(__fsub_rn(__uint_as_float(v[1]), cy));
+          v[2] = round_tf32(__fsub_rn(__uint_as_float(v[2]), cz));
+        }
+#pragma unroll
+        for (int g = 0; g < kBatch / 8; ++g) {
+          if (c0 + g * 8 < prm.k0) {                  // CTA-uniform
+            uint32_t q[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) q[t] = v[g * 8 + t];
+            tmem_st8(lane_addr + (uint32_t)(prm.tm_a0 + c0 + g * 8), q);
+          }
+        }
+      }
+    } else {
       const int j = valid ? flat >> lg_ns : 0;
       const float *px = prm.xyz + ((size_t)cloud * n + p) * 3;
       const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
@@ -345,6 +386,25 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
       // the accumulator has been read: the next tile's gather may overwrite TMEM
       __syncthreads();
       const int centre0 = t_in * cpt;
+      if (prm.out_pm) {
+        // the same pooled values once more, point-major, for the next level's gather (channels fastest: coalesced)
+        float *base = prm.out_pm + ((size_t)cloud * prm.m + centre0) * prm.ld_pm;
+        for (int i = row; i < cpt * prm.c3; i += kThreads) {
+          const int k = i / prm.c3, c = i - k * prm.c3;
+          if (centre0 + k < prm.m) base[(size_t)k * prm.ld_pm + 3 + prm.out_coff + c] = __uint_as_float(s_pool[c * cpt + k]);
+        }
+        if (prm.pm_xyz) {   // this scale also writes the centre coordinates and the zero padding behind the channels
+          const int tail0 = 3 + prm.out_ctot, per = 3 + (prm.ld_pm - tail0);
+          for (int i = row; i < cpt * per; i += kThreads) {
+            const int k = i / per, q = i - k * per;
+            if (centre0 + k < prm.m) {
+              if (q < 3) base[(size_t)k * prm.ld_pm + q] = __ldg(prm.new_xyz + ((size_t)cloud * prm.m + centre0 + k) * 3 + q);
+              else base[(size_t)k * prm.ld_pm + tail0 + (q - 3)] = 0.f;
+            }
+          }
+        }
+        if (ns > 32) __syncthreads();   // the loop below clears s_pool rows other threads have just read
+      }
       for (int c = row; c < prm.c3; c += kThreads) {
         float *dst = prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + c) * prm.m + centre0;
         unsigned int *src = s_pool + c * cpt;
@@ -457,16 +517,22 @@ WS3D_API int ws3d_sa_mlp_fused_supported(int c_feat, int nsample, int c1, int c2
 //   w1 (n1 x 32*ceil(k0/32)), w2 (n2 x 32*ceil(n1/32)), w3 (n3 x 32*ceil(n2/32)): BN-folded, zero padded, TF32-rounded,
 //     row-major; k0 = roundup(3 + c_feat, 8), n_l = roundup(c_l, 16); w1's columns are [dx,dy,dz, features...];
 //   shift_l (n_l) zero padded;  out (B, out_ctot, m): channels [out_coff, out_coff + c3) are written.
-WS3D_API int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
-                               const float *features, const int *idx, int c1, int c2, int c3, const float *w1,
-                               const float *shift1, const float *w2, const float *shift2, const float *w3,
-                               const float *shift3, float *out, int out_ctot, int out_coff, ws3d_stream_t stream) {
+static int sa_mlp_fused_impl(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
+                             const float *features, const int *idx, int c1, int c2, int c3, const float *w1,
+                             const float *shift1, const float *w2, const float *shift2, const float *w3,
+                             const float *shift3, float *out, int out_ctot, int out_coff, const float *rows, int ld,
+                             float *out_pm, int ld_pm, int pm_xyz, ws3d_stream_t stream) {
   const char *what = "sa_mlp_fused";
   if (b < 0 || n <= 0 || m < 0 || out_coff < 0 || out_coff + c3 > out_ctot) return fail_arg(what);
   if (!ws3d_sa_mlp_fused_supported(c_feat, nsample, c1, c2, c3)) return fail_arg("sa_mlp_fused (unsupported shape)");
   if (b == 0 || m == 0) return 0;
-  if (!xyz || !new_xyz || !idx || !w1 || !w2 || !w3 || !shift1 || !shift2 || !shift3 || !out || (c_feat > 0 && !features))
+  if (!new_xyz || !idx || !w1 || !w2 || !w3 || !shift1 || !shift2 || !shift3 || !out) return fail_arg(what);
+  if (rows) {
+    if (ld < 3 + c_feat || ld % 4 || (reinterpret_cast<uintptr_t>(rows) & 15u)) return fail_arg("sa_mlp_fused (rows: ld % 4, ld >= 3 + c_feat, 16-byte aligned)");
+  } else if (!xyz || (c_feat > 0 && !features)) {
     return fail_arg(what);
+  }
+  if (out_pm && (ld_pm < 3 + out_ctot || ld_pm % 4)) return fail_arg("sa_mlp_fused (out_pm: ld_pm % 4, ld_pm >= 3 + out_ctot)");
   const Plan pl = make_plan(c_feat, nsample, c1, c2, c3);
   SaFusedParams prm;
   prm.n = n; prm.m = m; prm.ns = nsample; prm.c_feat = c_feat;
@@ -481,6 +547,7 @@ WS3D_API int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, con
   prm.xyz = xyz; prm.new_xyz = new_xyz; prm.feat = c_feat > 0 ? features : nullptr; prm.idx = idx;
   prm.shift1 = shift1; prm.shift2 = shift2; prm.shift3 = shift3;
   prm.out = out; prm.out_ctot = out_ctot; prm.out_coff = out_coff;
+  prm.rows = rows; prm.ld = ld; prm.out_pm = out_pm; prm.ld_pm = ld_pm; prm.pm_xyz = pm_xyz;
   CUtensorMap m1, m2, m3;
   if (!weight_map(&m1, w1, pl.n1, pl.nk1 * 32) || !weight_map(&m2, w2, pl.n2, pl.nk2 * 32) ||
       !weight_map(&m3, w3, pl.n3, pl.nk3 * 32))
@@ -493,4 +560,23 @@ WS3D_API int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, con
   const int ctas = (int)(tiles < (long long)pc ? tiles : (long long)pc);
   kern<<<ctas, kThreads, pl.smem, to_stream(stream)>>>(m1, m2, m3, prm);
   return check_launch(what);
+}
+
+WS3D_API int ws3d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
+                               const float *features, const int *idx, int c1, int c2, int c3, const float *w1,
+                               const float *shift1, const float *w2, const float *shift2, const float *w3,
+                               const float *shift3, float *out, int out_ctot, int out_coff, ws3d_stream_t stream) {
+  return sa_mlp_fused_impl(b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, c1, c2, c3, w1, shift1, w2, shift2, w3, shift3, out,
+                           out_ctot, out_coff, nullptr, 0, nullptr, 0, 0, stream);
+}
+
+// Same with the grouped points gathered from point-major rows (B, n, ld) = [x, y, z, features..., zeros] (see SaFusedParams)
+// and, optionally, this scale's pooled channels also written point-major into out_pm (B, m, ld_pm) for the next level.
+WS3D_API int ws3d_sa_mlp_fused_rows(int b, int n, int m, int nsample, int c_feat, const float *rows, int ld, const float *new_xyz,
+                                    const int *idx, int c1, int c2, int c3, const float *w1, const float *shift1, const float *w2,
+                                    const float *shift2, const float *w3, const float *shift3, float *out, int out_ctot, int out_coff,
+                                    float *out_pm, int ld_pm, int pm_xyz, ws3d_stream_t stream) {
+  if (!rows) return fail_arg("sa_mlp_fused_rows (null pointer)");
+  return sa_mlp_fused_impl(b, n, m, nsample, c_feat, nullptr, new_xyz, nullptr, idx, c1, c2, c3, w1, shift1, w2, shift2, w3, shift3, out,
+                           out_ctot, out_coff, rows, ld, out_pm, ld_pm, pm_xyz, stream);
 }

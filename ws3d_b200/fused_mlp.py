@@ -250,13 +250,19 @@ class FusedSAScale:
             k_in = n_pad
         self._versions = self._stamp()
 
-    def __call__(self, xyz, new_xyz, features, idx, out, c_off):
-        """xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or None, idx (B,M,K) int32; writes out[:, c_off:c_off+c3, :]."""
+    def __call__(self, xyz, new_xyz, features, idx, out, c_off, rows=None, out_pm=None, pm_xyz=False):
+        """xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or None, idx (B,M,K) int32; writes out[:, c_off:c_off+c3, :].
+        `rows` (B,N,ld) = [xyz | features | zeros] point-major: gather from it instead (same result, 16-byte loads);
+        `out_pm` (B,M,ld_pm): the pooled channels also land there point-major (the next level's `rows`)."""
         if self._versions != self._stamp():
             self._build()
         B, N, _ = xyz.shape
         M, K = idx.shape[1], idx.shape[2]
         c_feat = 0 if features is None else features.shape[1]
+        if rows is not None:
+            native.sa_mlp_fused_rows(B, N, M, K, c_feat, rows, new_xyz, idx, self.widths, self.w, self.shift, out, out.shape[1], c_off,
+                                     out_pm, pm_xyz)
+            return
         native.sa_mlp_fused(B, N, M, K, c_feat, xyz, new_xyz, features, idx, self.widths, self.w, self.shift, out,
                             out.shape[1], c_off)
 

@@ -75,6 +75,30 @@ class Pointnet2MSG(nn.Module):
         features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
         return xyz, features
 
+    def _sa_level(self, k: int, pointcloud: torch.Tensor, rows, xyz, feats, new_xyz=None, indices=None):
+        """Set-abstraction level k -> (new_xyz, new_features, rows_out).  `rows` are the point-major operand rows
+        [xyz | features | zeros] the fused kernels gather from in inference: level 0 reads the (B,N,3+C) input cloud itself
+        when its rows are 16-byte multiples, and a level emits its output in that layout (rows_out) when the next level
+        runs fused too (pointnet2_modules.fused_scales_eligible); None wherever that does not apply."""
+        sa = self.SA_modules[k]
+        want = False
+        if fused_mlp.enabled_for(sa) and pointcloud.is_cuda:
+            if k == 0:
+                ok = (pointcloud.is_contiguous() and pointcloud.dtype == torch.float32 and pointcloud.shape[-1] % 4 == 0
+                      and sa.fused_scales_eligible(pointcloud.shape[-1] - 3))
+                rows = pointcloud if ok else None
+            if rows is not None and k + 1 < len(self.SA_modules):
+                want = self.SA_modules[k + 1].fused_scales_eligible(sum(m[-1].conv.out_channels for m in sa.mlps))
+        else:
+            rows = None
+        if rows is None:
+            nx, nf = sa(xyz, feats, new_xyz=new_xyz, indices=indices)
+            return nx, nf, None
+        if want:
+            return sa(xyz, feats, new_xyz=new_xyz, indices=indices, rows=rows, want_rows=True)
+        nx, nf = sa(xyz, feats, new_xyz=new_xyz, indices=indices, rows=rows)
+        return nx, nf, None
+
     def sample_first_level(self, pointcloud: torch.Tensor) -> torch.Tensor:
         """Level-1 sampling alone: (B,N,3+C) -> new_xyz (B, npoint_1, 3).  It depends on coordinates only and is the
         head of every dependency chain of the forward pass, so a caller that knows the NEXT batch can compute it
@@ -105,14 +129,15 @@ class Pointnet2MSG(nn.Module):
         else:
             xyz, features = self._break_up_pc(pointcloud)
         l_xyz, l_features = [xyz] + list(plan["xyz"]), [features]
-        for k, sa in enumerate(self.SA_modules):
-            _, nf = sa(l_xyz[k], l_features[k], new_xyz=l_xyz[k + 1], indices=plan["idx"][k])
+        rows = None
+        for k in range(len(self.SA_modules)):
+            _, nf, rows = self._sa_level(k, pointcloud, rows, l_xyz[k], l_features[k], new_xyz=l_xyz[k + 1], indices=plan["idx"][k])
             l_features.append(nf)
         for i in range(len(self.FP_modules) - 1, -1, -1):
             l_features[i] = self.FP_modules[i](l_xyz[i], l_xyz[i + 1], l_features[i], l_features[i + 1], nn=plan["nn"][i])
         return l_xyz[0], l_features[0]
 
-    def _forward_two_streams(self, xyz, features, first_samples=None):
+    def _forward_two_streams(self, pointcloud, xyz, features, first_samples=None):
         """Same computation as forward(), scheduled on two CUDA streams.
 
         Sampling (FPS) and the interpolation stencils (three_nn + weights) depend on coordinates only, and FPS is a
@@ -148,10 +173,10 @@ class Pointnet2MSG(nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(side)
                 stencil_done[i] = ev
-        l_features = [features]
-        for i, sa in enumerate(self.SA_modules):
+        l_features, rows = [features], None
+        for i in range(len(self.SA_modules)):
             main.wait_event(fps_done[i])
-            _, nf = sa(l_xyz[i], l_features[i], new_xyz=l_xyz[i + 1])
+            _, nf, rows = self._sa_level(i, pointcloud, rows, l_xyz[i], l_features[i], new_xyz=l_xyz[i + 1])
             l_features.append(nf)
         for i in range(len(self.FP_modules) - 1, -1, -1):
             main.wait_event(stencil_done[i])
@@ -165,10 +190,10 @@ class Pointnet2MSG(nn.Module):
         xyz, features = self._break_up_pc(pointcloud)
         if (xyz.is_cuda and os.environ.get("WS3D_TWO_STREAMS", "1") != "0" and len(self.FP_modules) == len(self.SA_modules)
                 and all(sa.npoint is not None for sa in self.SA_modules)):
-            return self._forward_two_streams(xyz, features, first_samples)
-        l_xyz, l_features = [xyz], [features]
-        for k, sa in enumerate(self.SA_modules):
-            nx, nf = sa(l_xyz[-1], l_features[-1], new_xyz=first_samples if k == 0 else None)
+            return self._forward_two_streams(pointcloud, xyz, features, first_samples)
+        l_xyz, l_features, rows = [xyz], [features], None
+        for k in range(len(self.SA_modules)):
+            nx, nf, rows = self._sa_level(k, pointcloud, rows, l_xyz[-1], l_features[-1], new_xyz=first_samples if k == 0 else None)
             l_xyz.append(nx)
             l_features.append(nf)
         for i in range(-1, -(len(self.FP_modules) + 1), -1):

@@ -408,6 +408,19 @@ def sa_mlp_fused(b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, 
                                       ptr(w[2]), ptr(shift[2]), ptr(out), out_ctot, out_coff, stream()), "sa_mlp_fused")
 
 
+def sa_mlp_fused_rows(b, n, m, nsample, c_feat, rows, new_xyz, idx, widths, w, shift, out, out_ctot, out_coff, out_pm=None, pm_xyz=False):
+    """Extension: ws3d_sa_mlp_fused gathering from point-major rows (B, n, ld) = [x, y, z, features, zeros]; optionally the
+    pooled channels also written point-major into out_pm (B, m, ld_pm) for the next level (include/ws3d_ops.h)."""
+    ld = rows.shape[-1]
+    ld_pm = 0 if out_pm is None else out_pm.shape[-1]
+    require("sa_mlp_fused_rows", (rows, F32, b * n * ld), (new_xyz, F32, b * m * 3), (idx, I32, b * m * nsample), (out, F32, b * out_ctot * m),
+            (out_pm, F32, b * m * ld_pm), *[(t, F32, None) for t in list(w) + list(shift)])
+    with device_of(rows):
+        check(lib().ws3d_sa_mlp_fused_rows(b, n, m, nsample, c_feat, ptr(rows), ld, ptr(new_xyz), ptr(idx), widths[0], widths[1], widths[2],
+                                           ptr(w[0]), ptr(shift[0]), ptr(w[1]), ptr(shift[1]), ptr(w[2]), ptr(shift[2]), ptr(out), out_ctot,
+                                           out_coff, ptr(out_pm), ld_pm, int(bool(pm_xyz)), stream()), "sa_mlp_fused_rows")
+
+
 def group_affine(b, n, m, c, nsample, P, xyz, new_xyz, wx, shift, idx, flags, out):
     """Extension: out[b,c,j,s] = act(P[b,c,i] + wx[c] . (xyz[b,i] - new_xyz[b,j]) + shift[c]), i = idx[b,j,s]; flags: 1 ReLU, 2 TF32."""
     require("group_affine", (P, F32, b * c * n), (xyz, F32, b * n * 3), (new_xyz, F32, b * m * 3), (wx, F32, c * 3), (shift, F32, c),

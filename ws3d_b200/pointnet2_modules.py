@@ -86,11 +86,20 @@ class _PointnetSAModuleBase(nn.Module):
             out[k] = pointnet2_utils.ball_query(specs[k][0], specs[k][1], xyz, new_xyz)
         return out
 
+    def fused_scales_eligible(self, c_feat: int) -> bool:
+        """True when every scale of this layer runs as one fused kernel in inference (grouping + MLP + max-pool)."""
+        return (self.npoint is not None and self.pool_method == 'max_pool' and os.environ.get("WS3D_SA_FUSED", "1") != "0"
+                and all(getattr(g, "use_xyz", False) for g in self.groupers)
+                and all(fused_mlp.FusedSAScale.eligible(mlp, c_feat, g.nsample) for g, mlp in zip(self.groupers, self.mlps)))
+
     def forward(self, xyz: torch.Tensor, features: Optional[torch.Tensor] = None,
-                new_xyz: Optional[torch.Tensor] = None, indices=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                new_xyz: Optional[torch.Tensor] = None, indices=None, rows: Optional[torch.Tensor] = None,
+                want_rows: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B, sum_k mlps[k][-1], npoint).
         `new_xyz` / `indices` (one ball-query result per scale): the coordinate-only part of the layer if the caller
-        has already computed it (models.Pointnet2MSG.coordinate_phase)."""
+        has already computed it (models.Pointnet2MSG.coordinate_phase).
+        `rows` (B,N,ld) = [xyz | features | zeros], point-major: what the fused kernels gather from when given (inference);
+        `want_rows`: also return the layer's output in that layout -- (new_xyz, new_features, rows_out or None)."""
         if new_xyz is None and self.npoint is not None:
             _, new_xyz = pointnet2_utils.sample_and_gather(xyz, self.npoint)
         if self.npoint is not None and indices is not None:
@@ -111,6 +120,13 @@ class _PointnetSAModuleBase(nn.Module):
                 cache = self.__dict__.setdefault("_fused_scales", {})
                 widths = [mlp[-1].conv.out_channels for mlp in self.mlps]
                 out = torch.empty((xyz.shape[0], sum(widths), new_xyz.shape[1]), dtype=torch.float32, device=xyz.device)
+                if rows is not None and not (rows.is_contiguous() and rows.shape[-1] % 4 == 0 and rows.shape[-1] >= 3 + c_feat
+                                             and rows.data_ptr() % 16 == 0 and os.environ.get("WS3D_SA_ROWS", "1") != "0"):
+                    rows = None
+                out_pm = None
+                if want_rows and rows is not None:
+                    ld_pm = (3 + sum(widths) + 7) // 8 * 8
+                    out_pm = torch.empty((xyz.shape[0], new_xyz.shape[1], ld_pm), dtype=torch.float32, device=xyz.device)
                 streams = self._scale_side_streams(xyz) if os.environ.get("WS3D_SCALE_STREAMS", "1") != "0" else None
                 main = torch.cuda.current_stream(xyz.device)
                 for k, mlp in enumerate(self.mlps):
@@ -128,19 +144,19 @@ class _PointnetSAModuleBase(nn.Module):
                         st = streams[k - 1]
                         st.wait_event(fork)
                         with torch.cuda.stream(st):
-                            cache[k](xyz, new_xyz, features, idx, out, off)
+                            cache[k](xyz, new_xyz, features, idx, out, off, rows=rows, out_pm=out_pm, pm_xyz=False)
                             done = torch.cuda.Event()
                             done.record(st)
-                        for t in (xyz, new_xyz, features, idx, out):
+                        for t in (xyz, new_xyz, features, idx, out, rows, out_pm):
                             if t is not None:
                                 t.record_stream(st)
                         joins.append(done)
                     else:
-                        cache[k](xyz, new_xyz, features, idx, out, off)
+                        cache[k](xyz, new_xyz, features, idx, out, off, rows=rows, out_pm=out_pm, pm_xyz=(k == 0))
                     off += widths[k]
                 for ev in joins:
                     main.wait_event(ev)
-                return new_xyz, out
+                return (new_xyz, out, out_pm) if want_rows else (new_xyz, out)
         # inference, several scales: the scales are independent chains of small launches (group + three layers, each
         # well under one wave at the deeper levels), so they run side by side on per-scale streams
         side = None
@@ -199,8 +215,9 @@ class _PointnetSAModuleBase(nn.Module):
         if all_layers:
             for ev in joins:
                 main.wait_event(ev)
-            return new_xyz, cat_out
-        return new_xyz, torch.cat(pooled, dim=1)
+            return (new_xyz, cat_out, None) if want_rows else (new_xyz, cat_out)
+        res = torch.cat(pooled, dim=1)
+        return (new_xyz, res, None) if want_rows else (new_xyz, res)
 
 
 class PointnetSAModuleMSG(_PointnetSAModuleBase):
