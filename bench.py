@@ -250,6 +250,8 @@ class OpProfiler:
             "split_pointcloud": ("split_pointcloud", lambda pc, *r: dict(b=pc.shape[0], n=pc.shape[1], c=pc.shape[2] - 3)),
             "sa_mlp_fused": ("sa_mlp_fused", lambda b, n, m, nsample, c_feat, xyz, new_xyz, features, idx, widths, *r:
                              dict(b=b, n=n, m=m, k=nsample, c=c_feat, c1=widths[0], c2=widths[1], c3=widths[2])),
+            "sa_mlp_fused_rows": ("sa_mlp_fused", lambda b, n, m, nsample, c_feat, rows, new_xyz, idx, widths, *r:
+                                  dict(b=b, n=n, m=m, k=nsample, c=c_feat, c1=widths[0], c2=widths[1], c3=widths[2])),
             "mlp_layer": ("mlp_layer", lambda b, c_out, c_out_pad, c1, c2, cols, w, shift, x1, x2, out, relu, pool, *r:
                           dict(b=b, c_out=c_out, c_in=c1 + c2, cols=cols, pool=pool)),
         }

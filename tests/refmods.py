@@ -68,3 +68,66 @@ def require_reference_python(natives: dict):
     if ns is None:
         pytest.fail("oracle/_ref/refpy.zip is missing: run oracle/build_ref.sh where /root/reference exists")
     return ns
+
+
+# ---- TF32 emulation of the training-mode shared MLP (checker for ws3d_b200/train_mlp.py) ----------------------------------------
+def emulated_shared_mlp_train(mlp, x1, x2=None, pool: int = 0, product_dtype=None):
+    """Plain PyTorch (float64 products, autograd) restatement of `train_mlp.shared_mlp_train` WITH the operand rounding of the
+    tensor-core path: a GEMM reads its operands truncated to TF32 (10 explicit mantissa bits: the tcgen05 kind::tf32 read),
+    the activations handed to the next layer are rounded to the nearest TF32 value, everything else is FP32 / FP64.
+    Against this reference a ReLU mask or a max-pool arg-max flips only on ties at FP32 rounding level, so forward values
+    and gradients can be held to tolerances two orders tighter than against the cuDNN TF32 path (whose rounding differs).
+    `product_dtype=torch.float32` forms the products with FP32 accumulation instead (cuBLAS SGEMM, TF32 off): the same
+    arithmetic up to summation order, used by the whole-network test as its noise floor."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    class Trunc(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    class RoundNearest(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    mods = list(mlp)
+    blocks = [m for m in mods if not isinstance(m, nn.Dropout)]
+    cur = x1 if x2 is None else torch.cat([x1, x2], dim=1)
+    seen = 0
+    for m in mods:
+        if isinstance(m, nn.Dropout):
+            cur = F.dropout(cur, m.p, training=m.training)
+            continue
+        seen += 1
+        last = seen == len(blocks)
+        conv = m.conv
+        bn = m.bn.bn if hasattr(m, "bn") else None
+        w = Trunc.apply(conv.weight.reshape(conv.weight.shape[0], -1))
+        if product_dtype is torch.float32:
+            assert not torch.backends.cuda.matmul.allow_tf32
+            y = torch.matmul(w, Trunc.apply(cur))
+        else:
+            y = torch.matmul(w.double(), Trunc.apply(cur).double()).float()
+        if bn is not None:
+            y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+            bn.num_batches_tracked.add_(1)
+        elif conv.bias is not None:
+            y = y + conv.bias[None, :, None]
+        if hasattr(m, "activation"):
+            y = F.relu(y)
+        cur = y if last else RoundNearest.apply(y)
+    if pool:
+        B, C, cols = cur.shape
+        cur = cur.view(B, C, cols // pool, pool).max(dim=3)[0]
+    return cur

@@ -163,15 +163,14 @@ def _rel_l2(a, b):
     return float((a - b).norm()) / max(1e-12, float(b.norm()))
 
 
-@pytest.mark.parametrize("spec,cols,pool,two_inputs", [([99, 64, 96, 128], 1024 * 32, 32, False), ([4, 16, 16, 32], 4096 * 16, 16, False),
-                                                       ([257, 128, 128], 16384, 0, True), ([768, 512, 512], 1024, 0, True)])
-def test_shared_mlp_train_matches_pytorch_modules(spec, cols, pool, two_inputs):
-    """Forward, running statistics and every gradient of a SharedMLP in training mode: this library's layer kernels
-    against the PyTorch modules (cuDNN TF32 convolutions, native BatchNorm / ReLU / max-pool, autograd)."""
+_MLP_CASES = [([99, 64, 96, 128], 1024 * 32, 32, False), ([4, 16, 16, 32], 4096 * 16, 16, False),
+              ([257, 128, 128], 16384, 0, True), ([768, 512, 512], 1024, 0, True)]
+
+
+def _mlp_case(spec, cols, pool, two_inputs):
     import copy
 
     from ws3d_b200 import pytorch_utils as pt_utils
-    from ws3d_b200 import train_mlp
     torch.manual_seed(7)
     B = 2
     mine = pt_utils.SharedMLP(list(spec), bn=True).to(dev).train()
@@ -186,7 +185,45 @@ def test_shared_mlp_train_matches_pytorch_modules(spec, cols, pool, two_inputs):
     x2 = torch.randn(B, c2, cols, device=dev) if c2 else None
     a1, a2 = x1.clone().requires_grad_(True), (x2.clone().requires_grad_(True) if c2 else None)
     b1, b2 = x1.clone().requires_grad_(True), (x2.clone().requires_grad_(True) if c2 else None)
+    return B, mine, ref, c2, a1, a2, b1, b2
+
+
+@pytest.mark.parametrize("spec,cols,pool,two_inputs", _MLP_CASES)
+def test_shared_mlp_train_matches_tf32_emulation(spec, cols, pool, two_inputs):
+    """THE parity test of the training layers: forward, running statistics and every gradient against a float64 PyTorch
+    autograd restatement that rounds the GEMM operands exactly as the tensor-core path does (tests/refmods.py).  With the
+    rounding points aligned no ReLU mask / arg-max flips, so the tolerances are FP32-accumulation level for the forward and
+    TF32-rounding-of-dY level (the one rounding autograd does not have) for the gradients."""
+    from refmods import emulated_shared_mlp_train
+
+    from ws3d_b200 import train_mlp
+    B, mine, ref, c2, a1, a2, b1, b2 = _mlp_case(spec, cols, pool, two_inputs)
     assert train_mlp.enabled_for(mine, a1, pool)
+    out = train_mlp.shared_mlp_train(mine, a1, a2, pool=pool)
+    want = emulated_shared_mlp_train(ref, b1, b2, pool=pool)
+    assert _rel_l2(out, want) < 1e-4, ("forward", _rel_l2(out, want))
+    assert _rel(out, want) < 5e-3, ("forward max", _rel(out, want))      # a TF32 ulp where an FP32-level difference straddles a rounding boundary
+    gout = torch.randn_like(want)
+    (out * gout).sum().backward()
+    (want * gout).sum().backward()
+    # 3e-4 = dY rounded to TF32 for the two gradient GEMMs; the pooled cases add a few arg-max flips at FP32-level ties
+    tol = 1e-2 if pool else 3e-3
+    assert _rel_l2(a1.grad, b1.grad) < tol, ("dx1", _rel_l2(a1.grad, b1.grad))
+    if c2:
+        assert _rel_l2(a2.grad, b2.grad) < tol, ("dx2", _rel_l2(a2.grad, b2.grad))
+    for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert _rel_l2(p.grad, q.grad) < tol, (n, _rel_l2(p.grad, q.grad))
+    for (n, p), (_, q) in zip(mine.named_buffers(), ref.named_buffers()):
+        torch.testing.assert_close(p.float(), q.float(), rtol=1e-4, atol=1e-5, msg=n)
+
+
+@pytest.mark.parametrize("spec,cols,pool,two_inputs", _MLP_CASES)
+def test_shared_mlp_train_close_to_cudnn_modules(spec, cols, pool, two_inputs):
+    """Sanity bound against the PyTorch modules themselves (cuDNN TF32 convolutions, native BatchNorm / ReLU / max-pool,
+    autograd).  cuDNN rounds its TF32 operands differently, so ReLU masks and max-pool arg-maxes flip on near-ties and
+    move single gradient elements by O(1): the bound is loose by construction -- the sharp test is the emulation above."""
+    from ws3d_b200 import train_mlp
+    B, mine, ref, c2, a1, a2, b1, b2 = _mlp_case(spec, cols, pool, two_inputs)
     out = train_mlp.shared_mlp_train(mine, a1, a2, pool=pool)
     xin = b1 if b2 is None else torch.cat([b1, b2], dim=1)
     K = pool if pool else 1
@@ -196,21 +233,107 @@ def test_shared_mlp_train_matches_pytorch_modules(spec, cols, pool, two_inputs):
     gout = torch.randn_like(want)
     (out * gout).sum().backward()
     (want * gout).sum().backward()
-    assert _rel_l2(a1.grad, b1.grad) < 3e-2, ("dx1", _rel_l2(a1.grad, b1.grad))
-    if c2:
-        assert _rel_l2(a2.grad, b2.grad) < 3e-2, ("dx2", _rel_l2(a2.grad, b2.grad))
+    assert _rel_l2(a1.grad, b1.grad) < 0.12, ("dx1", _rel_l2(a1.grad, b1.grad))
     for (n, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
-        assert _rel_l2(p.grad, q.grad) < 3e-2, (n, _rel_l2(p.grad, q.grad))
+        assert _rel_l2(p.grad, q.grad) < 0.12, (n, _rel_l2(p.grad, q.grad))
     for (n, p), (_, q) in zip(mine.named_buffers(), ref.named_buffers()):
         torch.testing.assert_close(p.float(), q.float(), rtol=2e-3, atol=2e-3, msg=n)
 
 
-def test_rpn_training_step_on_own_kernels_matches_pytorch_path():
-    """The whole Stage-1 training forward / backward (labels on the GPU, get_rpn_loss) with WS3D_TRAIN_MLP=1 against the
-    same step on the PyTorch MLPs: loss and gradients agree to TF32 tolerance; every parameter receives a gradient."""
+def _rpn_step(model, pts, cls_label, reg_label):
+    from ws3d_b200 import train_functions
+    torch.manual_seed(3)           # dropout masks
+    out = model({"pts_input": pts})
+    loss, _ = train_functions.get_rpn_loss(out["rpn_cls"], out["rpn_reg"], cls_label, reg_label)
+    loss.backward()
+    return float(loss.detach())
+
+
+def test_rpn_training_step_on_own_kernels_matches_tf32_emulation(monkeypatch):
+    """The whole Stage-1 training forward / backward (labels on the GPU, get_rpn_loss): this library's training layers
+    against the SAME network with every shared MLP replaced by the float64 TF32-emulating autograd restatement
+    (tests/refmods.py); grouping / interpolation / sampling kernels are the same on both sides.
+
+    The gradient of this 32-layer BatchNorm network is ill-conditioned with respect to FP32-level forward differences:
+    two runs of the emulation itself that differ only in the accumulation of the products (FP32 against FP64) part by
+    5-10 % per parameter in the Frobenius norm, because the forward activations drift apart to 1e-3 by the last layer and
+    ReLU masks / arg-maxes near zero flip (measured: tools/train_debug.py).  That pair is the NOISE FLOOR; this library
+    must sit within a small factor of it.  The sharp per-layer statement is the isolation loop below: every shared MLP of
+    the step on the step's own input, where no drift can accumulate."""
     import copy
 
-    from ws3d_b200 import label_utils, models, synth, train_functions
+    from refmods import emulated_shared_mlp_train
+
+    from ws3d_b200 import label_utils, models, synth, train_mlp
+    torch.manual_seed(0)
+    net = models.RPN().to(dev).train()
+    ref, ref32 = copy.deepcopy(net), copy.deepcopy(net)
+    pts = torch.from_numpy(synth.make_batch(2, 16384)).to(dev)
+    gt, cnt = synth.make_gt_boxes(2)
+    cls_label, reg_label = label_utils.generate_gaussian_training_labels(pts[..., :3].contiguous(), torch.from_numpy(gt).to(dev),
+                                                                         torch.from_numpy(cnt).to(dev))
+    calls = []
+    own = train_mlp.shared_mlp_train
+
+    def recording(mlp, x1, x2=None, pool=0):
+        calls.append((mlp, x1.detach().clone(), None if x2 is None else x2.detach().clone(), pool))
+        return own(mlp, x1, x2, pool=pool)
+
+    monkeypatch.setattr(train_mlp, "shared_mlp_train", recording)
+    mine = _rpn_step(net, pts, cls_label, reg_label)
+    ref_mlps = []
+    monkeypatch.setattr(train_mlp, "shared_mlp_train",
+                        lambda m, a, b=None, pool=0: (ref_mlps.append(m), emulated_shared_mlp_train(m, a, b, pool=pool))[1])
+    want = _rpn_step(ref, pts, cls_label, reg_label)
+    monkeypatch.setattr(train_mlp, "shared_mlp_train",
+                        lambda m, a, b=None, pool=0: emulated_shared_mlp_train(m, a, b, pool=pool, product_dtype=torch.float32))
+    want32 = _rpn_step(ref32, pts, cls_label, reg_label)
+    monkeypatch.undo()
+    assert abs(mine - want) < 1e-4 * abs(want) and abs(want32 - want) < 1e-4 * abs(want), (mine, want, want32)
+    errs, floor = {}, {}
+    for (n, p), (_, q), (_, q32) in zip(net.named_parameters(), ref.named_parameters(), ref32.named_parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        assert q.grad is not None, n
+        if float(q.grad.abs().max()) > 1e-6:
+            errs[n], floor[n] = _rel_l2(p.grad, q.grad), _rel_l2(q32.grad, q.grad)
+    med = lambda d: sorted(d.values())[len(d) // 2]                                    # noqa: E731
+    assert len(errs) > 100
+    assert med(errs) < 2.0 * med(floor) + 5e-3, (med(errs), med(floor))
+    assert max(errs.values()) < 2.5 * max(floor.values()) + 1e-2, (max(errs.values()), max(floor.values()))
+    for (n, p), (_, q) in zip(net.named_buffers(), ref.named_buffers()):       # running statistics: the forward drift, 1e-3 of the scale
+        assert _rel(p.float(), q.float()) < 5e-3, (n, _rel(p.float(), q.float()))
+    # every shared MLP of the step in isolation, on the input the step gave it (grouped neighbourhoods with duplicate
+    # columns, interpolated + skip features, the heads with dropout): forward 2e-4, gradients 3 % (narrow deep levels
+    # have 512 columns, where a single flipped arg-max is visible)
+    assert len(calls) == len(ref_mlps) == 14
+    for k, ((mlp, x1, x2, pool), rmlp) in enumerate(zip(calls, ref_mlps)):
+        xa, xb = x1.clone().requires_grad_(True), x1.clone().requires_grad_(True)
+        x2a = None if x2 is None else x2.clone().requires_grad_(True)
+        x2b = None if x2 is None else x2.clone().requires_grad_(True)
+        for q in list(mlp.parameters()) + list(rmlp.parameters()):
+            q.grad = None
+        torch.manual_seed(11)
+        oa = own(mlp, xa, x2a, pool=pool)
+        torch.manual_seed(11)
+        ob = emulated_shared_mlp_train(rmlp, xb, x2b, pool=pool)
+        assert _rel_l2(oa, ob) < 2e-4, (k, "forward", _rel_l2(oa, ob))
+        g = torch.randn_like(ob)
+        (oa * g).sum().backward()
+        (ob * g).sum().backward()
+        assert _rel_l2(xa.grad, xb.grad) < 3e-2, (k, "dx1", _rel_l2(xa.grad, xb.grad))
+        if x2 is not None:
+            assert _rel_l2(x2a.grad, x2b.grad) < 3e-2, (k, "dx2", _rel_l2(x2a.grad, x2b.grad))
+        for (n, p), (_, q) in zip(mlp.named_parameters(), rmlp.named_parameters()):
+            assert _rel_l2(p.grad, q.grad) < 4e-2, (k, n, _rel_l2(p.grad, q.grad))
+
+
+def test_rpn_training_step_close_to_cudnn_path():
+    """Same step against the PyTorch / cuDNN MLP path (WS3D_TRAIN_MLP=0): 32 chained TF32 layers whose rounding differs
+    between the two implementations, so masks / arg-maxes flip and the per-parameter agreement is loose by construction
+    (see the emulation test for the sharp statement): loss to 2 %, gradient direction (cosine) per parameter."""
+    import copy
+
+    from ws3d_b200 import label_utils, models, synth
     torch.manual_seed(0)
     net = models.RPN().to(dev).train()
     ref = copy.deepcopy(net)
@@ -222,17 +345,15 @@ def test_rpn_training_step_on_own_kernels_matches_pytorch_path():
     for model, flag in ((net, "1"), (ref, "0")):
         os.environ["WS3D_TRAIN_MLP"] = flag
         try:
-            torch.manual_seed(3)           # dropout masks
-            out = model({"pts_input": pts})
-            loss, _ = train_functions.get_rpn_loss(out["rpn_cls"], out["rpn_reg"], cls_label, reg_label)
-            loss.backward()
-            losses.append(float(loss))
+            losses.append(_rpn_step(model, pts, cls_label, reg_label))
         finally:
             os.environ.pop("WS3D_TRAIN_MLP", None)
     assert abs(losses[0] - losses[1]) < 2e-2 * abs(losses[1]), losses
-    worst = 0.0
+    cos = {}
     for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
         if float(q.grad.abs().max()) > 1e-6:
-            worst = max(worst, _rel_l2(p.grad, q.grad))
-    assert worst < 0.15, worst       # 32 chained TF32 layers with batch statistics, atomics in the irregular gradients
+            cos[n] = float(F.cosine_similarity(p.grad.flatten().double(), q.grad.flatten().double(), dim=0))
+    worst = sorted(cos.items(), key=lambda kv: kv[1])[:5]
+    med = sorted(cos.values())[len(cos) // 2]
+    assert med > 0.97 and worst[0][1] > 0.85, (med, worst)

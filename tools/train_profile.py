@@ -1,38 +1,21 @@
-"""Where a Stage-1 RPN training step spends its GPU time (torch.profiler / kineto, eager launches): top kernels."""
+"""Where a Stage-1 RPN training step spends its GPU time (torch.profiler / kineto, eager launches): top kernels.
+The step is workloads.RpnTrainStep -- forward in training mode, Gaussian labels on the GPU, get_rpn_loss, backward, Adam --
+on this library's training kernels (WS3D_TRAIN_MLP=0 profiles the PyTorch / cuDNN MLP path instead).
+
+    python tools/train_profile.py [scenes_per_gpu]          -> gpurun_out/train_profile.txt
+"""
 import os
 import sys
 
 import torch
-import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ws3d_b200 import models, synth  # noqa: E402
+from ws3d_b200 import workloads  # noqa: E402
 
-dev = "cuda:0"
-torch.manual_seed(0)
-net = models.RPN().to(dev).train()
-opt = torch.optim.Adam(net.parameters(), lr=2e-3)
-B = 16
-pts = torch.from_numpy(synth.make_batch(B, 16384)).to(dev)
-g = torch.Generator(device="cpu").manual_seed(0)
-cls_label = (torch.rand(B, 16384, generator=g) < 0.05).float().to(dev)
-reg_label = torch.randn(B, 16384, 40, generator=g).to(dev)
-
-
-def step():
-    out = net({"pts_input": pts})
-    logit = out["rpn_cls"].squeeze(-1)
-    p = torch.sigmoid(logit)
-    focal = (0.25 * cls_label * (1 - p) ** 2 + 0.75 * (1 - cls_label) * p ** 2) * \
-        F.binary_cross_entropy_with_logits(logit, cls_label, reduction="none")
-    fg = cls_label.unsqueeze(-1)
-    loss = focal.sum() / cls_label.sum().clamp_min(1.0) + \
-        (F.smooth_l1_loss(out["rpn_reg"], reg_label, reduction="none") * fg).sum() / fg.sum().clamp_min(1.0)
-    opt.zero_grad(set_to_none=True)
-    loss.backward()
-    opt.step()
-
-
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+step = workloads.RpnTrainStep(B, dev, graph=False)
 for _ in range(3):
     step()
 torch.cuda.synchronize()
@@ -44,6 +27,10 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 rows = sorted(prof.key_averages(), key=lambda r: -r.self_device_time_total)
 total = sum(r.self_device_time_total for r in rows)
-print(f"GPU time per step: {total / 2e3:.2f} ms (sum of kernels, 2 steps profiled)")
-for r in rows[:30]:
-    print(f"{r.self_device_time_total / 2e3:8.3f} ms/step  {100 * r.self_device_time_total / total:5.1f} %  x{r.count // 2:<4d} {r.key[:110]}")
+lines = [f"GPU time per step: {total / 2e3:.2f} ms (sum of kernels, 2 steps profiled, {B} scenes, WS3D_TRAIN_MLP={os.environ.get('WS3D_TRAIN_MLP', '1')})"]
+for r in rows[:40]:
+    lines.append(f"{r.self_device_time_total / 2e3:8.3f} ms/step  {100 * r.self_device_time_total / total:5.1f} %  x{r.count // 2:<4d} {r.key[:120]}")
+print("\n".join(lines))
+os.makedirs("gpurun_out", exist_ok=True)
+with open(os.path.join("gpurun_out", f"train_profile_mlp{os.environ.get('WS3D_TRAIN_MLP', '1')}.txt"), "w") as f:
+    f.write("\n".join(lines) + "\n")
