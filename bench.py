@@ -606,41 +606,54 @@ def run_gpu(args):
 
 def bench_training(args, torch, dist, dev, world, rank, workloads, max_ms):
     """Config 3: Stage-1 RPN training step.  Weak scaling (32 scenes per GPU) and strong scaling (global batch 32);
-    with world > 1 the gradient all-reduce (NCCL) is inside the step; its share = 1 - t(no_sync) / t(sync)."""
-    out = {"workload": "Stage-1 RPN training step (forward in training mode, Gaussian labels on the GPU, get_rpn_loss, backward, Adam), "
-                       "synthetic scenes 16384 x 4"}
+    with world > 1 the gradient all-reduce (NCCL, one collective of all gradients inside the replayed graph) is part of the
+    step; its share = 1 - t(step without the collective) / t(step)."""
+    out = {"workload": "Stage-1 RPN training step (forward in training mode, Gaussian labels on the GPU, get_rpn_loss, backward, "
+                       "gradient all-reduce, Adam), synthetic scenes 16384 x 4"}
+    n = max(3, min(args.steps, 8))
+
+    def timed(step):
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            loss = step()
+        e.record()
+        e.synchronize()
+        return max_ms(s.elapsed_time(e)) / n, float(loss.detach())
+
     for tag, per_gpu in (("weak_32_per_gpu", 32), ("strong_global_32", max(1, 32 // world))):
         if tag.startswith("strong") and world == 1:
             continue
         step = workloads.RpnTrainStep(per_gpu, dev, world, rank, graph=True)
-        n = max(3, min(args.steps, 8))
-
-        def timed(sync_grads):
-            for _ in range(2):
-                step(sync_grads)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-                torch.cuda.synchronize()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(n):
-                loss = step(sync_grads)
-            e.record()
-            e.synchronize()
-            return max_ms(s.elapsed_time(e)) / n, float(loss)
-
-        ms, loss = timed(True)
+        ms, loss = timed(step)
         rec = {"scenes_per_gpu": per_gpu, "n_gpus": world, "ms_per_step": round(ms, 3), "scenes_per_s": round(world * per_gpu / ms * 1e3, 1),
-               "final_loss": round(loss, 4), "steps": n, "launch": "one CUDA graph replay per step" if step.graphed else "eager (DDP)",
+               "final_loss": round(loss, 4), "steps": n,
+               "launch": "one CUDA graph replay per step" + (" (the NCCL all-reduce is a node of the graph)" if world > 1 else ""),
                "mlp": train_mlp_description()}
         if world > 1:
-            ms_ns, _ = timed(False)
-            rec["allreduce"] = {"bytes": step.param_bytes, "ms_per_step_without": round(ms_ns, 3),
+            # replicas must hold identical parameters after identical averaged updates
+            probe = torch.stack([p.detach().double().sum() for p in step.net.parameters()]).sum().reshape(1)
+            lo, hi = probe.clone(), probe.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            rec["replicas_in_sync"] = bool(float(hi - lo) <= 1e-9 * max(1.0, abs(float(hi))))
+            del step
+            alone = workloads.RpnTrainStep(per_gpu, dev, world, rank, graph=True, exchange=False)
+            ms_ns, _ = timed(alone)
+            rec["allreduce"] = {"bytes": alone.param_bytes, "ms_per_step_without": round(ms_ns, 3),
                                 "share_of_step": round(max(0.0, 1.0 - ms_ns / ms), 4),
-                                "note": "DDP gradient all-reduce over NCCL / NVLink, overlapped with backward; share = 1 - t(no_sync) / t(sync)"}
+                                "note": "ONE averaged all-reduce of all gradients (flat 12.2 MB buffer) over NCCL / NVLink after "
+                                        "backward; share = 1 - t(step without the collective) / t(step)"}
+            del alone
+        else:
+            del step
         out[tag] = rec
-        del step
         torch.cuda.synchronize()
     return out
 

@@ -1,13 +1,12 @@
 """The BASELINE.json workloads besides the backbone forward, as callable pieces (bench.py and tools/ share them):
 
   config 1   one set-abstraction layer's irregular ops on ONE cloud (FPS 16384 -> 4096, ball query r = 0.8, K = 32)
-  config 3   the Stage-1 RPN training step (forward, labels, loss, backward, Adam; DDP over NCCL when world > 1)
+  config 3   the Stage-1 RPN training step (forward, labels, loss, backward, gradient all-reduce over NCCL when world > 1, Adam)
   config 4   rotated BEV IoU + NMS on 16384 boxes and roipool3d of 16384 boxes x 16384 points
   config 5   the Stage-2 set-abstraction stack on 512 pooled proposals per scene
 
 Everything here runs on this repo's kernels; nothing imports oracle/.
 """
-import contextlib
 from typing import Callable, Dict, Optional
 
 import numpy as np
@@ -68,27 +67,30 @@ def single_sa_layer(dev, flush=None, iters: int = 20, npoint: int = 4096, radius
 # ---- config 3 -------------------------------------------------------------------------------------
 class RpnTrainStep:
     """One Stage-1 training step on `batch` synthetic scenes per rank: RPN forward (training mode: batch statistics),
-    Gaussian labels on the GPU (label_utils), get_rpn_loss (train_functions), backward, Adam.
-    world > 1: DistributedDataParallel -- the gradient all-reduce over NCCL is the path's only collective."""
+    Gaussian labels on the GPU (label_utils), get_rpn_loss (train_functions), backward, the data-parallel
+    gradient exchange (sharding.FlatGradients: ONE averaged all-reduce over NCCL, the path's only collective), Adam.
+    The whole step -- collective included -- is captured once and replayed as one CUDA graph (`graph=True`); BatchNorm
+    statistics stay per replica, as under the reference's DataParallel / DDP.  `exchange=False` leaves the collective out
+    (the all-reduce share of a step is measured as the difference)."""
 
-    def __init__(self, batch: int, dev, world: int = 1, rank: int = 0, graph: bool = True, lr: float = 2e-3):
-        torch.manual_seed(0)
+    def __init__(self, batch: int, dev, world: int = 1, rank: int = 0, graph: bool = True, lr: float = 2e-3, exchange: bool = True):
+        from . import sharding
+        torch.manual_seed(0)                      # identical initial replicas on every rank
         self.net = models.RPN().to(dev).train()
+        self.model = self.net
         self.param_bytes = sum(p.numel() for p in self.net.parameters()) * 4
         self.world, self.batch = world, batch
-        if world > 1:
-            self.model = torch.nn.parallel.DistributedDataParallel(self.net, device_ids=[dev.index], gradient_as_bucket_view=True)
-        else:
-            self.model = self.net
-        self.graphed = bool(graph) and world == 1
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, capturable=self.graphed)
+        self.grads = sharding.FlatGradients(self.net.parameters(), world=world)
+        self.exchange = bool(exchange) and world > 1
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=lr, capturable=bool(graph))
         self.pts = torch.from_numpy(synth.make_batch(batch, 16384, first_scene=rank * batch)).to(dev)
         gt, cnt = synth.make_gt_boxes(batch, 16384, first_scene=rank * batch)
         self.gt, self.gt_cnt = torch.from_numpy(gt).to(dev), torch.from_numpy(cnt).to(dev)
         self.xyz = self.pts[..., :3].contiguous()
         self.terms = None
         self._graph = None
-        if self.graphed:
+        self.graphed = False
+        if graph:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
@@ -99,24 +101,25 @@ class RpnTrainStep:
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._static_loss = self._eager()
+            self.graphed = True
 
-    def _eager(self, sync_grads: bool = True):
-        ctx = contextlib.nullcontext() if (sync_grads or self.world == 1) else self.model.no_sync()
-        with ctx:
-            out = self.model({"pts_input": self.pts})
-            with torch.no_grad():
-                cls_label, reg_label = label_utils.generate_gaussian_training_labels(self.xyz, self.gt, self.gt_cnt)
-            loss, self.terms = train_functions.get_rpn_loss(out["rpn_cls"], out["rpn_reg"], cls_label, reg_label)
-            self.opt.zero_grad(set_to_none=True)
-            loss.backward()
+    def _eager(self):
+        out = self.model({"pts_input": self.pts})
+        with torch.no_grad():
+            cls_label, reg_label = label_utils.generate_gaussian_training_labels(self.xyz, self.gt, self.gt_cnt)
+        loss, self.terms = train_functions.get_rpn_loss(out["rpn_cls"], out["rpn_reg"], cls_label, reg_label)
+        self.grads.zero()
+        loss.backward()
+        if self.exchange:
+            self.grads.exchange()
         self.opt.step()
         return loss
 
-    def __call__(self, sync_grads: bool = True):
+    def __call__(self):
         if self._graph is not None:
             self._graph.replay()
             return self._static_loss
-        return self._eager(sync_grads)
+        return self._eager()
 
 
 # ---- config 4 -------------------------------------------------------------------------------------
