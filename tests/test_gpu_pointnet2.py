@@ -318,6 +318,42 @@ def test_three_interpolate(b, c, m, n):
         assert torch.equal(r, out.detach())
 
 
+@pytest.mark.parametrize("b,c,m,n,stencil", [(2, 64, 256, 1024, "nn"), (1, 19, 4096, 16384, "nn"), (2, 7, 33, 100, "random"),
+                                             (1, 40, 64, 256, "nn"), (1, 5, 2, 50, "random"), (2, 130, 1024, 4096, "nn"),
+                                             (1, 3, 30000, 64, "random")])
+def test_three_interpolate_grad_gather_over_inverse_stencil(b, c, m, n, stencil):
+    """three_interpolate_grad as a gather over the per-call inverse of the stencil (csrc/interp_grad.cu): equal to the oracle's
+    scatter (interpolate_gpu.cu:112-137) up to FP32 summation order, ADDS to grad_points like the reference's atomicAdd,
+    and -- unlike the atomic formulation -- bit-reproducible.  Shapes: the four FP levels' row lengths (chunked rows, long rows
+    that leave one CTA per SM, channel counts that do not divide the chunk), n not a multiple of 4 (no TMA tail), duplicate
+    (i, j) pairs and m < 3, and m beyond the builder's limit (the atomic kernel takes it)."""
+    from ws3d_b200 import native
+    rng = np.random.default_rng(b * 1000 + c + m)
+    if stencil == "nn":       # a real stencil: three nearest known points, inverse-distance weights
+        known = _cloud(rng, b, m, "scene")
+        unknown = _cloud(rng, b, n, "scene")
+        d2, idx = oracle.three_nn(unknown, known)
+        r = 1.0 / (np.sqrt(d2) + 1e-8)
+        w = (r / r.sum(-1, keepdims=True)).astype(np.float32)
+    else:
+        idx = rng.integers(0, m, (b, n, 3)).astype(np.int32)
+        w = rng.uniform(0, 1, (b, n, 3)).astype(np.float32)
+    g = rng.normal(size=(b, c, n)).astype(np.float32)
+    want = oracle.three_interpolate_grad(g, idx, w, m)
+    outs = []
+    for _ in range(2):
+        gp = torch.ones((b, c, m), dtype=torch.float32, device=dev)
+        native.three_interpolate_grad_wrapper(b, c, n, m, _t(g), _t(idx), _t(w), gp)
+        outs.append(gp)
+    np.testing.assert_allclose(outs[0].cpu().numpy() - 1.0, want, rtol=1e-4, atol=2e-5)
+    if m <= 24576:
+        assert torch.equal(outs[0], outs[1])          # fixed summation order
+    ref = require_ref("pointnet2_cuda")
+    rp = torch.zeros((b, c, m), dtype=torch.float32, device=dev)
+    ref.three_interpolate_grad_wrapper(b, c, n, m, _t(g), _t(idx), _t(w), rp)
+    np.testing.assert_allclose(outs[0].cpu().numpy() - 1.0, rp.cpu().numpy(), rtol=1e-4, atol=2e-5)
+
+
 @pytest.mark.parametrize("c,use_xyz", [(1, True), (96, True), (0, True), (5, False)])
 def test_query_and_group_fused_equals_composition(c, use_xyz):
     from ws3d_b200 import pointnet2_utils

@@ -20,6 +20,9 @@
 #include "tma.cuh"
 
 namespace ws3d {
+// interp_grad.cu: 0 = done, 1 = shape outside the gather path's limits, else a cudaError code
+int three_interpolate_grad_gather(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                                  float *grad_points, cudaStream_t stream);
 
 // ball_query_grid.cu: cell-list pruned scan for clouds that are large against the ball
 bool ball_query_grid_applicable(int nr, int b, int n, int m, const float *radius);
@@ -708,6 +711,12 @@ WS3D_API int ws3d_three_interpolate_grad(int b, int c, int n, int m, const float
   if (b < 0 || c < 0 || m < 0 || n < 0) return fail_arg("three_interpolate_grad");
   if (b == 0 || c == 0 || n == 0) return 0;
   if (!grad_out || !idx || !weight || !grad_points) return fail_arg("three_interpolate_grad (null pointer)");
+  // gather over the inverse stencil (interp_grad.cu): no atomics, fixed summation order; 1 = shape outside its limits
+  static const bool force_atomic = [] { const char *e = getenv("WS3D_INTERP_GRAD_ATOMIC"); return e && e[0] == '1'; }();
+  if (!force_atomic) {
+    const int rc = three_interpolate_grad_gather(b, c, n, m, grad_out, idx, weight, grad_points, to_stream(stream));
+    if (rc != 1) return rc;
+  }
   if (b > 65535 || ceil_div(c, kInterpChannels) > 65535) return fail_arg("three_interpolate_grad (grid too large)");
   dim3 grid((unsigned)ceil_div(n, kInterpThreads), (unsigned)ceil_div(c, kInterpChannels), (unsigned)b);
   three_interpolate_grad_kernel<<<grid, kInterpThreads, 0, to_stream(stream)>>>(c, n, m, grad_out, idx, weight, grad_points);
