@@ -6,7 +6,7 @@
 Small shapes (the tools slow kernels down 10-100x) that still reach every kernel family of the forward path: cluster /
 DSMEM FPS (flat and two-level) and the bucketed FPS, cell-grid and shared-memory ball query, ring-search three_nn with
 the weight epilogue, grouping, interpolation (plain and affine), the tcgen05 layer kernel and the fused SA kernel
-(TMEM reuse in place), iou3d / NMS / roipool3d, the f2-f4 kernels, and a StreamedBackboneRunner whose graphs replay
+(TMEM reuse in place), iou3d / NMS / roipool3d, the f2-f4 kernels, one training forward / backward (training layers, gradient kernels), and a StreamedBackboneRunner whose graphs replay
 concurrently on per-buffer scratch arenas.  Outputs are compared with the plain forward so that a silent corruption
 would also fail the run."""
 import os
@@ -77,6 +77,17 @@ def main():
         if not torch.equal(got, want[k]):
             problems.append(f"streamed batch {k} differs from the plain forward: max diff {float((got - want[k]).abs().max())}, "
                             f"{int((got != want[k]).sum())} of {got.numel()} values")
+    # ---- training mode: the tcgen05 GEMM with batch statistics, fused BN + ReLU (+ pool) forward / backward, split-K weight
+    #      gradient, the grouping gradient and three_interpolate_grad as a gather over the inverse stencil
+    trainee = models.Pointnet2MSG(input_channels=1, sa_config=cfg, fp_mlps=[[32, 32], [48, 48], [64, 64], [64, 64]]).to(dev).train()
+    grads = []
+    for _ in range(2):
+        trainee.zero_grad(set_to_none=True)
+        trainee(batches[0])[1].square().mean().backward()
+        grads.append(torch.cat([q.grad.flatten() for q in trainee.parameters() if q.grad is not None]).clone())
+    torch.cuda.synchronize()
+    if not torch.isfinite(grads[0]).all():
+        problems.append("training step produced non-finite gradients")
     rpn = models.RPN().to(dev).eval()
     with torch.no_grad():
         rpn(torch.from_numpy(synth.make_batch(1, 16384 if not quick else 4096)).to(dev))
