@@ -576,6 +576,7 @@ def run_gpu(args):
 
     # ---- BASELINE.json configs 3 and 5 run on every rank (they shard); 1, 4 and the baselines on rank 0 of a 1-GPU run
     configs = {}
+    native.set_sm_budget(0)      # the SM cap of the persistent kernels belongs to the streamed pipeline only
     if not args.no_configs:
         configs["3"] = bench_training(args, torch, dist, dev, world, rank, workloads, max_ms)
         st2 = workloads.stage2_stack(dev, rank, scenes=1, flush=flush, iters=10)
@@ -782,20 +783,24 @@ def bench_oracle_gpu(torch, model, residents, flush, dev, ms_single, ms_streamed
         # best effort: 4 batches side by side on 4 streams, 2 rounds
         streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
         main = torch.cuda.current_stream(dev)
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for st in streams:
-            st.wait_stream(main)
-        for r in range(2):
-            for k, st in enumerate(streams):
-                with torch.cuda.stream(st):
-                    ref_forward(model, ops, residents[(r + k) % 2])
-        for st in streams:
-            main.wait_stream(st)
-        e.record()
-        e.synchronize()
-        ms_multi = s.elapsed_time(e) / 8
+        def multi_round():
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for st in streams:
+                st.wait_stream(main)
+            for r in range(2):
+                for k, st in enumerate(streams):
+                    with torch.cuda.stream(st):
+                        ref_forward(model, ops, residents[(r + k) % 2])
+            for st in streams:
+                main.wait_stream(st)
+            e.record()
+            e.synchronize()
+            return s.elapsed_time(e) / 8
+
+        multi_round()                                       # untimed: the caching allocator grows its per-stream pools
+        ms_multi = min(multi_round() for _ in range(3))     # the reference arm gets its best round
     return {"impl": "reference kernels (pointnet2_lib/pointnet2/src/*.cu, unmodified, -gencode sm_100a) under the same PyTorch modules, cuDNN TF32 MLPs",
             "one_in_flight": {"ms_per_step": round(ms_one, 3), "Mpoints_per_s": round(BATCH * NPTS / ms_one / 1e3, 3)},
             "four_streams": {"ms_per_step": round(ms_multi, 3), "Mpoints_per_s": round(BATCH * NPTS / ms_multi / 1e3, 3)},

@@ -43,6 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scenes", type=int, default=1, help="scenes per GPU (512 proposals each)")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the forward as one CUDA graph (no per-launch host work)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -67,11 +68,23 @@ def main():
             dist.barrier()
         l0 = _C.launch_count()
         total = 0.0
+        run = lambda: model(xyz, feats)                                                # noqa: E731
+        if args.graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                model(xyz, feats)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = model(xyz, feats)
+            run = lambda: (graph.replay(), static_out)[1]                              # noqa: E731
         for _ in range(args.steps):
             flush.fill_(0)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            out = model(xyz, feats)
+            out = run()
             e.record()
             e.synchronize()
             total += s.elapsed_time(e)
@@ -83,7 +96,7 @@ def main():
         print(json.dumps({"metric": "Stage-2 SA stack proposals/sec (4 SA levels, 512 pts x 128 ch per proposal)", "value": round(world * B / (ms / 1e3), 1),
                           "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "ms_per_step": round(ms, 3), "scaling": "weak",
                           "config": {"proposals_per_gpu": B, "points_per_proposal": 512, "out_shape": list(out.shape)},
-                          "gpu_launches": int(_C.launch_count() - l0)}), flush=True)
+                          "launch": "graph replay" if args.graph else "eager", "gpu_launches": int(_C.launch_count() - l0)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
