@@ -626,7 +626,7 @@ def bench_training(args, torch, dist, dev, world, rank, workloads, max_ms):
             loss = step()
         e.record()
         e.synchronize()
-        return max_ms(s.elapsed_time(e)) / n, float(loss.detach())
+        return max_ms(s.elapsed_time(e)) / (n * step.steps_per_call), float(loss.detach())
 
     for tag, per_gpu in (("weak_32_per_gpu", 32), ("strong_global_32", max(1, 32 // world))):
         if tag.startswith("strong") and world == 1:
@@ -634,8 +634,10 @@ def bench_training(args, torch, dist, dev, world, rank, workloads, max_ms):
         step = workloads.RpnTrainStep(per_gpu, dev, world, rank, graph=True)
         ms, loss = timed(step)
         rec = {"scenes_per_gpu": per_gpu, "n_gpus": world, "ms_per_step": round(ms, 3), "scenes_per_s": round(world * per_gpu / ms * 1e3, 1),
-               "final_loss": round(loss, 4), "steps": n,
-               "launch": "one CUDA graph replay per step" + (" (the NCCL all-reduce is a node of the graph)" if world > 1 else ""),
+               "final_loss": round(loss, 4), "steps": n * step.steps_per_call,
+               "launch": "one CUDA graph replay per TWO steps" + (" (the NCCL all-reduces are nodes of the graph)" if world > 1 else ""),
+               "prefetch": "the coordinate phase (FPS, ball queries, stencils) of batch k+1 runs on a side stream beside step k, as a "
+                           "loader that knows the next batch allows; two synthetic batches alternate",
                "mlp": train_mlp_description()}
         if world > 1:
             # replicas must hold identical parameters after identical averaged updates

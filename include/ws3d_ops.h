@@ -123,6 +123,14 @@ int ws3d_group_points(int b, int c, int n, int npoints, int nsample, const float
 int ws3d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
                            const int *idx, float *grad_points, ws3d_stream_t stream);
 
+/* Extension: gradient of ws3d_group_concat with respect to `features` (the autograd mirror of
+ * QueryAndGroup.forward, pointnet2_utils.py:241-264, where GroupingOperation.backward :187-197 receives
+ * a contiguous copy of grad[:, 3:]).  grad_out (B, 3*use_xyz + C, M, nsample) is read in place -- the
+ * coordinate channels are skipped by addressing, not by a strided copy; grad_features (B,C,N) is
+ * accumulated into (caller zero-fills), exactly like ws3d_group_points_grad. */
+int ws3d_group_concat_grad(int b, int n, int m, int c, int nsample, int use_xyz, const float *grad_out,
+                           const int *idx, float *grad_features, ws3d_stream_t stream);
+
 /* Extension: QueryAndGroup.forward (pointnet2_utils.py:241-264) as one pass per
  * scale: ball_query -> gather xyz -> subtract centre -> gather features -> concat,
  * written once.  xyz (B,N,3), new_xyz (B,M,3), features (B,C,N) or NULL,

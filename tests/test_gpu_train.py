@@ -357,3 +357,39 @@ def test_rpn_training_step_close_to_cudnn_path():
     worst = sorted(cos.items(), key=lambda kv: kv[1])[:5]
     med = sorted(cos.values())[len(cos) // 2]
     assert med > 0.97 and worst[0][1] > 0.85, (med, worst)
+
+
+def test_training_forward_on_a_prefetched_plan_equals_the_plain_forward():
+    """config 3 runs the coordinate phase (FPS in throughput mode, ball queries, stencils) of the NEXT batch beside the
+    current step; the step then consumes that plan.  Same kernels, same indices: outputs are bit-identical."""
+    import copy
+
+    from ws3d_b200 import models, native, synth
+    torch.manual_seed(0)
+    net = models.RPN().to(dev).train()
+    twin = copy.deepcopy(net)
+    pts = torch.from_numpy(synth.make_batch(2, 16384, first_scene=4)).to(dev)
+    torch.manual_seed(3)
+    want = net({"pts_input": pts})
+    with torch.no_grad():
+        prev = native.set_fps_mode(1)
+        plan = twin.backbone_net.coordinate_phase(pts)
+        native.set_fps_mode(prev)
+    torch.manual_seed(3)
+    got = twin({"pts_input": pts}, plan=plan)
+    assert torch.equal(got["rpn_cls"], want["rpn_cls"]) and torch.equal(got["rpn_reg"], want["rpn_reg"])
+
+
+def test_rpn_train_step_with_prefetch_replays_and_hands_plans_over():
+    """workloads.RpnTrainStep (two alternating batches, one graph replay = two steps): the loss falls over a few replays
+    and the plan buffers each step consumes equal a fresh coordinate phase of its batch after every replay."""
+    from ws3d_b200 import workloads
+    step = workloads.RpnTrainStep(2, torch.device(dev), graph=True)
+    assert step.steps_per_call == 2 and step.graphed
+    losses = [float(step().detach()) for _ in range(6)]
+    torch.cuda.synchronize()
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    for d in step.data:
+        fresh = workloads._plan_tensors(step._coordinate_phase(d["pts"]))
+        for a, b in zip(workloads._plan_tensors(d["plan"]), fresh):
+            assert torch.equal(a, b)

@@ -15,7 +15,7 @@ from ws3d_b200 import workloads  # noqa: E402
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-step = workloads.RpnTrainStep(B, dev, graph=False)
+step = workloads.RpnTrainStep(B, dev, graph=False, prefetch=False)
 for _ in range(3):
     step()
 torch.cuda.synchronize()

@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32, help="scenes per GPU")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--prefetch", type=int, default=1, help="1: the next batch's coordinate phase runs beside the current step (two steps per call)")
     ap.add_argument("--graph", type=int, default=1, help="1: one CUDA graph replay per step (collective included); 0: eager launches")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -53,14 +54,14 @@ def main():
         t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / args.steps, float(loss.detach()), int(_C.launch_count() - l0)
+        return float(t.item()) / (args.steps * step.steps_per_call), float(loss.detach()), int(_C.launch_count() - l0)
 
-    step = workloads.RpnTrainStep(args.batch, dev, world, rank, graph=bool(args.graph))
+    step = workloads.RpnTrainStep(args.batch, dev, world, rank, graph=bool(args.graph), prefetch=bool(args.prefetch))
     ms, loss, launches = timed(step)
     rec = {"metric": "Stage-1 RPN training scenes/sec (forward + labels + loss + backward + gradient all-reduce + Adam)",
-           "value": round(world * args.batch / (ms / 1e3), 1), "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+           "value": round(world * args.batch / (ms / 1e3), 1), "unit": "scenes/s", "n_gpus": world, "steps": args.steps * step.steps_per_call,
            "ms_per_step": round(ms, 3), "scaling": "weak", "final_loss": round(loss, 4), "gpu_launches_eager": launches,
-           "config": {"scenes_per_gpu": args.batch, "points_per_scene": 16384, "optimizer": "Adam", "mlp": train_mlp.DESCRIPTION,
+           "config": {"prefetch_next_coordinate_phase": bool(args.prefetch), "scenes_per_gpu": args.batch, "points_per_scene": 16384, "optimizer": "Adam", "mlp": train_mlp.DESCRIPTION,
                       "launch": "one CUDA graph replay per training step" if step.graphed else "eager launches",
                       "collective": ("one averaged all-reduce (NCCL) of %.2f MB fp32 per step, inside the graph" % (step.param_bytes / 1e6))
                       if world > 1 else "none (1 GPU)"}}
@@ -71,7 +72,7 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         rec["replicas_in_sync"] = bool(float(hi - lo) <= 1e-9 * max(1.0, abs(float(hi))))
         del step
-        alone = workloads.RpnTrainStep(args.batch, dev, world, rank, graph=bool(args.graph), exchange=False)
+        alone = workloads.RpnTrainStep(args.batch, dev, world, rank, graph=bool(args.graph), exchange=False, prefetch=bool(args.prefetch))
         ms_ns, _, _ = timed(alone)
         rec["allreduce"] = {"ms_per_step_without": round(ms_ns, 3), "share_of_step": round(max(0.0, 1.0 - ms_ns / ms), 4)}
     if rank == 0:

@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(kGatherThreads) group_points_kernel(int c, int
 
 template <bool VEC>
 __global__ void __launch_bounds__(kGatherThreads) group_points_grad_kernel(int c, int n, long long per_cloud, int c_per_cta,
+                                                                             long long grad_cloud_stride,
                                                                              const float *__restrict__ grad_out,
                                                                              const int *__restrict__ idx,
                                                                              float *__restrict__ grad_points) {
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kGatherThreads) group_points_grad_kernel(int c
   if (e0 >= per_cloud) return;
   const int cb = blockIdx.z * c_per_cta, ce = min(c, cb + c_per_cta);
   const int *ip = idx + cloud * per_cloud + e0;
-  const float *g = grad_out + cloud * (size_t)c * per_cloud + e0;
+  const float *g = grad_out + cloud * (size_t)grad_cloud_stride + e0;   // a cloud's block may hold leading channels that carry no gradient
   float *dst = grad_points + cloud * (size_t)c * n;
   if (VEC) {
     const int4 id = __ldg(reinterpret_cast<const int4 *>(ip));
@@ -290,7 +291,8 @@ int channels_per_cta(long long ctas_without_split, int c) {
 }
 
 int group_dispatch(bool grad, int b, int c, int n, long long per_cloud, const float *a, const int *idx, float *o,
-                   cudaStream_t stream, const char *what) {
+                   cudaStream_t stream, const char *what, long long grad_cloud_stride = -1) {
+  if (grad_cloud_stride < 0) grad_cloud_stride = (long long)c * per_cloud;
   if (b < 0 || c < 0 || n < 0 || per_cloud < 0) return fail_arg(what);
   if (b == 0 || c == 0 || per_cloud == 0) return 0;
   if (!a || !idx || !o) return fail_arg(what);
@@ -305,8 +307,8 @@ int group_dispatch(bool grad, int b, int c, int n, long long per_cloud, const fl
     if (vec) group_points_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
     else group_points_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
   } else {
-    if (vec) group_points_grad_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
-    else group_points_grad_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, a, idx, o);
+    if (vec) group_points_grad_kernel<true><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, grad_cloud_stride, a, idx, o);
+    else group_points_grad_kernel<false><<<grid, kGatherThreads, 0, stream>>>(c, n, per_cloud, c_per_cta, grad_cloud_stride, a, idx, o);
   }
   return check_launch(what);
 }
@@ -598,6 +600,15 @@ WS3D_API int ws3d_group_points_grad(int b, int c, int n, int npoints, int nsampl
                                     const int *idx, float *grad_points, ws3d_stream_t stream) {
   return group_dispatch(true, b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points, to_stream(stream),
                         "group_points_grad");
+}
+
+WS3D_API int ws3d_group_concat_grad(int b, int n, int m, int c, int nsample, int use_xyz, const float *grad_out, const int *idx,
+                                    float *grad_features, ws3d_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || c < 0 || nsample < 0) return fail_arg("group_concat_grad");
+  const long long per_cloud = (long long)m * nsample;
+  const int lead = use_xyz ? 3 : 0;     // the coordinate channels of the grouped tensor carry no gradient
+  return group_dispatch(true, b, c, n, per_cloud, grad_out ? grad_out + (size_t)lead * per_cloud : nullptr, idx, grad_features,
+                        to_stream(stream), "group_concat_grad", (long long)(lead + c) * per_cloud);
 }
 
 WS3D_API int ws3d_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,

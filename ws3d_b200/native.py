@@ -56,6 +56,15 @@ def group_points_wrapper(b, c, n, npoints, nsample, points_tensor, idx_tensor, o
     return 1
 
 
+def group_concat_grad(b, n, m, c, nsample, use_xyz, grad_out, idx, grad_features):
+    """Gradient of group_concat with respect to the features, reading grad_out (B, 3*use_xyz + C, M, nsample) in place."""
+    lead = 3 if use_xyz else 0
+    require("group_concat_grad", (grad_out, F32, b * (lead + c) * m * nsample), (idx, I32, b * m * nsample), (grad_features, F32, b * c * n))
+    with device_of(grad_out):
+        check(lib().ws3d_group_concat_grad(b, n, m, c, nsample, int(bool(use_xyz)), ptr(grad_out), ptr(idx), ptr(grad_features), stream()),
+              "group_concat_grad")
+
+
 def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_tensor, grad_points_tensor):
     require("group_points_grad", (grad_out_tensor, F32, b * c * npoints * nsample), (idx_tensor, I32, b * npoints * nsample),
             (grad_points_tensor, F32, b * c * n))

@@ -238,9 +238,9 @@ class _GroupConcat(Function):
         grad_features = None
         if C > 0 and ctx.needs_input_grad[2]:
             B, _, M, K = grad_out.shape
-            g = grad_out[:, off:].contiguous()
             grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-            native.group_points_grad_wrapper(B, C, N, M, K, g, idx, grad_features)
+            # the coordinate channels are skipped by addressing: no contiguous copy of grad_out[:, 3:]
+            native.group_concat_grad(B, N, M, C, K, off == 3, grad_out.contiguous(), idx, grad_features)
         return None, None, grad_features, None, None
 
 

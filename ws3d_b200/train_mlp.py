@@ -132,15 +132,24 @@ class _TrainLayer(torch.autograd.Function):
                 native.mlp_wgrad(B, c_out, c2, cols, dy, x2, dw2d, c_in, c1)
             dw = dw2d.view_as(weight)
         dx1 = dx2 = None
-        if need[0] or (c2 and need[1]):
-            c_in_pad, k_pad = _ceil(c_in, _TILE_M), _ceil(c_out, _CHUNK_K)
-            wt = _buffer(ctx.conv, ("wt", c_in, c_out), (c_in_pad, k_pad), dev)
-            wt[:c_in, :c_out].copy_(weight.detach().reshape(c_out, c_in).t())
-            zero_shift = _buffer(ctx.conv, ("zst", c_in), (c_in_pad,), dev)
-            dx = torch.empty((B, c_in, cols), dtype=torch.float32, device=dev)
-            native.mlp_layer(B, c_in, c_in_pad, c_out, 0, cols, wt, zero_shift, dy, None, dx, 0, 0)
-            dx1 = dx[:, :c1] if need[0] else None
-            dx2 = dx[:, c1:] if (c2 and need[1]) else None
+        w2d = weight.detach().reshape(c_out, c_in)
+        k_pad = _ceil(c_out, _CHUNK_K)
+
+        def dgrad(lo: int, hi: int) -> torch.Tensor:
+            """dX[:, lo:hi] = W[:, lo:hi]^T dY as its own contiguous tensor (the two inputs of a feature-propagation layer get
+            one launch each: dY is read twice, but neither consumer has to copy a strided slice of a joint dX)."""
+            rows, rows_pad = hi - lo, _ceil(hi - lo, _TILE_M)
+            wt = _buffer(ctx.conv, ("wt", lo, hi, c_out), (rows_pad, k_pad), dev)
+            wt[:rows, :c_out].copy_(w2d[:, lo:hi].t())
+            zero_shift = _buffer(ctx.conv, ("zst", rows_pad), (rows_pad,), dev)
+            out = torch.empty((B, rows, cols), dtype=torch.float32, device=dev)
+            native.mlp_layer(B, rows, rows_pad, c_out, 0, cols, wt, zero_shift, dy, None, out, 0, 0)
+            return out
+
+        if need[0]:
+            dx1 = dgrad(0, c1)
+        if c2 and need[1]:
+            dx2 = dgrad(c1, c_in)
         return dx1, dx2, dw, dgamma, dbeta, dbias, None, None, None, None, None
 
 

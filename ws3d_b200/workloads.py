@@ -65,31 +65,60 @@ def single_sa_layer(dev, flush=None, iters: int = 20, npoint: int = 4096, radius
 
 
 # ---- config 3 -------------------------------------------------------------------------------------
+def _plan_tensors(plan: Dict):
+    out = list(plan["xyz"])
+    for scales in plan["idx"]:
+        out += [t for t in scales if t is not None]
+    for idx, w in plan["nn"]:
+        out += [idx, w]
+    out.append(plan["xyz0"])
+    if plan["feat0"] is not None:
+        out.append(plan["feat0"])
+    return out
+
+
 class RpnTrainStep:
-    """One Stage-1 training step on `batch` synthetic scenes per rank: RPN forward (training mode: batch statistics),
+    """Stage-1 training on `batch` synthetic scenes per rank and step: RPN forward (training mode: batch statistics),
     Gaussian labels on the GPU (label_utils), get_rpn_loss (train_functions), backward, the data-parallel
     gradient exchange (sharding.FlatGradients: ONE averaged all-reduce over NCCL, the path's only collective), Adam.
-    The whole step -- collective included -- is captured once and replayed as one CUDA graph (`graph=True`); BatchNorm
-    statistics stay per replica, as under the reference's DataParallel / DDP.  `exchange=False` leaves the collective out
-    (the all-reduce share of a step is measured as the difference)."""
+    BatchNorm statistics stay per replica, as under the reference's DataParallel / DDP.
 
-    def __init__(self, batch: int, dev, world: int = 1, rank: int = 0, graph: bool = True, lr: float = 2e-3, exchange: bool = True):
+    `prefetch=True` (default): sampling, ball queries and interpolation stencils depend on coordinates only
+    (Pointnet2MSG.coordinate_phase), so -- as a data loader knows the NEXT batch while the current one trains -- the
+    coordinate phase of batch k+1 runs on a side stream in throughput mode (one SM per cloud) beside step k's forward /
+    backward, and step k consumes the plan made during step k-1: the 2.7 ms latency chain of the samplers leaves the
+    critical path.  Two synthetic batches alternate; a call = TWO steps (A then B), captured once and replayed as one
+    CUDA graph (`graph=True`), collective included.  `exchange=False` leaves the collective out (the all-reduce share of
+    a step is measured as the difference).  `steps_per_call` tells the caller how many steps a call makes."""
+
+    def __init__(self, batch: int, dev, world: int = 1, rank: int = 0, graph: bool = True, lr: float = 2e-3, exchange: bool = True,
+                 prefetch: bool = True):
         from . import sharding
         torch.manual_seed(0)                      # identical initial replicas on every rank
         self.net = models.RPN().to(dev).train()
         self.model = self.net
         self.param_bytes = sum(p.numel() for p in self.net.parameters()) * 4
-        self.world, self.batch = world, batch
+        self.world, self.batch, self.dev = world, batch, dev
         self.grads = sharding.FlatGradients(self.net.parameters(), world=world)
         self.exchange = bool(exchange) and world > 1
         self.opt = torch.optim.Adam(self.net.parameters(), lr=lr, capturable=bool(graph))
-        self.pts = torch.from_numpy(synth.make_batch(batch, 16384, first_scene=rank * batch)).to(dev)
-        gt, cnt = synth.make_gt_boxes(batch, 16384, first_scene=rank * batch)
-        self.gt, self.gt_cnt = torch.from_numpy(gt).to(dev), torch.from_numpy(cnt).to(dev)
-        self.xyz = self.pts[..., :3].contiguous()
+        self.prefetch = bool(prefetch)
+        self.steps_per_call = 2 if self.prefetch else 1
+        self.data = []
+        for k in range(self.steps_per_call):
+            first = (2 * rank + k) * batch
+            pts = torch.from_numpy(synth.make_batch(batch, 16384, first_scene=first)).to(dev)
+            gt, cnt = synth.make_gt_boxes(batch, 16384, first_scene=first)
+            self.data.append({"pts": pts, "xyz": pts[..., :3].contiguous(), "gt": torch.from_numpy(gt).to(dev),
+                              "cnt": torch.from_numpy(cnt).to(dev), "plan": None})
         self.terms = None
         self._graph = None
         self.graphed = False
+        self._side = torch.cuda.Stream(device=dev) if self.prefetch else None
+        if self.prefetch:
+            self.data[0]["plan"] = self._coordinate_phase(self.data[0]["pts"])
+            self.data[1]["plan"] = self._coordinate_phase(self.data[1]["pts"])
+            torch.cuda.synchronize()
         if graph:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -103,16 +132,41 @@ class RpnTrainStep:
                 self._static_loss = self._eager()
             self.graphed = True
 
-    def _eager(self):
-        out = self.model({"pts_input": self.pts})
+    def _coordinate_phase(self, pts):
         with torch.no_grad():
-            cls_label, reg_label = label_utils.generate_gaussian_training_labels(self.xyz, self.gt, self.gt_cnt)
+            prev = native.set_fps_mode(1)          # throughput mode: one SM per cloud, beside the step's wide kernels
+            try:
+                return self.net.backbone_net.coordinate_phase(pts)
+            finally:
+                native.set_fps_mode(prev)
+
+    def _one_step(self, d, plan):
+        out = self.model({"pts_input": d["pts"]}, plan=plan)
+        with torch.no_grad():
+            cls_label, reg_label = label_utils.generate_gaussian_training_labels(d["xyz"], d["gt"], d["cnt"])
         loss, self.terms = train_functions.get_rpn_loss(out["rpn_cls"], out["rpn_reg"], cls_label, reg_label)
         self.grads.zero()
         loss.backward()
         if self.exchange:
             self.grads.exchange()
         self.opt.step()
+        return loss
+
+    def _eager(self):
+        if not self.prefetch:
+            return self._one_step(self.data[0], None)
+        main = torch.cuda.current_stream(self.dev)
+        loss = None
+        for cur, nxt in ((0, 1), (1, 0)):
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                fresh = self._coordinate_phase(self.data[nxt]["pts"])          # what the NEXT step will consume
+            loss = self._one_step(self.data[cur], self.data[cur]["plan"])
+            main.wait_stream(self._side)
+            with torch.no_grad():   # hand-over into the buffers the next step (and the next replay) reads
+                for dst, src in zip(_plan_tensors(self.data[nxt]["plan"]), _plan_tensors(fresh)):
+                    dst.copy_(src)
+                    src.record_stream(main)
         return loss
 
     def __call__(self):
