@@ -14,6 +14,9 @@
 // Tried and not kept (measured, B = 32, FP0): a warp per block of 16 lists with lane = entry and a segmented shuffle scan -- perfectly
 // balanced, but 127 instructions per 32 entries x 3 channels (17 SHFL + 15 FADD + the segment bookkeeping) made it issue-bound
 // (80 % issue-active, 1.05 ms against 0.89 ms for the unsorted one-thread-per-list form at 5 of 32 lanes active).
+// Also measured: group_points_grad through the same machinery (lists = the grouped slots of every source point, weight 1).  Its rows
+// are npoint x nsample floats (128 KB at SA2), so one channel fills a CTA's shared memory and the lists are re-read per channel:
+// 1.76 ms against 0.70 ms for the atomic scatter over the six launches of a training step -- the grouping gradient keeps atomics.
 //
 // Clouds whose inverse does not fit the one-CTA-per-cloud builder (m > kMaxKnown) or whose rows do not fit shared memory
 // (n > kMaxRow) keep the atomic kernel in pointnet2_ops.cu.
@@ -33,7 +36,9 @@ constexpr int kStageBudget = 96 * 1024;   // bytes of staged rows per CTA when s
 struct __align__(8) Entry { int key; float w; };   // key = 3 i + k in the unsorted buffer, i in the sorted one
 
 // One CTA per cloud: count -> exclusive scan -> fill -> per-list sort by (i, k).
-__global__ void __launch_bounds__(kBuildThreads) stencil_inverse_kernel(int n, int m, const int *__restrict__ idx,
+// `total` entries per cloud; entry e refers to row element e / div (div = 3: the three neighbours of an unknown point; div = 1:
+// one grouped slot); weight == nullptr means weight 1 (grouping).
+__global__ void __launch_bounds__(kBuildThreads) stencil_inverse_kernel(int total, int m, int div, const int *__restrict__ idx,
                                                                         const float *__restrict__ weight, int *__restrict__ off_g,
                                                                         Entry *__restrict__ ent_g, Entry *__restrict__ out_g,
                                                                         unsigned short *__restrict__ order_g) {
@@ -42,11 +47,11 @@ __global__ void __launch_bounds__(kBuildThreads) stencil_inverse_kernel(int n, i
   int *cur = sm_i + (m + 1);   // m
   __shared__ int warp_tot[kBuildThreads / 32];
   const size_t cloud = blockIdx.x;
-  const int *ip = idx + cloud * (size_t)n * 3;
-  const float *wp = weight + cloud * (size_t)n * 3;
+  const int *ip = idx + cloud * (size_t)total;
+  const float *wp = weight ? weight + cloud * (size_t)total : nullptr;
   int *off = off_g + cloud * (size_t)(m + 1);
-  Entry *ent = ent_g + cloud * (size_t)n * 3;
-  const int t = threadIdx.x, total = 3 * n;
+  Entry *ent = ent_g + cloud * (size_t)total;
+  const int t = threadIdx.x;
   for (int j = t; j <= m; j += kBuildThreads) cnt[j] = 0;
   __syncthreads();
   for (int e = t; e < total; e += kBuildThreads) {
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(kBuildThreads) stencil_inverse_kernel(int n, i
       const int slot = atomicAdd(&cur[j], 1);
       Entry en;
       en.key = e;
-      en.w = __ldg(wp + e);
+      en.w = wp ? __ldg(wp + e) : 1.0f;
       ent[slot] = en;
     }
   }
@@ -138,9 +143,9 @@ __global__ void __launch_bounds__(kBuildThreads) stencil_inverse_kernel(int n, i
       int rank = 0;
       for (int q = 0; q < L; ++q) rank += (ent[b + q].key < x.key) ? 1 : 0;
       Entry y;
-      y.key = x.key / 3;
+      y.key = x.key / div;
       y.w = x.w;
-      out_g[cloud * (size_t)n * 3 + b + rank] = y;
+      out_g[cloud * (size_t)total + b + rank] = y;
     }
   }
 }
@@ -164,7 +169,8 @@ __device__ __forceinline__ void red_add(float *p, float v) {
 // offsets and the order of the cloud sit in shared memory next to the rows, and the entries of a list are fetched four at a time
 // so that one L2 latency covers four of them.
 template <int G>
-__global__ void __launch_bounds__(kMaxGatherThreads) interp_grad_gather_kernel(int c, int n, int m, int chunk,
+__global__ void __launch_bounds__(kMaxGatherThreads) interp_grad_gather_kernel(int c, int n, int m, int chunk, int total,
+                                                                               long long grad_cloud_stride,
                                                                                const float *__restrict__ grad_out,
                                                                                const int *__restrict__ off_g,
                                                                                const Entry *__restrict__ ent_g,
@@ -187,8 +193,8 @@ __global__ void __launch_bounds__(kMaxGatherThreads) interp_grad_gather_kernel(i
     for (int j = threadIdx.x; j < m; j += blockDim.x) order[j] = __ldg(rg + j);
   }
   __syncthreads();
-  stage_floats(rows, grad_out + (cloud * (size_t)c + c0) * n, chs * n, &bar, 0);
-  const Entry *ent = ent_g + cloud * (size_t)n * 3;
+  stage_floats(rows, grad_out + cloud * (size_t)grad_cloud_stride + (size_t)c0 * n, chs * n, &bar, 0);
+  const Entry *ent = ent_g + cloud * (size_t)total;
   float *out = grad_points + (cloud * (size_t)c + c0) * m;
   const int groups = (chs + G - 1) / G;
   for (int item = threadIdx.x; item < groups * m; item += blockDim.x) {
@@ -228,8 +234,10 @@ __global__ void __launch_bounds__(kMaxGatherThreads) interp_grad_gather_kernel(i
 
 // Returns 0 when the gather path ran, 1 when the shape is outside its limits (the caller falls back to the atomic kernel),
 // or a cudaError code.
-int three_interpolate_grad_gather(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
-                                  float *grad_points, cudaStream_t stream) {
+// Generic form: out[b, ch, idx[b, e]] += weight[b, e] * grad_out[b, ch, e / div] for e < total, rows of n = total / div floats,
+// m targets per cloud; a cloud's rows start grad_cloud_stride floats apart (rows of one cloud are contiguous).
+int scatter_as_gather(int b, int c, int n, int total, int div, int m, const float *grad_out, long long grad_cloud_stride, const int *idx,
+                      const float *weight, float *grad_points, cudaStream_t stream, const char *what) {
   static_assert(kMaxKnown <= 65536, "the length order stores list numbers in 16 bits");
   if (m < 1 || m > kMaxKnown || n < 1 || n > kMaxRow) return 1;
   // channels per CTA and per work item
@@ -254,7 +262,7 @@ int three_interpolate_grad_gather(int b, int c, int n, int m, const float *grad_
   }
   if (b > 65535 || ceil_div(c, chunk) > 0x7fffffff) return 1;
   const size_t off_bytes = ((size_t)b * (m + 1) * sizeof(int) + 255) & ~(size_t)255;
-  const size_t ent_bytes = (size_t)b * n * 3 * sizeof(Entry);
+  const size_t ent_bytes = (size_t)b * total * sizeof(Entry);
   const size_t order_bytes = ((size_t)b * m * sizeof(unsigned short) + 255) & ~(size_t)255;
   char *ws = (char *)scratch(off_bytes + 2 * ent_bytes + order_bytes, 7);
   if (!ws) return (int)cudaErrorMemoryAllocation;
@@ -275,18 +283,24 @@ int three_interpolate_grad_gather(int b, int c, int n, int m, const float *grad_
     cudaFuncSetAttribute(interp_grad_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     attr_done = true;
   }
-  stencil_inverse_kernel<<<b, kBuildThreads, build_smem, stream>>>(n, m, idx, weight, off, unsorted, ent, order);
-  int rc = check_launch("three_interpolate_grad (stencil inverse)");
+  stencil_inverse_kernel<<<b, kBuildThreads, build_smem, stream>>>(total, m, div, idx, weight, off, unsorted, ent, order);
+  int rc = check_launch(what);
   if (rc) return rc;
   dim3 grid((unsigned)ceil_div(c, chunk), (unsigned)b);
   const size_t smem = (size_t)chunk * n * sizeof(float) + off_smem;
   switch (G) {
-    case 1: interp_grad_gather_kernel<1><<<grid, threads, smem, stream>>>(c, n, m, chunk, grad_out, off, ent, order, grad_points); break;
-    case 2: interp_grad_gather_kernel<2><<<grid, threads, smem, stream>>>(c, n, m, chunk, grad_out, off, ent, order, grad_points); break;
-    case 3: interp_grad_gather_kernel<3><<<grid, threads, smem, stream>>>(c, n, m, chunk, grad_out, off, ent, order, grad_points); break;
-    default: interp_grad_gather_kernel<4><<<grid, threads, smem, stream>>>(c, n, m, chunk, grad_out, off, ent, order, grad_points); break;
+    case 1: interp_grad_gather_kernel<1><<<grid, threads, smem, stream>>>(c, n, m, chunk, total, grad_cloud_stride, grad_out, off, ent, order, grad_points); break;
+    case 2: interp_grad_gather_kernel<2><<<grid, threads, smem, stream>>>(c, n, m, chunk, total, grad_cloud_stride, grad_out, off, ent, order, grad_points); break;
+    case 3: interp_grad_gather_kernel<3><<<grid, threads, smem, stream>>>(c, n, m, chunk, total, grad_cloud_stride, grad_out, off, ent, order, grad_points); break;
+    default: interp_grad_gather_kernel<4><<<grid, threads, smem, stream>>>(c, n, m, chunk, total, grad_cloud_stride, grad_out, off, ent, order, grad_points); break;
   }
-  return check_launch("three_interpolate_grad (gather)");
+  return check_launch(what);
+}
+
+int three_interpolate_grad_gather(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                                  float *grad_points, cudaStream_t stream) {
+  if ((long long)n * 3 > 0x3fffffffLL) return 1;
+  return scatter_as_gather(b, c, n, 3 * n, 3, m, grad_out, (long long)c * n, idx, weight, grad_points, stream, "three_interpolate_grad (gather)");
 }
 
 }  // namespace ws3d
