@@ -250,6 +250,12 @@ int ws3d_mlp_wgrad(int b, int c_out, int c_in, int cols, const float *dy, const 
 int ws3d_split_pointcloud(int b, int n, int c, const float *pc, float *xyz, float *features,
                           ws3d_stream_t stream);
 
+/* Extension: the opposite packing -- xyz (B,N,3) and channel-major features (B,C,N) (NULL when C == 0) -> point-major
+ * rows (B,N,ld) = [xyz | features | zeros], ld >= 3 + C: the operand layout ws3d_sa_mlp_fused_rows gathers from
+ * (what `pts[..., 3:].transpose(1, 2)` in lib/net/rcnn_net.py undoes for the pooled Stage-2 input). */
+int ws3d_pack_rows(int b, int n, int c, int ld, const float *xyz, const float *features, float *rows,
+                   ws3d_stream_t stream);
+
 /* Extension (complete form): ONE set-abstraction scale in one kernel --
  * QueryAndGroup's grouping (pointnet2_utils.py:241-264, use_xyz = True), the three SharedMLP layers
  * (pytorch_utils.py:5-32: conv1x1 + BatchNorm(eval, folded) + ReLU) and the max-pool over nsample

@@ -387,3 +387,36 @@ def test_fused_sa_point_major_rows_path_is_bit_identical():
         a = sa(x5, f5)
         b = sa(x5, f5, rows=pts5, want_rows=True)
         assert torch.equal(a[1], b[1]) and torch.equal(b[2][..., 3:99], b[1].transpose(1, 2))
+
+
+def test_pack_rows_and_stage2_stack_chain_equal_module_by_module():
+    """pack_rows = [xyz | features^T | zeros] exactly; the Stage-2 stack through sa_stack_forward (rows packed once, fused
+    levels hand point-major rows to each other) returns what the modules return one after the other on channel-major
+    features (WS3D_SA_ROWS=0), bit for bit: the gather source changes, not the values."""
+    import os
+
+    from ws3d_b200 import pointnet2_utils, workloads
+    from ws3d_b200.pointnet2_modules import sa_stack_forward
+    torch.manual_seed(0)
+    B, N, C = 24, 512, 128
+    rng = np.random.default_rng(5)
+    xyz = torch.from_numpy((rng.normal(0, 1, (B, N, 3)) * np.array([1.2, 0.6, 2.2])).astype(np.float32)).to(dev)
+    feats = torch.randn(B, C, N, device=dev)
+    rows = pointnet2_utils.pack_rows(xyz, feats)
+    assert rows.shape == (B, N, 136)
+    want = torch.cat([xyz, feats.transpose(1, 2), torch.zeros(B, N, 136 - 3 - C, device=dev)], dim=2)
+    assert torch.equal(rows, want)
+    odd = pointnet2_utils.pack_rows(xyz[:, :77].contiguous(), feats[:, :5, :77].contiguous())       # ragged tiles
+    assert torch.equal(odd, torch.cat([xyz[:, :77], feats[:, :5, :77].transpose(1, 2)], dim=2))
+    assert torch.equal(pointnet2_utils.pack_rows(xyz, None)[..., :3], xyz)
+    model = workloads.Stage2SA().to(dev).eval()
+    with torch.no_grad():
+        got = sa_stack_forward(model.SA_modules, xyz, feats)[1]
+        os.environ["WS3D_SA_ROWS"] = "0"
+        try:
+            x, f = xyz, feats
+            for sa in model.SA_modules:
+                x, f = sa(x, f)
+        finally:
+            os.environ.pop("WS3D_SA_ROWS", None)
+    assert torch.equal(got, f)

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ws3d_b200 import _C  # noqa: E402
-from ws3d_b200.pointnet2_modules import PointnetSAModule  # noqa: E402
+from ws3d_b200.pointnet2_modules import PointnetSAModule, sa_stack_forward  # noqa: E402
 
 SA = {"NPOINTS": [256, 128, 32, -1], "RADIUS": [0.2, 0.4, 1.0, 100.0], "NSAMPLE": [16, 32, 64, 64],
       "MLPS": [[128, 128, 128], [128, 128, 128], [128, 128, 256], [256, 256, 512]]}
@@ -34,9 +34,7 @@ class Stage2SA(nn.Module):
             channel_in = SA["MLPS"][k][-1]
 
     def forward(self, xyz, features):
-        for sa in self.SA_modules:
-            xyz, features = sa(xyz, features)
-        return features
+        return sa_stack_forward(self.SA_modules, xyz, features)[1]
 
 
 def main():

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "ws3d_ball_query2": [_i, _i, _i, _f, _i, _f, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_group_points": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "ws3d_pack_rows": [_i, _i, _i, _i, _vp, _vp, _vp],
     "ws3d_group_concat_grad": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_query_and_group": [_i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ws3d_group_concat": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],

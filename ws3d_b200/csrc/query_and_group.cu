@@ -233,8 +233,44 @@ __global__ void __launch_bounds__(256) split_pointcloud_kernel(int n, int c, con
   x[0] = __ldg(p); x[1] = __ldg(p + 1); x[2] = __ldg(p + 2);
   for (int k = 0; k < c; ++k) feat[(cloud * (size_t)c + k) * n + i] = __ldg(p + 3 + k);
 }
+
+// The inverse direction: xyz (B,N,3) + channel-major features (B,C,N) -> point-major rows (B,N,ld) = [xyz | features | zeros], the
+// operand layout the fused set-abstraction kernel gathers from (one contiguous row per neighbour instead of one 32-byte sector per
+// channel).  32 x 32 tiles through shared memory: reads are coalesced along the points, writes along the row.
+__global__ void __launch_bounds__(256) pack_rows_kernel(int n, int c, int ld, const float *__restrict__ xyz, const float *__restrict__ feat,
+                                                        float *__restrict__ rows) {
+  __shared__ float tile[32][33];
+  const size_t cloud = blockIdx.z;
+  const int i0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int q = q0 + ty + r, i = i0 + tx;     // column q of the row of point i
+    float v = 0.f;
+    if (i < n) {
+      if (q < 3) v = __ldg(xyz + (cloud * (size_t)n + i) * 3 + q);
+      else if (q < 3 + c) v = __ldg(feat + (cloud * (size_t)c + (q - 3)) * n + i);
+    }
+    tile[ty + r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const int i = i0 + ty + r, q = q0 + tx;
+    if (i < n && q < ld) rows[(cloud * (size_t)n + i) * ld + q] = tile[tx][ty + r];
+  }
+}
 }  // namespace
 }  // namespace ws3d
+
+WS3D_API int ws3d_pack_rows(int b, int n, int c, int ld, const float *xyz, const float *features, float *rows, ws3d_stream_t stream) {
+  if (b < 0 || n < 0 || c < 0 || ld < 3 + c || b > 65535) return fail_arg("pack_rows");
+  if (b == 0 || n == 0) return 0;
+  if (!xyz || !rows || (c > 0 && !features)) return fail_arg("pack_rows (null pointer)");
+  pack_rows_kernel<<<dim3((unsigned)ceil_div(n, 32), (unsigned)ceil_div(ld, 32), (unsigned)b), 256, 0, to_stream(stream)>>>(n, c, ld, xyz,
+                                                                                                                        features, rows);
+  return check_launch("pack_rows");
+}
 
 WS3D_API int ws3d_split_pointcloud(int b, int n, int c, const float *pc, float *xyz, float *features, ws3d_stream_t stream) {
   if (b < 0 || n < 0 || c < 0 || b > 65535) return fail_arg("split_pointcloud");

@@ -31,7 +31,7 @@ namespace ws3d {
 namespace {
 
 constexpr int kRows = 128;          // grouped points per tile (UMMA M)
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;      // per half: a CTA has kThreads x kHalves threads (see the kernel)
 
 struct SaFusedParams {
   int n, m, ns, c_feat;          // points per cloud, centres per cloud, nsample, feature channels
@@ -133,8 +133,14 @@ __device__ __forceinline__ float pool_scatter(float (&v)[G], int lane) {
 
 // kBatch feature channels are fetched per thread before they are stored to TMEM (independent loads in flight);
 // the wide variant (64) is for the scales whose TMEM / shared-memory footprint allows two CTAs per SM anyway.
-template <int kBatch, int kMinCtas>
-__global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
+// kHalves = 2 / 4 (256 / 512 threads) is for the shapes whose resident weights leave ONE CTA per SM (the Stage-2 widths: 208 KB):
+// with four warps every scheduler of the SM would own a single warp and idle through each of its stalls (ncu: 6 % of the warp
+// slots active, 18 % issue-active).  Warps w, w + 4, ... share a TMEM lane quarter and split every per-row phase by columns -- the
+// row's gather, the two in-place epilogues, the pooling groups, the output loops -- so each phase has kHalves times the warps to
+// issue from and to hide latency behind; barriers and the MMA issue are unchanged.  Measured on the Stage-2 stack (512 proposals):
+// 2.84 ms with 128 threads, 2.52 with 256, 2.42 with 512.
+template <int kBatch, int kMinCtas, int kHalves>
+__global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
                                                                    const __grid_constant__ CUtensorMap map_w2,
                                                                    const __grid_constant__ CUtensorMap map_w3,
                                                                    const SaFusedParams prm) {
@@ -142,7 +148,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
   __shared__ __align__(8) unsigned long long s_bar_w, s_bar_d;
   __shared__ uint32_t s_tmem_base;
 
+  constexpr int kT = kThreads * kHalves;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = kHalves > 1 ? (int)(threadIdx.x >> 7) : 0;       // which of the kHalves column shares this thread takes
   const uint32_t w_base = (smem_u32(s_raw) + 1023u) & ~1023u;      // 128B-swizzle atoms need 1 KB alignment
   const uint32_t w1 = w_base, w2 = w1 + (uint32_t)prm.nk1 * prm.n1 * 128u, w3 = w2 + (uint32_t)prm.nk2 * prm.n2 * 128u;
   const uint32_t w_end = w3 + (uint32_t)prm.nk3 * prm.n3 * 128u;
@@ -158,10 +166,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
     mbar_init(bar_d, 1);    // tcgen05.commit
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < prm.n1; i += kThreads) s_shift[i] = __ldg(prm.shift1 + i);
-  for (int i = threadIdx.x; i < prm.n2; i += kThreads) s_shift[prm.n1 + i] = __ldg(prm.shift2 + i);
-  for (int i = threadIdx.x; i < prm.n3; i += kThreads) s_shift[prm.n1 + prm.n2 + i] = __ldg(prm.shift3 + i);
-  for (int i = threadIdx.x; i < prm.c3 * cpt; i += kThreads) s_pool[i] = 0u;
+  for (int i = threadIdx.x; i < prm.n1; i += kT) s_shift[i] = __ldg(prm.shift1 + i);
+  for (int i = threadIdx.x; i < prm.n2; i += kT) s_shift[prm.n1 + i] = __ldg(prm.shift2 + i);
+  for (int i = threadIdx.x; i < prm.n3; i += kT) s_shift[prm.n1 + prm.n2 + i] = __ldg(prm.shift3 + i);
+  for (int i = threadIdx.x; i < prm.c3 * cpt; i += kT) s_pool[i] = 0u;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(prm.tmem_cols)
                  : "memory");
@@ -203,8 +211,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
   };
 
   // ---- thread = one grouped point (TMEM lane)
-  const int row = threadIdx.x;                        // 0..127
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int row = threadIdx.x & (kRows - 1);          // 0..127 (both halves)
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const int ns = prm.ns;
   const int cols = prm.m * ns;                        // grouped points per cloud
   const int n = prm.n, c_feat = prm.c_feat;
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
       const float4 *rp = reinterpret_cast<const float4 *>(prm.rows + ((size_t)cloud * n + p) * prm.ld);
       const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
       const float cx = __ldg(pc), cy = __ldg(pc + 1), cz = __ldg(pc + 2);
-      for (int c0 = 0; c0 < prm.k0; c0 += kBatch) {
+      for (int c0 = half * kBatch; c0 < prm.k0; c0 += kBatch * kHalves) {     // the halves take alternate column batches
         uint32_t v[kBatch];
 #pragma unroll
         for (int t = 0; t < kBatch; t += 4) {
@@ -261,20 +269,23 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
       const float *px = prm.xyz + ((size_t)cloud * n + p) * 3;
       const float *pc = prm.new_xyz + ((size_t)cloud * prm.m + j) * 3;
       const float *pf = prm.feat + (size_t)cloud * c_feat * n;     // not dereferenced when c_feat == 0
-      uint32_t r[8];
-      unsigned off = (unsigned)p;                     // index of (channel, point p) in this cloud's features
-      // first group: 3 coordinates + channels 0..4 (raw FP32 features: the tensor core truncates to TF32)
+      if (half == 0) {
+        uint32_t r[8];
+        unsigned off = (unsigned)p;                   // index of (channel, point p) in this cloud's features
+        // first group: 3 coordinates + channels 0..4 (raw FP32 features: the tensor core truncates to TF32)
 #pragma unroll
-      for (int t = 0; t < 5; ++t) {
-        r[3 + t] = t < c_feat ? __float_as_uint(__ldg(pf + off)) : 0u;
-        off += (unsigned)n;
+        for (int t = 0; t < 5; ++t) {
+          r[3 + t] = t < c_feat ? __float_as_uint(__ldg(pf + off)) : 0u;
+          off += (unsigned)n;
+        }
+        r[0] = round_tf32(__fsub_rn(__ldg(px), __ldg(pc)));
+        r[1] = round_tf32(__fsub_rn(__ldg(px + 1), __ldg(pc + 1)));
+        r[2] = round_tf32(__fsub_rn(__ldg(px + 2), __ldg(pc + 2)));
+        tmem_st8(lane_addr + (uint32_t)prm.tm_a0, r);
       }
-      r[0] = round_tf32(__fsub_rn(__ldg(px), __ldg(pc)));
-      r[1] = round_tf32(__fsub_rn(__ldg(px + 1), __ldg(pc + 1)));
-      r[2] = round_tf32(__fsub_rn(__ldg(px + 2), __ldg(pc + 2)));
-      tmem_st8(lane_addr + (uint32_t)prm.tm_a0, r);
-      // then kBatch channels (independent loads) at a time; the last batch is predicated / zero padded
-      for (int ch = 5; ch + 3 < prm.k0; ch += kBatch) {
+      // then kBatch channels (independent loads) at a time; the last batch is predicated / zero padded; the halves alternate
+      for (int ch = 5 + half * kBatch; ch + 3 < prm.k0; ch += kBatch * kHalves) {
+        unsigned off = (unsigned)p + (unsigned)ch * (unsigned)n;
         uint32_t v[kBatch];
         if (ch + kBatch <= c_feat) {
 #pragma unroll
@@ -306,6 +317,23 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
       ++phase_d;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t ra[16], rb[16];
+      if (kHalves > 1) {
+        // kHalves warps per lane quarter: each takes every kHalves-th group of 16 columns (the second warp of the scheduler covers the
+        // TMEM round trip of the first, so no software pipelining inside a thread)
+        for (int c0 = 16 * half; c0 < nl; c0 += 16 * kHalves) {
+          tmem_ld16(acc + (uint32_t)c0, ra);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 16; t += 4) {
+            const float4 s4 = sh[(c0 + t) >> 2];
+            ra[t] = __float_as_uint(fmaxf(__uint_as_float(ra[t]) + s4.x, 0.f)) + 0x1000u;
+            ra[t + 1] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 1]) + s4.y, 0.f)) + 0x1000u;
+            ra[t + 2] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 2]) + s4.z, 0.f)) + 0x1000u;
+            ra[t + 3] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 3]) + s4.w, 0.f)) + 0x1000u;
+          }
+          tmem_st16(acc + (uint32_t)c0, ra);
+        }
+      } else {
       tmem_ld16(acc, ra);
       for (int c0 = 0; c0 < nl; c0 += 32) {
         tmem_ld_wait();
@@ -333,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
           tmem_st16(acc + (uint32_t)(c0 + 16), rb);
         }
       }
+      }
       if (l == 0) issue_layer(w2, prm.n2, prm.n1, (uint32_t)prm.tm_r1, (uint32_t)prm.tm_r2);
       else issue_layer(w3, prm.n3, prm.n2, (uint32_t)prm.tm_r2, (uint32_t)prm.tm_r3);
     }
@@ -349,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
       int c0 = 0;
       if (ns >= 32) {
         for (; c0 + 32 <= prm.n3; c0 += 32) {
+          if (kHalves > 1 && ((c0 >> 5) & (kHalves - 1)) != half) continue;     // warp-uniform: the shares take alternate channel groups
           uint32_t ra[16], rb[16];
           tmem_ld16(acc + (uint32_t)c0, ra);
           tmem_ld16(acc + (uint32_t)(c0 + 16), rb);
@@ -366,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
         }
       }
       for (; c0 < prm.n3; c0 += 16) {
+        if (kHalves > 1 && ((c0 >> 4) & (kHalves - 1)) != half) continue;
         uint32_t ra[16];
         tmem_ld16(acc + (uint32_t)c0, ra);
         tmem_ld_wait();
@@ -389,13 +420,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
       if (prm.out_pm) {
         // the same pooled values once more, point-major, for the next level's gather (channels fastest: coalesced)
         float *base = prm.out_pm + ((size_t)cloud * prm.m + centre0) * prm.ld_pm;
-        for (int i = row; i < cpt * prm.c3; i += kThreads) {
+        for (int i = (int)threadIdx.x; i < cpt * prm.c3; i += kT) {
           const int k = i / prm.c3, c = i - k * prm.c3;
           if (centre0 + k < prm.m) base[(size_t)k * prm.ld_pm + 3 + prm.out_coff + c] = __uint_as_float(s_pool[c * cpt + k]);
         }
         if (prm.pm_xyz) {   // this scale also writes the centre coordinates and the zero padding behind the channels
           const int tail0 = 3 + prm.out_ctot, per = 3 + (prm.ld_pm - tail0);
-          for (int i = row; i < cpt * per; i += kThreads) {
+          for (int i = (int)threadIdx.x; i < cpt * per; i += kT) {
             const int k = i / per, q = i - k * per;
             if (centre0 + k < prm.m) {
               if (q < 3) base[(size_t)k * prm.ld_pm + q] = __ldg(prm.new_xyz + ((size_t)cloud * prm.m + centre0 + k) * 3 + q);
@@ -405,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sa_mlp_fused_kernel(const 
         }
         if (ns > 32) __syncthreads();   // the loop below clears s_pool rows other threads have just read
       }
-      for (int c = row; c < prm.c3; c += kThreads) {
+      for (int c = (int)threadIdx.x; c < prm.c3; c += kT) {
         float *dst = prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + c) * prm.m + centre0;
         unsigned int *src = s_pool + c * cpt;
         if (cpt % 4 == 0 && centre0 + cpt <= prm.m && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
@@ -553,12 +584,20 @@ static int sa_mlp_fused_impl(int b, int n, int m, int nsample, int c_feat, const
       !weight_map(&m3, w3, pl.n3, pl.nk3 * 32))
     return (int)cudaErrorInvalidValue;
   const bool wide = pl.ctas_per_sm <= 2 && c_feat > 37;
-  auto kern = wide ? sa_mlp_fused_kernel<64, 2> : sa_mlp_fused_kernel<32, 4>;
+  // one CTA per SM (resident weights > half the shared memory): four column shares, 512 threads; WS3D_SA_HALVES=1|2|4 overrides (A/B runs)
+  static const int env_halves = [] { const char *e = getenv("WS3D_SA_HALVES"); return e && *e ? atoi(e) : -1; }();
+  int halves = pl.ctas_per_sm == 1 ? 4 : 1;
+  if (pl.ctas_per_sm == 1 && (env_halves == 1 || env_halves == 2 || env_halves == 4)) halves = env_halves;
+  // (two CTAs per SM x 256 threads was measured for the SA2 shapes: 0.305 ms either way -- they stay at 128 threads)
+  auto kern = halves == 4 ? sa_mlp_fused_kernel<32, 1, 4>
+              : halves == 2 ? sa_mlp_fused_kernel<64, 1, 2>
+              : wide        ? sa_mlp_fused_kernel<64, 2, 1>
+                            : sa_mlp_fused_kernel<32, 4, 1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) { set_error("sa_mlp_fused: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   const int pc = persistent_ctas(pl.ctas_per_sm);
   const int ctas = (int)(tiles < (long long)pc ? tiles : (long long)pc);
-  kern<<<ctas, kThreads, pl.smem, to_stream(stream)>>>(m1, m2, m3, prm);
+  kern<<<ctas, kThreads * halves, pl.smem, to_stream(stream)>>>(m1, m2, m3, prm);
   return check_launch(what);
 }
 

@@ -215,6 +215,18 @@ def split_pointcloud(pc, xyz, features):
         check(lib().ws3d_split_pointcloud(b, n, c, ptr(pc), ptr(xyz), ptr(features), stream()), "split_pointcloud")
 
 
+def pack_rows(xyz, features, rows):
+    """Extension: xyz (B,N,3) + features (B,C,N) or None -> rows (B,N,ld) = [xyz | features | zeros], point-major."""
+    b, n = xyz.size(0), xyz.size(1)
+    c = 0 if features is None else features.size(1)
+    ld = rows.size(2)
+    require("pack_rows", (xyz, F32, b * n * 3), (features, F32, b * c * n), (rows, F32, b * n * ld))
+    if ld < 3 + c:
+        raise RuntimeError("pack_rows: rows must hold 3 + C columns")
+    with device_of(xyz):
+        check(lib().ws3d_pack_rows(b, n, c, ld, ptr(xyz), ptr(features), ptr(rows), stream()), "pack_rows")
+
+
 # ---- iou3d_cuda -------------------------------------------------------------------------------
 def _bev(what, boxes):
     """(N, 5) float32 CUDA BEV boxes, the reference's CHECK_INPUT (iou3d.cpp:10-12) plus dtype / shape."""

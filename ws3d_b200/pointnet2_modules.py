@@ -120,6 +120,11 @@ class _PointnetSAModuleBase(nn.Module):
                 cache = self.__dict__.setdefault("_fused_scales", {})
                 widths = [mlp[-1].conv.out_channels for mlp in self.mlps]
                 out = torch.empty((xyz.shape[0], sum(widths), new_xyz.shape[1]), dtype=torch.float32, device=xyz.device)
+                if rows is None and c_feat >= 4 and os.environ.get("WS3D_SA_ROWS", "1") != "0":
+                    # channel-major features only: one transposing pass builds the point-major operand rows; every point is
+                    # gathered npoint * nsample / N times (8 - 12 at the WS3D shapes), each time as ONE contiguous row instead
+                    # of c_feat separate 32-byte sectors (Stage-2 level 1: 8.8 GB -> 1.1 GB of L2 traffic per launch)
+                    rows = pointnet2_utils.pack_rows(xyz, features)
                 if rows is not None and not (rows.is_contiguous() and rows.shape[-1] % 4 == 0 and rows.shape[-1] >= 3 + c_feat
                                              and rows.data_ptr() % 16 == 0 and os.environ.get("WS3D_SA_ROWS", "1") != "0"):
                     rows = None
@@ -246,6 +251,29 @@ class PointnetSAModule(PointnetSAModuleMSG):
                  bn: bool = True, use_xyz: bool = True, pool_method='max_pool', instance_norm=False):
         super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample], bn=bn, use_xyz=use_xyz,
                          pool_method=pool_method, instance_norm=instance_norm)
+
+
+def sa_stack_forward(sa_modules, xyz: torch.Tensor, features: Optional[torch.Tensor]):
+    """A chain of set-abstraction levels (the four levels of the Stage-2 network, lib/net/rcnn_net.py:40-58 / its forward loop)
+    -> (xyz, features) of the last one.  Same results as calling the modules one after the other; in inference a level that
+    runs as the fused kernel also hands its output to the next fused level as point-major operand rows, so only the first
+    level packs rows from the channel-major input."""
+    mods = list(sa_modules)
+    rows = None
+    for k, sa in enumerate(mods):
+        c_out = sum(m[-1].conv.out_channels for m in sa.mlps)
+        c_in = 0 if features is None else features.shape[1]
+        chain = (fused_mlp.enabled_for(sa) and xyz.is_cuda and sa.fused_scales_eligible(c_in) and k + 1 < len(mods)
+                 and mods[k + 1].fused_scales_eligible(c_out))
+        if chain:
+            if rows is None and c_in >= 4:
+                rows = pointnet2_utils.pack_rows(xyz, features)
+            if rows is not None:
+                xyz, features, rows = sa(xyz, features, rows=rows, want_rows=True)
+                continue
+        xyz, features = sa(xyz, features, rows=rows)
+        rows = None
+    return xyz, features
 
 
 class PointnetFPModule(nn.Module):

@@ -57,6 +57,18 @@ def sample_and_gather(xyz: torch.Tensor, npoint: int) -> Tuple[torch.Tensor, tor
     return idx, new_xyz
 
 
+def pack_rows(xyz: torch.Tensor, features: Optional[torch.Tensor]) -> torch.Tensor:
+    """xyz (B,N,3), features (B,C,N) -> point-major operand rows (B,N,ld) = [xyz | features | zeros], ld a multiple of 8:
+    what the fused set-abstraction kernels gather from (one contiguous row per neighbour).  No gradient (inference path)."""
+    _f32c(xyz)
+    B, N, _ = xyz.shape
+    C = 0 if features is None else features.shape[1]
+    rows = torch.empty((B, N, (3 + C + 7) // 8 * 8), dtype=torch.float32, device=xyz.device)
+    with torch.no_grad():
+        native.pack_rows(xyz, None if features is None else _f32c(features.detach()), rows)
+    return rows
+
+
 class _GatherOperation(Function):
     """pointnet2_utils.py:39-73.  features (B,C,N), idx (B,npoint) -> (B,C,npoint)."""
 

@@ -235,9 +235,8 @@ class Stage2SA(nn.Module):
             channel_in = STAGE2_SA["MLPS"][k][-1]
 
     def forward(self, xyz, features):
-        for sa in self.SA_modules:
-            xyz, features = sa(xyz, features)
-        return features
+        from .pointnet2_modules import sa_stack_forward
+        return sa_stack_forward(self.SA_modules, xyz, features)[1]
 
 
 def stage2_stack(dev, rank: int = 0, scenes: int = 1, flush=None, iters: int = 10) -> Dict:
