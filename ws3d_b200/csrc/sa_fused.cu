@@ -138,7 +138,9 @@ __device__ __forceinline__ float pool_scatter(float (&v)[G], int lane) {
 // slots active, 18 % issue-active).  Warps w, w + 4, ... share a TMEM lane quarter and split every per-row phase by columns -- the
 // row's gather, the two in-place epilogues, the pooling groups, the output loops -- so each phase has kHalves times the warps to
 // issue from and to hide latency behind; barriers and the MMA issue are unchanged.  Measured on the Stage-2 stack (512 proposals):
-// 2.84 ms with 128 threads, 2.52 with 256, 2.42 with 512.
+// 2.84 ms with 128 threads, 2.52 with 256, 2.42 with 512.  Tried on top and not kept: issuing every layer as two halves of its output
+// columns with separate commits, so that the epilogue of the first half overlaps the MMAs of the second -- 2.99 ms: the N = 64
+// instructions take as long as the N = 128 ones, so the tensor-core time doubles and eats the overlap.
 template <int kBatch, int kMinCtas, int kHalves>
 __global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_kernel(const __grid_constant__ CUtensorMap map_w1,
                                                                    const __grid_constant__ CUtensorMap map_w2,
