@@ -88,6 +88,19 @@ def main():
     torch.cuda.synchronize()
     if not torch.isfinite(grads[0]).all():
         problems.append("training step produced non-finite gradients")
+    # ---- Stage-2 widths: the fused kernel with one CTA per SM and four column shares (512 threads), rows packed from
+    #      channel-major features, fused levels chained through point-major rows
+    from ws3d_b200 import workloads
+    from ws3d_b200.pointnet2_modules import sa_stack_forward
+    s2 = workloads.Stage2SA().to(dev).eval()
+    sx = torch.from_numpy((np.random.default_rng(3).normal(0, 1, (3, 512, 3)) * np.array([1.2, 0.6, 2.2])).astype(np.float32)).to(dev)
+    sf = torch.randn(3, 128, 512, device=dev)
+    with torch.no_grad():
+        a = sa_stack_forward(s2.SA_modules, sx, sf)[1].clone()
+        b2 = sa_stack_forward(s2.SA_modules, sx, sf)[1].clone()
+    torch.cuda.synchronize()
+    if not torch.equal(a, b2):
+        problems.append(f"Stage-2 stack is not reproducible: max diff {float((a - b2).abs().max())}")
     rpn = models.RPN().to(dev).eval()
     with torch.no_grad():
         rpn(torch.from_numpy(synth.make_batch(1, 16384 if not quick else 4096)).to(dev))
