@@ -819,7 +819,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side legs (cpu_baseline, fp32_exact, oracle_gpu)")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE.json configs 1, 3, 4, 5")
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "6")),
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("WS3D_INFLIGHT", "7")),
                     help="batches in flight: the coordinate phase (FPS, ball queries, stencils) runs N-1 batches ahead of the feature phase")
     ap.add_argument("--feature-streams", type=int, default=int(os.environ.get("WS3D_FEATURE_STREAMS", "2")),
                     help="streams the feature phases of consecutive batches alternate between")
