@@ -388,7 +388,7 @@ def run_gpu(args):
         del pr
 
     # ---- the headline: coordinate phases `look` batches ahead of the feature phases (StreamedBackboneRunner)
-    sr = StreamedBackboneRunner(model, resident, lookahead=look, feature_streams=args.feature_streams)
+    sr = StreamedBackboneRunner(model, resident, lookahead=look, feature_streams=args.feature_streams, cold_start=args.cold_start)
 
     def timed_streamed(runner_, n, from_host, check):
         """Exactly n batches between two device synchronisations: s.record -> the first `look` submits (pipeline fill) ->
@@ -484,7 +484,8 @@ def run_gpu(args):
         o = rpn(pc, plan=plan)
         return o["backbone_features"], o["rpn_cls"], o["rpn_reg"]
 
-    rpn_sr = StreamedBackboneRunner(model, resident, fn=rpn_heads_plan, lookahead=look, feature_streams=args.feature_streams)
+    rpn_sr = StreamedBackboneRunner(model, resident, fn=rpn_heads_plan, lookahead=look, feature_streams=args.feature_streams,
+                                    cold_start=args.cold_start)
     timed_streamed(rpn_sr, warm + look, False, None)
     ms_rpn, ok_rpn = timed_streamed(rpn_sr, steps, False, plain_sums)
     ms_rpn_long, _ = timed_streamed(rpn_sr, long_steps, False, plain_sums) if long_steps != steps else (ms_rpn, None)
@@ -543,7 +544,8 @@ def run_gpu(args):
                               "SA1 / SA2 one fused kernel per scale, other layers one launch per conv1x1+BN+ReLU[+max-pool]; "
                               "`fp32_exact` has the FP32 figure",
                        "launch": "two CUDA graph replays per step (coordinate phase of batch i+N-1, feature phase of batch i)",
-                       "pipeline": f"{args.inflight} batches in flight, feature phases alternate between {args.feature_streams} stream(s)",
+                       "pipeline": f"{args.inflight} batches in flight, feature phases alternate between {args.feature_streams} stream(s); "
+                                   f"a batch submitted with fewer than {args.cold_start} in flight uses the latency samplers (same indices)",
                        "sm_budget_persistent_kernels": args.sm_budget, "sharding": "scenes per rank, no data-path collective"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4) * world,
                     "d2h_bytes_per_step": BATCH * 4 * world, "ms_per_step": round(ms_e2e / steps, 4),
@@ -823,6 +825,8 @@ def main():
                     help="batches in flight: the coordinate phase (FPS, ball queries, stencils) runs N-1 batches ahead of the feature phase")
     ap.add_argument("--feature-streams", type=int, default=int(os.environ.get("WS3D_FEATURE_STREAMS", "2")),
                     help="streams the feature phases of consecutive batches alternate between")
+    ap.add_argument("--cold-start", type=int, default=int(os.environ.get("WS3D_COLD_START", "2")),
+                    help="batches submitted into a pipeline with fewer than this many in flight use the latency samplers (0 = never)")
     ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "100")),
                     help="SMs a persistent MLP kernel spreads over in the pipelined modes (0 = all)")
     args = ap.parse_args()

@@ -13,7 +13,7 @@ from ws3d_b200 import native, synth
 dev = "cuda:0"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 out = []
-for (b, n, m) in [(16, 16384, 4096), (1, 16384, 4096), (16, 4096, 1024), (16, 1024, 256), (32, 16384, 4096), (64, 16384, 4096)]:
+for (b, n, m) in [(16, 16384, 4096), (1, 16384, 4096), (16, 4096, 1024), (16, 1024, 256), (32, 16384, 4096), (64, 16384, 4096), (96, 16384, 4096), (96, 4096, 1024)]:
     pts = torch.from_numpy(np.ascontiguousarray(synth.make_batch(min(b, 16), n)[..., :3])).to(dev)
     if b > 16: pts = pts.repeat(b // 16, 1, 1).contiguous()
     idx = torch.empty((b, m), dtype=torch.int32, device=dev)
@@ -37,14 +37,17 @@ print(json.dumps(out))
 def main():
     res = {}
     for name, env in [("auto", {}), ("flat", {"WS3D_FPS_BUCKET": "0", "WS3D_FPS_FLAT": "1"}),
-                      ("cluster", {"WS3D_FPS_BUCKET": "0", "WS3D_FPS_FLAT": "0"}), ("bucket", {"WS3D_FPS_BUCKET": "1"})]:
+                      ("cluster", {"WS3D_FPS_BUCKET": "0", "WS3D_FPS_FLAT": "0"}), ("bucket", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "0"}),
+                      ("smem", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1"}),
+                      ("smem1", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1", "WS3D_FPS_SMEM_CLOUDS": "1"}),
+                      ("smem3", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1", "WS3D_FPS_SMEM_3": "1"})]:
         e = dict(os.environ); e.update(env)
         p = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
         if p.returncode:
             print(name, "FAILED", p.stderr[-2000:])
             continue
         res[name] = json.loads(p.stdout.strip().splitlines()[-1])
-    names = [k for k in ("auto", "flat", "cluster", "bucket") if k in res]
+    names = [k for k in ("auto", "flat", "cluster", "bucket", "smem", "smem1", "smem3") if k in res]
     for i in range(len(res[names[0]])):
         a = res[names[0]][i]
         line = f"b={a['b']:3d} n={a['n']:6d} m={a['m']:5d} "

@@ -129,6 +129,9 @@ __global__ void __launch_bounds__(T, 1) fps_bucket_kernel(FpsParams prm) {
         const uint32_t qz = (uint32_t)fminf(fmaxf((z - org[2]) * inv_cell, 0.f), 63.f);
         mort = spread3(qx) | (spread3(qz) << 1) | (spread3(qy) << 2);
       }
+      // the all-ones code is the padding's: a real point never shares it (the sort looks at the code only, so padding must sort
+      // strictly last; and (code << 14 | k) of a real point must never equal the padding key 0xFFFFFFFF)
+      if (mort == 0x3FFFFu) mort = 0x3FFFEu;
       key = (mort << 14) | (uint32_t)k;
     }
     keys[j] = key;
@@ -366,6 +369,9 @@ bool fps_bucket_applicable(int b, int n, int m) {
 
 int fps_bucket_launch(const FpsParams &prm, int b, cudaStream_t stream) {
   const int n = prm.n;
+  // default: the shared-memory-distance kernel (fps_smem.cu: three clouds per SM); WS3D_FPS_SMEM=0 keeps the kernel of this file
+  static const int use_smem = env_int2("WS3D_FPS_SMEM", 1);
+  if (use_smem) return fps_smem_launch(prm, b, stream);
   // buckets per warp: 16 with twice the warps up to 8192 points (measured at b = 16, 4096 -> 1024: 0.70 ms against 0.84:
   // half the select tree and half the rescan), 32 at 16384 points, where 1024 threads would cap at 64 registers and spill (4.3 ms against 3.5)
   if (n <= 4096) return launch_bucket<256, 16>(prm, b, stream);

@@ -80,5 +80,7 @@ __device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_
 // fps_bucket.cu
 bool fps_bucket_applicable(int b, int n, int m);
 int fps_bucket_launch(const FpsParams &prm, int b, cudaStream_t stream);
+// fps_smem.cu: same shapes, running distances in shared memory, several clouds per SM
+int fps_smem_launch(const FpsParams &prm, int b, cudaStream_t stream);
 
 }  // namespace ws3d

@@ -1,0 +1,366 @@
+// Furthest point sampling for THROUGHPUT: several clouds per SM, exact.
+//
+// The bucketed kernel of fps_bucket.cu keeps a cloud's coordinates in shared memory (196 KB at 16384 points) and its running
+// distances in registers (a quarter of the register file), so a cloud owns a whole SM for the 3.5 ms of its latency chain while
+// issuing on a third of the cycles -- a third of the machine's SM-time in the streamed pipeline.  This kernel
+// turns the storage round: the running distances (4 B per point) live in SHARED memory, the Morton-sorted coordinates
+// (16 B per point, with the original index in the fourth word) in a scratch array that stays in L2 and is read only for the
+// buckets a new sample can still lower (~8 of 512 per iteration), and every lane owns whole BUCKETS (box, maximum, tie key and
+// coordinates of the maximum: 11 registers) instead of one point of every bucket.  Consequences:
+//   * no register-indexed state: an active bucket is updated by the 32 lanes of its warp (one point each) and its maximum is
+//     recomputed on the spot with two redux.sync -- no select tree, no dirty-lane rescan;
+//   * 64 KB of shared memory and ~40 registers per thread: THREE clouds share an SM and cover each other's stalls, so a cloud
+//     costs a third of an SM for the length of its chain instead of a whole one.
+// Same culling rule, same update arithmetic and same tie key as fps_bucket.cu / fps.cu: bit-identical sample order.
+//
+// Two launches: fps_sort_kernel (one CTA per cloud: Morton sort in shared memory, writes the sorted float4 array) and
+// fps_smem_kernel (the m - 1 iterations).
+#include <cub/block/block_radix_sort.cuh>
+
+#include <limits.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "fps_common.cuh"
+
+namespace ws3d {
+namespace {
+
+constexpr float kCullShrink = 0.9999f;  // >> the 4 ulp the box distance and the point distance can differ by
+constexpr int kIterThreads = 512;       // 16 warps; lane l of warp w owns bucket l * 16 + w: a new sample's neighbourhood is a few runs of
+                                        // CONSECUTIVE Morton buckets, which this interleaving hands to different warps (one L2 round each)
+constexpr int kIterWarps = kIterThreads / 32;
+
+__device__ __forceinline__ int f2ord(float f) {
+  const int i = __float_as_int(f);
+  return i ^ ((i >> 31) & 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ord2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7FFFFFFF)); }
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 6 bits -> every third bit
+  v &= 0x3Fu;
+  v = (v | (v << 8)) & 0x300Fu;
+  v = (v | (v << 4)) & 0x30C3u;
+  v = (v | (v << 2)) & 0x9249u;
+  return v;
+}
+
+// ---- launch 1: Morton order of a cloud -> sorted (x, y, z, original index) in global memory; slots beyond n hold index -1
+template <int T, int P>
+__global__ void __launch_bounds__(T, 1) fps_sort_kernel(int n, const float *__restrict__ xyz_g, float4 *__restrict__ sorted_g) {
+  using Sort = cub::BlockRadixSort<uint32_t, T, P>;
+  constexpr int kWarps = T / 32;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_box[6][kWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t cloud = blockIdx.x;
+  const float *xyz = xyz_g + cloud * (size_t)n * 3;
+  float4 *sorted = sorted_g + cloud * (size_t)(T * P);
+
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (int k = tid; k < n; k += T) {
+    const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      lo[0] = min(lo[0], f2ord(x)); hi[0] = max(hi[0], f2ord(x));
+      lo[1] = min(lo[1], f2ord(y)); hi[1] = max(hi[1], f2ord(y));
+      lo[2] = min(lo[2], f2ord(z)); hi[2] = max(hi[2], f2ord(z));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
+    hi[a] = __reduce_max_sync(0xFFFFFFFFu, hi[a]);
+    if (lane == 0) { s_box[a][warp] = lo[a]; s_box[3 + a][warp] = hi[a]; }
+  }
+  __syncthreads();
+  float org[3], inv_cell;
+  {
+    float ext = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int l = lane < kWarps ? s_box[a][lane] : INT_MAX, h = lane < kWarps ? s_box[3 + a][lane] : INT_MIN;
+      l = __reduce_min_sync(0xFFFFFFFFu, l);
+      h = __reduce_max_sync(0xFFFFFFFFu, h);
+      org[a] = l <= h ? ord2f(l) : 0.f;
+      ext = fmaxf(ext, l <= h ? ord2f(h) - ord2f(l) : 0.f);
+    }
+    inv_cell = (ext > 0.f && isfinite(ext)) ? 64.f / ext : 0.f;
+    if (!isfinite(inv_cell)) inv_cell = 0.f;
+  }
+  uint32_t keys[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int k = j * T + tid;
+    uint32_t key = 0xFFFFFFFFu;
+    if (k < n) {
+      const float x = __ldg(xyz + (size_t)k * 3), y = __ldg(xyz + (size_t)k * 3 + 1), z = __ldg(xyz + (size_t)k * 3 + 2);
+      uint32_t mort = 0x3FFFFu;
+      if (isfinite(x) && isfinite(y) && isfinite(z)) {
+        const uint32_t qx = (uint32_t)fminf(fmaxf((x - org[0]) * inv_cell, 0.f), 63.f);
+        const uint32_t qy = (uint32_t)fminf(fmaxf((y - org[1]) * inv_cell, 0.f), 63.f);
+        const uint32_t qz = (uint32_t)fminf(fmaxf((z - org[2]) * inv_cell, 0.f), 63.f);
+        mort = spread3(qx) | (spread3(qz) << 1) | (spread3(qy) << 2);
+      }
+      // the all-ones code is the padding's: a real point never shares it (the sort looks at the code only, so padding must sort
+      // strictly last; and (code << 14 | k) of a real point must never equal the padding key 0xFFFFFFFF)
+      if (mort == 0x3FFFFu) mort = 0x3FFFEu;
+      key = (mort << 14) | (uint32_t)k;
+    }
+    keys[j] = key;
+  }
+  __syncthreads();
+  Sort(*reinterpret_cast<typename Sort::TempStorage *>(s_raw)).SortBlockedToStriped(keys, 14, 32);
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int r = j * T + tid;            // sorted rank
+    float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (keys[j] != 0xFFFFFFFFu) {
+      const int k = (int)(keys[j] & 0x3FFFu);
+      v.x = __ldg(xyz + (size_t)k * 3); v.y = __ldg(xyz + (size_t)k * 3 + 1); v.z = __ldg(xyz + (size_t)k * 3 + 2);
+      v.w = __int_as_float(k);
+    }
+    sorted[r] = v;
+  }
+}
+
+struct __align__(16) WarpRec {   // a warp's candidate (value bits, tie key, coordinates), 32 bytes
+  int v;
+  uint32_t key;
+  float x, y, z;
+  int pad[3];
+};
+
+struct SmemFpsParams {
+  int b, n, m, L, cap;         // clouds, points, samples, log2(reference block size), sorted slots per cloud
+  int clouds_per_cta, cloud_smem;   // sub-blocks of a CTA (one cloud each) and the bytes of shared memory each one owns
+  const float4 *sorted;        // (B, cap)
+  float *temp;                 // (B, n) or null
+  int *idx;                    // (B, m)
+  float *new_xyz;              // (B, m, 3) or null
+  const float *xyz;            // (B, n, 3): the first sample is point 0
+};
+
+__device__ __forceinline__ void sub_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// ---- launch 2: the iterations.  A CTA is cut into independent sub-blocks of kWarps warps, one cloud each (own named barrier, own
+// slice of the shared memory), so that SEVERAL CLOUDS SHARE ONE SM and cover each other's latency chain -- the hardware would
+// otherwise spread one-cloud CTAs over as many SMs as there are clouds.  Lane l of warp w owns bucket l * kWarps + w:
+// a new sample's neighbourhood is a few runs of CONSECUTIVE Morton buckets, which this interleaving hands to different
+// warps (one L2 round each).
+// Shared memory of a sub-block: coordinates of every bucket's current maximum (16 B x nb: written by the lane that holds that
+// point, read by its own warp only), running distance of every sorted slot (4 B x 32 nb), the warps' standing candidates and the
+// two parities of the exchange records.
+template <int kWarps>
+__global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  constexpr int kSub = kWarps * 32;
+  const int sub = threadIdx.x / kSub, tid = threadIdx.x % kSub, lane = tid & 31, warp = tid >> 5;
+  const int cloud_i = blockIdx.x * prm.clouds_per_cta + sub;
+  if (sub >= prm.clouds_per_cta || cloud_i >= prm.b) return;        // whole sub-blocks leave: their barrier is their own
+  const int n = prm.n, m = prm.m, L = prm.L;
+  const int nb = (n + 31) >> 5;                       // buckets of 32 consecutive sorted slots
+  unsigned char *base = s_dyn + (size_t)sub * prm.cloud_smem;
+  float4 *s_m4 = reinterpret_cast<float4 *>(base);                              // [nb]
+  float *s_t = reinterpret_cast<float *>(base + (size_t)nb * 16);               // [nb * 32], -1 for padding
+  WarpRec *s_mine = reinterpret_cast<WarpRec *>(base + (size_t)nb * 144);       // [kWarps]   (private to each warp)
+  WarpRec *s_rec = s_mine + kWarps;                                             // [2][kWarps]
+  const size_t cloud = cloud_i;
+  const float4 *pts = prm.sorted + cloud * (size_t)prm.cap;
+  int *idx = prm.idx + cloud * (size_t)m;
+  float *new_xyz = prm.new_xyz ? prm.new_xyz + cloud * (size_t)m * 3 : nullptr;
+  auto bucket_of = [&](int j) { return j * kWarps + warp; };   // this warp's buckets: lane j owns bucket_of(j)
+
+  // per-lane state of bucket bucket_of(lane)
+  float bx0 = __int_as_float(0x7f800000), by0 = bx0, bz0 = bx0, bx1 = -bx0, by1 = -bx0, bz1 = -bx0;   // empty box: never active
+  int bmax = INT_MIN;          // bits of the bucket's largest running distance (>= 0: int order == float order)
+  uint32_t bkey = kNoKey;      // tie key of that point
+
+  // (Re)compute the maximum of bucket b = bucket_of(j) from the warp's 32 values.
+  auto bucket_max = [&](int j, int b, float t, const float4 &p) {
+    const int orig = __float_as_int(p.w);
+    const int vb = __float_as_int(t);
+    const int wv = __reduce_max_sync(0xFFFFFFFFu, vb);
+    const uint32_t kk = (vb == wv && orig >= 0) ? fps_key((uint32_t)orig, L) : kNoKey;
+    const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, kk);
+    if (kk == wk && kk != kNoKey) s_m4[b] = p;          // keys are unique: exactly one lane (none if the bucket is all padding)
+    if (lane == j) { bmax = wv; bkey = wk; }
+  };
+
+  // ---- setup: running distances, boxes, bucket maxima
+  {
+    const float *temp = prm.temp ? prm.temp + cloud * (size_t)n : nullptr;
+    for (int j = 0; j < 32; ++j) {
+      const int b = bucket_of(j);
+      if (b >= nb) break;                               // warp-uniform
+      const float4 p = pts[b * 32 + lane];
+      const int orig = __float_as_int(p.w);
+      const float t = orig >= 0 ? (temp ? temp[orig] : 1e10f) : -1.f;
+      s_t[b * 32 + lane] = t;
+      const bool fin = orig >= 0 && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);  // others can never change: not in the box
+      const int l0 = __reduce_min_sync(0xFFFFFFFFu, fin ? f2ord(p.x) : INT_MAX), h0 = __reduce_max_sync(0xFFFFFFFFu, fin ? f2ord(p.x) : INT_MIN);
+      const int l1 = __reduce_min_sync(0xFFFFFFFFu, fin ? f2ord(p.y) : INT_MAX), h1 = __reduce_max_sync(0xFFFFFFFFu, fin ? f2ord(p.y) : INT_MIN);
+      const int l2 = __reduce_min_sync(0xFFFFFFFFu, fin ? f2ord(p.z) : INT_MAX), h2 = __reduce_max_sync(0xFFFFFFFFu, fin ? f2ord(p.z) : INT_MIN);
+      if (lane == j && l0 <= h0) {
+        bx0 = ord2f(l0); bx1 = ord2f(h0);
+        by0 = ord2f(l1); by1 = ord2f(h1);
+        bz0 = ord2f(l2); bz1 = ord2f(h2);
+      }
+      if (lane == 0) s_m4[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      bucket_max(j, b, t, p);
+    }
+  }
+  float cx = __ldg(prm.xyz + cloud * (size_t)n * 3), cy = __ldg(prm.xyz + cloud * (size_t)n * 3 + 1),
+        cz = __ldg(prm.xyz + cloud * (size_t)n * 3 + 2);       // idx[0] = 0
+  if (tid == 0 && m > 0) {
+    idx[0] = 0;
+    if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
+  }
+  float t_max = __int_as_float(0x7f800000);           // upper bound of every running distance
+  bool warp_stale = true;
+
+  for (int it = 0; it + 1 < m; ++it) {
+    // ---- 1. which of this warp's buckets can still be lowered?  (NaN sample -> comparison false -> active)
+    const float ax = fmaxf(fmaxf(bx0 - cx, cx - bx1), 0.f);
+    const float ay = fmaxf(fmaxf(by0 - cy, cy - by1), 0.f);
+    const float az = fmaxf(fmaxf(bz0 - cz, cz - bz1), 0.f);
+    const float lb = ax * ax + ay * ay + az * az;
+    const bool act = bucket_of(lane) < nb && !(lb * kCullShrink >= t_max);
+    uint32_t mm = __ballot_sync(0xFFFFFFFFu, act);
+    // ---- 2. exact update of the active buckets: one point per lane, coordinates from the L2-resident sorted copy.
+    //         Two buckets are fetched per round so that their L2 latencies overlap.
+    while (mm) {
+      const int j0 = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const bool two = mm != 0;
+      const int j1 = two ? __ffs(mm) - 1 : j0;
+      mm &= mm - 1;                                   // no-op when mm is already 0
+      const int q0 = bucket_of(j0), q1 = bucket_of(j1);
+      const int r0 = q0 * 32 + lane, r1 = q1 * 32 + lane;
+      const float4 p0 = pts[r0];
+      const float4 p1 = pts[r1];                      // the same line again when there is no second bucket
+      {
+        const float d = sqdist_ref(p0.x - cx, p0.y - cy, p0.z - cz);
+        const float old = s_t[r0];
+        const float nt = fminf(d, old);
+        const bool ch = nt != old;
+        if (ch) s_t[r0] = nt;
+        if (__any_sync(0xFFFFFFFFu, ch)) { bucket_max(j0, q0, nt, p0); warp_stale = true; }
+      }
+      if (two) {
+        const float d = sqdist_ref(p1.x - cx, p1.y - cy, p1.z - cz);
+        const float old = s_t[r1];
+        const float nt = fminf(d, old);
+        const bool ch = nt != old;
+        if (ch) s_t[r1] = nt;
+        if (__any_sync(0xFFFFFFFFu, ch)) { bucket_max(j1, q1, nt, p1); warp_stale = true; }
+      }
+    }
+    // ---- 3. warp candidate (only if one of its buckets changed), one barrier, sub-block winner
+    WarpRec *rec = s_rec + (it & 1) * kWarps;
+    if (warp_stale) {
+      const int wv = __reduce_max_sync(0xFFFFFFFFu, bmax);
+      const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, bmax == wv ? bkey : kNoKey);
+      __syncwarp();                                   // s_m4 of this warp's buckets was written by other lanes
+      if (bmax == wv && bkey == wk) {                 // one lane when the key is real; any of them otherwise (all padding: never wins)
+        const float4 c = s_m4[bucket_of(lane)];
+        WarpRec w;
+        w.v = wv; w.key = wk; w.x = c.x; w.y = c.y; w.z = c.z;
+        w.pad[0] = w.pad[1] = w.pad[2] = 0;
+        s_mine[warp] = w;
+        rec[warp] = w;
+      }
+      warp_stale = false;
+    } else if (lane == 0) {
+      rec[warp] = s_mine[warp];
+    }
+    sub_barrier(1 + sub, kSub);
+    {
+      int v = INT_MIN;
+      uint32_t kk = kNoKey;
+      if (lane < kWarps) { v = rec[lane].v; kk = rec[lane].key; }
+      const int bv = __reduce_max_sync(0xFFFFFFFFu, v);
+      const uint32_t win_key = __reduce_min_sync(0xFFFFFFFFu, v == bv ? kk : kNoKey);
+      const int src = __ffs(__ballot_sync(0xFFFFFFFFu, v == bv && kk == win_key)) - 1;
+      cx = rec[src].x; cy = rec[src].y; cz = rec[src].z;          // broadcast reads
+      t_max = __int_as_float(bv);
+      if (tid == 0) {
+        idx[it + 1] = (int)fps_unkey(win_key, L);
+        if (new_xyz) {
+          new_xyz[(size_t)(it + 1) * 3 + 0] = cx;
+          new_xyz[(size_t)(it + 1) * 3 + 1] = cy;
+          new_xyz[(size_t)(it + 1) * 3 + 2] = cz;
+        }
+      }
+    }
+  }
+
+  if (prm.temp) {
+    float *temp = prm.temp + cloud * (size_t)n;
+    sub_barrier(1 + sub, kSub);
+    for (int r = tid; r < nb * 32; r += kSub) {
+      const int orig = __float_as_int(pts[r].w);
+      if (orig >= 0) temp[orig] = s_t[r];
+    }
+  }
+}
+
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
+template <int T, int P>
+int launch_sort(int b, int n, const float *xyz, float4 *sorted, cudaStream_t stream) {
+  using Sort = cub::BlockRadixSort<uint32_t, T, P>;
+  auto kern = fps_sort_kernel<T, P>;
+  const size_t smem = sizeof(typename Sort::TempStorage);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("fps (sort): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  kern<<<b, T, smem, stream>>>(n, xyz, sorted);
+  return check_launch("furthest_point_sampling (sort)");
+}
+
+}  // namespace
+
+// Same shapes as the bucketed kernel: 2048 <= n <= 16384, m >= 64.
+int fps_smem_launch(const FpsParams &prm, int b, cudaStream_t stream) {
+  const int n = prm.n;
+  const int cap = n <= 4096 ? 4096 : n <= 8192 ? 8192 : 16384;
+  float4 *sorted = (float4 *)scratch((size_t)b * cap * sizeof(float4), 8);
+  if (!sorted) return (int)cudaErrorMemoryAllocation;
+  int rc = n <= 4096 ? launch_sort<256, 16>(b, n, prm.xyz, sorted, stream)
+         : n <= 8192 ? launch_sort<512, 16>(b, n, prm.xyz, sorted, stream)
+                     : launch_sort<512, 32>(b, n, prm.xyz, sorted, stream);
+  if (rc) return rc;
+  SmemFpsParams q;
+  q.b = b; q.n = n; q.m = prm.m; q.L = prm.L; q.cap = cap;
+  const int nb = (n + 31) / 32;
+  q.sorted = sorted; q.temp = prm.temp; q.idx = prm.idx; q.new_xyz = prm.new_xyz; q.xyz = prm.xyz;
+  // sub-block shape by bucket count; clouds per CTA by what 1024 threads and the shared memory of one SM hold.
+  // WS3D_FPS_SMEM_CLOUDS caps it (1 = one cloud per CTA, which the hardware spreads over as many SMs).
+  static const int max_clouds = std::max(1, env_int("WS3D_FPS_SMEM_CLOUDS", 8));
+  const int warps = nb <= 128 ? 4 : nb <= 256 ? 8 : 16;
+  q.cloud_smem = nb * 144 + 3 * warps * (int)sizeof(WarpRec);
+  const int cpc = std::min(std::min(std::min(32 / warps, (226 * 1024) / q.cloud_smem), max_clouds), b);
+  q.clouds_per_cta = cpc;
+  const size_t smem = (size_t)cpc * q.cloud_smem;
+  const int grid = (b + cpc - 1) / cpc;
+  cudaError_t e = cudaSuccess;
+#define WS3D_FPS_SMEM_LAUNCH(W)                                                                                      \
+  do {                                                                                                                \
+    auto kern = fps_smem_kernel<W>;                                                                                   \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);                          \
+    if (e == cudaSuccess) kern<<<grid, cpc * W * 32, smem, stream>>>(q);                                              \
+  } while (0)
+  if (warps == 4) WS3D_FPS_SMEM_LAUNCH(4);
+  else if (warps == 8) WS3D_FPS_SMEM_LAUNCH(8);
+  else WS3D_FPS_SMEM_LAUNCH(16);
+#undef WS3D_FPS_SMEM_LAUNCH
+  if (e != cudaSuccess) { set_error("fps (shared-memory distances): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+  return check_launch("furthest_point_sampling (shared-memory distances)");
+}
+
+}  // namespace ws3d

@@ -22,7 +22,7 @@ void set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 namespace {
-constexpr int kMaxDev = 16, kSlots = 8, kArenas = 8;
+constexpr int kMaxDev = 16, kSlots = 12, kArenas = 8;
 struct Slot { void *p = nullptr; size_t cap = 0; };
 Slot g_slots[kMaxDev][kArenas][kSlots];
 std::vector<Slot> g_retired[kMaxDev];   // outgrown buffers: captured graphs / queued launches may still hold them
