@@ -525,10 +525,17 @@ def run_gpu(args):
     fps_k = [k for k in kernels if k["kernel"] == "fps"]
     if fps_k:
         f0 = max(fps_k, key=lambda k: k["avg_ms"])
+        prev_mode = native.set_fps_mode(1)
+        cpc = native.fps_clouds_per_cta(f0["dims"]["b"], f0["dims"]["n"])
+        native.set_fps_mode(prev_mode)
+        fps_sms = -(-f0["dims"]["b"] // cpc)
         fps_rec = {"dims": f0["dims"], "avg_launch_ms": round(f0["avg_ms"], 4), "us_per_iteration": round(f0["avg_ms"] * 1e3 / (f0["dims"]["m"] - 1), 4),
-                   "target_us_per_iteration": [0.25, 0.4], "sms": f0["dims"]["b"], "mode": "throughput (one SM per cloud)",
+                   "target_us_per_iteration": [0.25, 0.4], "sms": fps_sms, "clouds_per_sm": cpc,
+                   "sm_us_per_cloud_iteration": round(f0["avg_ms"] * 1e3 / (f0["dims"]["m"] - 1) / cpc, 4),
+                   "mode": "throughput (running distances in shared memory, several clouds per CTA: csrc/fps_smem.cu)",
                    "hbm_frac": round(f0["GBps"] / peak, 6),
-                   "note": "latency chain of m-1 dependent iterations (SURVEY.md 8d): not HBM-bound; runs beside the feature phases"}
+                   "note": "latency chain of m-1 dependent iterations (SURVEY.md 8d): not HBM-bound; runs beside the feature phases.  "
+                           "sm_us_per_cloud_iteration = the SM-time one cloud's iteration costs the pipeline (round 1: 0.87 on a whole SM)"}
 
     line = None
     if rank == 0:

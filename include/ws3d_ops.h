@@ -64,11 +64,14 @@ int ws3d_release_scratch(int all);
 int ws3d_set_sm_budget(int sms);
 /* How the calling thread's subsequent furthest-point-sampling launches trade latency for SMs:
  * 0 = automatic (default: thread-block clusters, 4 SMs per cloud, unless the batch leaves < 2 SMs per
- * cloud), 1 = throughput (the spatially bucketed kernel, ONE SM per cloud, for 2048 <= n <= 16384:
- * 1.7x the latency at a quarter of the SM time -- for samplers that run beside other work, see
- * ws3d_b200.graphs.StreamedBackboneRunner), 2 = latency (never the one-SM kernel).  Results are
- * bit-identical in every mode.  Returns the previous mode. */
+ * cloud), 1 = throughput (for 2048 <= n <= 16384: Morton buckets with exact culling, running distances in
+ * shared memory, SEVERAL CLOUDS PER SM -- two at 16384 points, eight at 4096: 1.5x the latency at an eighth
+ * of the SM time -- for samplers that run beside other work, see ws3d_b200.graphs.StreamedBackboneRunner),
+ * 2 = latency (never that kernel).  Results are bit-identical in every mode.  Returns the previous mode. */
 int ws3d_set_fps_mode(int mode);
+/* Clouds that share one CTA (= one SM) when the throughput sampler runs a batch of b clouds of n points under the calling
+ * thread's mode (diagnostics: SM-time accounting of a pipelined step). */
+int ws3d_fps_clouds_per_cta(int b, int n);
 
 /* ---- pointnet2_cuda -------------------------------------------------------- */
 

@@ -200,6 +200,21 @@ def test_streamed_runner_equals_plain_forward():
     torch.cuda.synchronize()
     for k, (g, w) in enumerate(zip(got2, want)):
         assert torch.equal(g, w), f"batch {k} differs (two feature streams)"
+    # cold start: a batch submitted into an (almost) empty pipeline replays the latency-sampler capture of its coordinate
+    # phase; here the pipeline runs dry after every other batch, so both captures of every buffer set are used
+    for cold in (0, 1, 3):
+        runner3 = StreamedBackboneRunner(model, batches[0].to(dev), lookahead=2, feature_streams=2, cold_start=cold)
+        got3 = []
+        runner3.fork()
+        for k in range(0, len(batches), 2):
+            runner3.submit(pinned[k])
+            runner3.submit(pinned[k + 1])
+            got3.append(runner3.complete(consume=lambda o: o.clone()))
+            got3.append(runner3.complete(consume=lambda o: o.clone()))
+        runner3.join()
+        torch.cuda.synchronize()
+        for k, (g, w) in enumerate(zip(got3, want)):
+            assert torch.equal(g, w), f"batch {k} differs (cold_start={cold})"
 
 
 def test_fps_modes_are_bit_identical():
@@ -218,9 +233,10 @@ def test_fps_modes_are_bit_identical():
 
 
 def test_streamed_runner_at_bench_config_equals_plain_forward():
-    """The HEADLINE configuration of bench.py -- full weaklyRPN.yaml network, 16 clouds x 16384 points, 6 batches in
-    flight (lookahead 5), two feature streams, persistent kernels capped at 100 SMs, TF32 MLPs -- returns exactly the
-    plain forward's tensor for every batch of a stream of 12 batches (two alternating inputs, host and resident)."""
+    """The HEADLINE configuration of bench.py -- full weaklyRPN.yaml network, 16 clouds x 16384 points, 7 batches in
+    flight (lookahead 6), two feature streams, persistent kernels capped at 100 SMs, TF32 MLPs, the first two batches on
+    the latency samplers (cold start) -- returns exactly the plain forward's tensor for every batch of a stream of 14
+    batches (two alternating inputs, host and resident)."""
     from ws3d_b200 import models, native, synth
     from ws3d_b200.graphs import StreamedBackboneRunner
     torch.backends.cudnn.allow_tf32 = True           # (the autouse fixture restores the previous value)
@@ -232,9 +248,10 @@ def test_streamed_runner_at_bench_config_equals_plain_forward():
         want = [model(h.to(dev))[1].clone() for h in hosts]
     prev = native.set_sm_budget(100)
     try:
-        runner = StreamedBackboneRunner(model, hosts[0].to(dev), lookahead=5, feature_streams=2)
-        n = 12
-        for j in range(5):
+        look = 6
+        runner = StreamedBackboneRunner(model, hosts[0].to(dev), lookahead=look, feature_streams=2, cold_start=2)
+        n = 14
+        for j in range(look):
             runner.submit(hosts[j % 2])
         runner.fork()
         bad = []
@@ -242,8 +259,8 @@ def test_streamed_runner_at_bench_config_equals_plain_forward():
             ok = runner.complete(consume=lambda o, j=j: torch.equal(o, want[j % 2]))
             if not ok:
                 bad.append(j)
-            if j + 5 < n:
-                runner.submit(hosts[(j + 5) % 2] if j % 3 else hosts[(j + 5) % 2].to(dev))
+            if j + look < n:
+                runner.submit(hosts[(j + look) % 2] if j % 3 else hosts[(j + look) % 2].to(dev))
         runner.join()
         torch.cuda.synchronize()
         assert not bad, f"batches {bad} differ from the plain forward"

@@ -72,12 +72,17 @@ def test_fps_matches_oracle_and_reference(b, n, m, kind):
 
 
 TILE_CASES = [(2, 16384, 4096, "scene"), (3, 4096, 1024, "uniform"), (2, 2048, 512, "grid"), (2, 5000, 700, "grid"),
-              (1, 16384, 300, "uniform"), (3, 8192, 2048, "scene"), (2, 3000, 3000, "uniform"), (1, 2500, 64, "special")]
+              (1, 16384, 300, "uniform"), (3, 8192, 2048, "scene"), (2, 3000, 3000, "uniform"), (1, 2500, 64, "special"),
+              # several clouds per CTA (csrc/fps_smem.cu): odd batch at two clouds per CTA, a tail CTA at eight and at four,
+              # lattice ties with every bucket full, a batch that fills the sub-blocks of many CTAs
+              (3, 16384, 512, "scene"), (17, 4096, 256, "uniform"), (5, 8192, 300, "grid"), (9, 2048, 2048, "grid"),
+              (40, 4096, 128, "scene"), (2, 16384, 700, "special")]
 
 
 @pytest.mark.parametrize("b,n,m,kind", TILE_CASES)
 def test_fps_throughput_mode_matches_oracle(b, n, m, kind):
-    """ws3d_set_fps_mode(1): the one-SM-per-cloud kernel with spatial buckets and exact culling (csrc/fps_bucket.cu)
+    """ws3d_set_fps_mode(1): the throughput sampler -- Morton buckets with exact culling, running distances in shared
+    memory, several clouds per CTA (csrc/fps_smem.cu; WS3D_FPS_SMEM=0: the one-SM-per-cloud kernel of csrc/fps_bucket.cu) --
     against the oracle: indices, coordinates and the written-back temp, incl. duplicates / lattice ties, non-finite
     points, far outliers and a cloud collapsed to a line."""
     from ws3d_b200 import native

@@ -46,6 +46,17 @@ def main():
         g = pointnet2_utils.group_concat(xyz, new_xyz, feat, i1, True)
         nn_idx, w = pointnet2_utils.three_nn_weights(xyz, new_xyz)
         pointnet2_utils.three_interpolate(g[:, :, :, 0].contiguous(), nn_idx, w)
+    # ---- throughput sampler with several clouds per CTA (csrc/fps_smem.cu): sub-blocks of 16 / 8 / 4 warps on their own named
+    #      barriers, odd batches (a sub-block of the last CTA leaves at once); few samples keep the tool's run time short
+    for b, n, m in ((3, 16384, 96), (5, 8192, 96), (9, 2048, 96)):
+        xyz = torch.from_numpy(np.ascontiguousarray(synth.make_batch(b, n)[..., :3])).to(dev)
+        outs = []
+        for mode in (0, 1):
+            prev = native.set_fps_mode(mode)
+            outs.append(pointnet2_utils.sample_and_gather(xyz, m)[0].clone())
+            native.set_fps_mode(prev)
+        if not torch.equal(outs[0], outs[1]):
+            problems.append(f"throughput FPS differs from the latency kernel at b={b} n={n} m={m}")
     # ---- whole backbone (fused SA kernel, layer kernel, affine gathers) eager, then streamed with 3 batches in flight
     cfg = {"NPOINTS": [512, 128, 32, 8], "RADIUS": models.RPN_SA_CONFIG["RADIUS"], "NSAMPLE": models.RPN_SA_CONFIG["NSAMPLE"],
            "MLPS": [[[8, 8, 16], [8, 8, 16]], [[16, 16, 32], [16, 24, 32]], [[32, 32, 64], [32, 48, 64]], [[64, 64, 96], [64, 64, 96]]]}

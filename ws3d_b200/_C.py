@@ -26,6 +26,7 @@ _SIGNATURES = {
     "ws3d_release_scratch": [_i],
     "ws3d_set_sm_budget": [_i],
     "ws3d_set_fps_mode": [_i],
+    "ws3d_fps_clouds_per_cta": [_i, _i],
     "ws3d_furthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "ws3d_furthest_point_sampling_gather": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "ws3d_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],

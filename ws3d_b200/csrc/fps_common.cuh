@@ -82,5 +82,6 @@ bool fps_bucket_applicable(int b, int n, int m);
 int fps_bucket_launch(const FpsParams &prm, int b, cudaStream_t stream);
 // fps_smem.cu: same shapes, running distances in shared memory, several clouds per SM
 int fps_smem_launch(const FpsParams &prm, int b, cudaStream_t stream);
+int fps_smem_clouds_per_cta(int b, int n);
 
 }  // namespace ws3d

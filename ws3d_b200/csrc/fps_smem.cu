@@ -323,7 +323,27 @@ int launch_sort(int b, int n, const float *xyz, float4 *sorted, cudaStream_t str
   return check_launch("furthest_point_sampling (sort)");
 }
 
+
+// Sub-block shape by bucket count; clouds per CTA by what 1024 threads and the shared memory of one SM hold.  In throughput
+// mode (ws3d_set_fps_mode(1)) CTAs are packed full: the sampler is meant to leave the SMs to other work.  Otherwise (a batch
+// too large for the cluster kernels) clouds are packed only as far as the batch exceeds the SM count.
+// WS3D_FPS_SMEM_CLOUDS caps it (1 = one cloud per CTA, which the hardware spreads over as many SMs).
+struct SmemShape { int warps, cloud_smem, clouds_per_cta; };
+SmemShape smem_shape(int b, int n) {
+  static const int max_clouds = std::max(1, env_int("WS3D_FPS_SMEM_CLOUDS", 8));
+  const int nb = (n + 31) / 32;
+  SmemShape sh;
+  sh.warps = nb <= 128 ? 4 : nb <= 256 ? 8 : 16;
+  sh.cloud_smem = nb * 144 + 3 * sh.warps * (int)sizeof(WarpRec);
+  int cpc = std::min(std::min(32 / sh.warps, (226 * 1024) / sh.cloud_smem), max_clouds);
+  if (fps_mode() != 1) cpc = std::min(cpc, (b + num_sms() - 1) / num_sms());
+  sh.clouds_per_cta = std::max(1, std::min(cpc, b));
+  return sh;
+}
+
 }  // namespace
+
+int fps_smem_clouds_per_cta(int b, int n) { return smem_shape(b, n).clouds_per_cta; }
 
 // Same shapes as the bucketed kernel: 2048 <= n <= 16384, m >= 64.
 int fps_smem_launch(const FpsParams &prm, int b, cudaStream_t stream) {
@@ -339,12 +359,9 @@ int fps_smem_launch(const FpsParams &prm, int b, cudaStream_t stream) {
   q.b = b; q.n = n; q.m = prm.m; q.L = prm.L; q.cap = cap;
   const int nb = (n + 31) / 32;
   q.sorted = sorted; q.temp = prm.temp; q.idx = prm.idx; q.new_xyz = prm.new_xyz; q.xyz = prm.xyz;
-  // sub-block shape by bucket count; clouds per CTA by what 1024 threads and the shared memory of one SM hold.
-  // WS3D_FPS_SMEM_CLOUDS caps it (1 = one cloud per CTA, which the hardware spreads over as many SMs).
-  static const int max_clouds = std::max(1, env_int("WS3D_FPS_SMEM_CLOUDS", 8));
-  const int warps = nb <= 128 ? 4 : nb <= 256 ? 8 : 16;
-  q.cloud_smem = nb * 144 + 3 * warps * (int)sizeof(WarpRec);
-  const int cpc = std::min(std::min(std::min(32 / warps, (226 * 1024) / q.cloud_smem), max_clouds), b);
+  const SmemShape sh = smem_shape(b, n);
+  const int warps = sh.warps, cpc = sh.clouds_per_cta;
+  q.cloud_smem = sh.cloud_smem;
   q.clouds_per_cta = cpc;
   const size_t smem = (size_t)cpc * q.cloud_smem;
   const int grid = (b + cpc - 1) / cpc;

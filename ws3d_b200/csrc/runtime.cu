@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fps_common.cuh"
 
 namespace ws3d {
 
@@ -126,6 +127,7 @@ WS3D_API int ws3d_release_scratch(int all) {
 }
 WS3D_API int ws3d_num_arenas(void) { return ws3d::kArenas; }
 WS3D_API int ws3d_set_sm_budget(int sms) { return ws3d::g_sm_budget.exchange(sms < 0 ? 0 : sms); }
+WS3D_API int ws3d_fps_clouds_per_cta(int b, int n) { return ws3d::fps_smem_clouds_per_cta(b, n); }
 WS3D_API int ws3d_set_fps_mode(int mode) {
   const int prev = ws3d::g_fps_mode;
   if (mode >= 0 && mode <= 2) ws3d::g_fps_mode = mode;

@@ -486,5 +486,10 @@ def set_sm_budget(sms: int) -> int:
 
 
 def set_fps_mode(mode: int) -> int:
-    """0 auto, 1 throughput (one SM per cloud), 2 latency (clusters) for this thread's FPS launches; returns the previous mode."""
+    """0 auto, 1 throughput (several clouds per SM), 2 latency (clusters) for this thread's FPS launches; returns the previous mode."""
     return int(lib().ws3d_set_fps_mode(int(mode)))
+
+
+def fps_clouds_per_cta(b: int, n: int) -> int:
+    """Clouds per CTA (= per SM) of the throughput sampler for a batch of b clouds of n points under this thread's mode."""
+    return int(lib().ws3d_fps_clouds_per_cta(int(b), int(n)))
