@@ -76,7 +76,8 @@ TILE_CASES = [(2, 16384, 4096, "scene"), (3, 4096, 1024, "uniform"), (2, 2048, 5
               # several clouds per CTA (csrc/fps_smem.cu): odd batch at two clouds per CTA, a tail CTA at eight and at four,
               # lattice ties with every bucket full, a batch that fills the sub-blocks of many CTAs
               (3, 16384, 512, "scene"), (17, 4096, 256, "uniform"), (5, 8192, 300, "grid"), (9, 2048, 2048, "grid"),
-              (40, 4096, 128, "scene"), (2, 16384, 700, "special")]
+              (40, 4096, 128, "scene"), (2, 16384, 700, "special"),
+              (1, 2048, 2100, "grid")]   # m > n: every distance reaches 0 and the tie key alone decides
 
 
 @pytest.mark.parametrize("b,n,m,kind", TILE_CASES)

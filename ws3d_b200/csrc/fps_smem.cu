@@ -18,6 +18,7 @@
 #include <cub/block/block_radix_sort.cuh>
 
 #include <limits.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -152,8 +153,10 @@ __device__ __forceinline__ void sub_barrier(int id, int threads) { asm volatile(
 // Shared memory of a sub-block: coordinates of every bucket's current maximum (16 B x nb: written by the lane that holds that
 // point, read by its own warp only), running distance of every sorted slot (4 B x 32 nb), the warps' standing candidates and the
 // two parities of the exchange records.
-template <int kWarps>
-__global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
+__device__ unsigned long long g_smem_stats[16];   // debug counters (WS3D_FPS_STATS=1): see fps_smem_launch
+
+template <int kWarps, int kBpl, int kMaxThreads, bool kStats = false>
+__global__ void __launch_bounds__(kMaxThreads, 1) fps_smem_kernel(SmemFpsParams prm) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   constexpr int kSub = kWarps * 32;
   const int sub = threadIdx.x / kSub, tid = threadIdx.x % kSub, lane = tid & 31, warp = tid >> 5;
@@ -170,12 +173,19 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
   const float4 *pts = prm.sorted + cloud * (size_t)prm.cap;
   int *idx = prm.idx + cloud * (size_t)m;
   float *new_xyz = prm.new_xyz ? prm.new_xyz + cloud * (size_t)m * 3 : nullptr;
-  auto bucket_of = [&](int j) { return j * kWarps + warp; };   // this warp's buckets: lane j owns bucket_of(j)
+  auto bucket_of = [&](int j) { return j * kWarps + warp; };   // this warp's buckets, j < 32 kBpl: lane j & 31, slot j >> 5
 
-  // per-lane state of bucket bucket_of(lane)
-  float bx0 = __int_as_float(0x7f800000), by0 = bx0, bz0 = bx0, bx1 = -bx0, by1 = -bx0, bz1 = -bx0;   // empty box: never active
-  int bmax = INT_MIN;          // bits of the bucket's largest running distance (>= 0: int order == float order)
-  uint32_t bkey = kNoKey;      // tie key of that point
+  // per-lane state of the buckets bucket_of(lane + 32 i), i < kBpl (every index below is a compile-time constant after
+  // unrolling: the arrays live in registers)
+  float bx0[kBpl], by0[kBpl], bz0[kBpl], bx1[kBpl], by1[kBpl], bz1[kBpl];
+  int bmax[kBpl];              // bits of the bucket's largest running distance (>= 0: int order == float order)
+  uint32_t bkey[kBpl];         // tie key of that point
+#pragma unroll
+  for (int i = 0; i < kBpl; ++i) {
+    bx0[i] = by0[i] = bz0[i] = __int_as_float(0x7f800000);   // empty box: never active
+    bx1[i] = by1[i] = bz1[i] = __int_as_float(0xff800000);
+    bmax[i] = INT_MIN; bkey[i] = kNoKey;
+  }
 
   // (Re)compute the maximum of bucket b = bucket_of(j) from the warp's 32 values.
   auto bucket_max = [&](int j, int b, float t, const float4 &p) {
@@ -185,15 +195,20 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
     const uint32_t kk = (vb == wv && orig >= 0) ? fps_key((uint32_t)orig, L) : kNoKey;
     const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, kk);
     if (kk == wk && kk != kNoKey) s_m4[b] = p;          // keys are unique: exactly one lane (none if the bucket is all padding)
-    if (lane == j) { bmax = wv; bkey = wk; }
+#pragma unroll
+    for (int i = 0; i < kBpl; ++i)
+      if (lane == (j & 31) && i == (j >> 5)) { bmax[i] = wv; bkey[i] = wk; }
   };
 
   // ---- setup: running distances, boxes, bucket maxima
   {
     const float *temp = prm.temp ? prm.temp + cloud * (size_t)n : nullptr;
-    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+    for (int slot = 0; slot < kBpl; ++slot)
+    for (int jl = 0; jl < 32; ++jl) {
+      const int j = slot * 32 + jl;
       const int b = bucket_of(j);
-      if (b >= nb) break;                               // warp-uniform
+      if (b >= nb) break;                               // warp-uniform (buckets grow with j: the later slots are empty too)
       const float4 p = pts[b * 32 + lane];
       const int orig = __float_as_int(p.w);
       const float t = orig >= 0 ? (temp ? temp[orig] : 1e10f) : -1.f;
@@ -202,11 +217,13 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
       const int l0 = __reduce_min_sync(0xFFFFFFFFu, fin ? f2ord(p.x) : INT_MAX), h0 = __reduce_max_sync(0xFFFFFFFFu, fin ? f2ord(p.x) : INT_MIN);
       const int l1 = __reduce_min_sync(0xFFFFFFFFu, fin ? f2ord(p.y) : INT_MAX), h1 = __reduce_max_sync(0xFFFFFFFFu, fin ? f2ord(p.y) : INT_MIN);
       const int l2 = __reduce_min_sync(0xFFFFFFFFu, fin ? f2ord(p.z) : INT_MAX), h2 = __reduce_max_sync(0xFFFFFFFFu, fin ? f2ord(p.z) : INT_MIN);
-      if (lane == j && l0 <= h0) {
-        bx0 = ord2f(l0); bx1 = ord2f(h0);
-        by0 = ord2f(l1); by1 = ord2f(h1);
-        bz0 = ord2f(l2); bz1 = ord2f(h2);
-      }
+#pragma unroll
+      for (int i = 0; i < kBpl; ++i)
+        if (lane == jl && i == slot && l0 <= h0) {
+          bx0[i] = ord2f(l0); bx1[i] = ord2f(h0);
+          by0[i] = ord2f(l1); by1[i] = ord2f(h1);
+          bz0[i] = ord2f(l2); bz1[i] = ord2f(h2);
+        }
       if (lane == 0) s_m4[b] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
       bucket_max(j, b, t, p);
@@ -220,23 +237,41 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
   }
   float t_max = __int_as_float(0x7f800000);           // upper bound of every running distance
   bool warp_stale = true;
+  unsigned long long st_active = 0, st_crit = 0, st_hist[6] = {0, 0, 0, 0, 0, 0};   // kStats only
 
   for (int it = 0; it + 1 < m; ++it) {
     // ---- 1. which of this warp's buckets can still be lowered?  (NaN sample -> comparison false -> active)
-    const float ax = fmaxf(fmaxf(bx0 - cx, cx - bx1), 0.f);
-    const float ay = fmaxf(fmaxf(by0 - cy, cy - by1), 0.f);
-    const float az = fmaxf(fmaxf(bz0 - cz, cz - bz1), 0.f);
-    const float lb = ax * ax + ay * ay + az * az;
-    const bool act = bucket_of(lane) < nb && !(lb * kCullShrink >= t_max);
-    uint32_t mm = __ballot_sync(0xFFFFFFFFu, act);
+    uint32_t mm[kBpl];
+#pragma unroll
+    for (int i = 0; i < kBpl; ++i) {
+      const float ax = fmaxf(fmaxf(bx0[i] - cx, cx - bx1[i]), 0.f);
+      const float ay = fmaxf(fmaxf(by0[i] - cy, cy - by1[i]), 0.f);
+      const float az = fmaxf(fmaxf(bz0[i] - cz, cz - bz1[i]), 0.f);
+      const float lb = ax * ax + ay * ay + az * az;
+      // a point p of the bucket changes only if d(sample, p) < t_p <= the bucket's OWN largest running distance (which
+      // this lane holds), a tighter radius than the global maximum t_max the bucket kernel of fps_bucket.cu tests against
+      const bool act = bucket_of(lane + 32 * i) < nb && !(lb * kCullShrink >= fminf(t_max, __int_as_float(bmax[i])));
+      mm[i] = __ballot_sync(0xFFFFFFFFu, act);
+    }
     // ---- 2. exact update of the active buckets: one point per lane, coordinates from the L2-resident sorted copy.
     //         Two buckets are fetched per round so that their L2 latencies overlap.
-    while (mm) {
-      const int j0 = __ffs(mm) - 1;
-      mm &= mm - 1;
-      const bool two = mm != 0;
-      const int j1 = two ? __ffs(mm) - 1 : j0;
-      mm &= mm - 1;                                   // no-op when mm is already 0
+    auto pop = [&]() -> int {                         // next active bucket slot of this warp, or -1 (warp-uniform)
+      int j = -1;
+#pragma unroll
+      for (int i = 0; i < kBpl; ++i)
+        if (j < 0 && mm[i]) { j = __ffs(mm[i]) - 1 + 32 * i; mm[i] &= mm[i] - 1; }
+      return j;
+    };
+    int st_rounds = 0;
+    if (kStats) {
+#pragma unroll
+      for (int i = 0; i < kBpl; ++i) st_active += (unsigned)__popc(mm[i]);
+    }
+    for (int j0 = pop(); j0 >= 0; j0 = pop()) {
+      if (kStats) ++st_rounds;
+      int j1 = pop();
+      const bool two = j1 >= 0;
+      if (!two) j1 = j0;
       const int q0 = bucket_of(j0), q1 = bucket_of(j1);
       const int r0 = q0 * 32 + lane, r1 = q1 * 32 + lane;
       const float4 p0 = pts[r0];
@@ -261,11 +296,16 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
     // ---- 3. warp candidate (only if one of its buckets changed), one barrier, sub-block winner
     WarpRec *rec = s_rec + (it & 1) * kWarps;
     if (warp_stale) {
-      const int wv = __reduce_max_sync(0xFFFFFFFFu, bmax);
-      const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, bmax == wv ? bkey : kNoKey);
+      int lv = bmax[0], li = 0;                       // this lane's best bucket
+      uint32_t lk = bkey[0];
+#pragma unroll
+      for (int i = 1; i < kBpl; ++i)
+        if (bmax[i] > lv || (bmax[i] == lv && bkey[i] < lk)) { lv = bmax[i]; lk = bkey[i]; li = i; }
+      const int wv = __reduce_max_sync(0xFFFFFFFFu, lv);
+      const uint32_t wk = __reduce_min_sync(0xFFFFFFFFu, lv == wv ? lk : kNoKey);
       __syncwarp();                                   // s_m4 of this warp's buckets was written by other lanes
-      if (bmax == wv && bkey == wk) {                 // one lane when the key is real; any of them otherwise (all padding: never wins)
-        const float4 c = s_m4[bucket_of(lane)];
+      if (lv == wv && lk == wk) {                     // one lane when the key is real; any of them otherwise (all padding: never wins)
+        const float4 c = s_m4[bucket_of(lane + 32 * li)];
         WarpRec w;
         w.v = wv; w.key = wk; w.x = c.x; w.y = c.y; w.z = c.z;
         w.pad[0] = w.pad[1] = w.pad[2] = 0;
@@ -276,7 +316,17 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
     } else if (lane == 0) {
       rec[warp] = s_mine[warp];
     }
+    if (kStats) {
+      __syncwarp();
+      if (lane == 0) rec[warp].pad[0] = st_rounds;
+    }
     sub_barrier(1 + sub, kSub);
+    if (kStats) {   // rounds of the slowest warp = what this iteration's chain paid for the updates
+      const int crit = __reduce_max_sync(0xFFFFFFFFu, lane < kWarps ? rec[lane].pad[0] : 0);
+      st_crit += (unsigned)crit;
+#pragma unroll
+      for (int h = 0; h < 6; ++h) st_hist[h] += (min(crit, 5) == h);
+    }
     {
       int v = INT_MIN;
       uint32_t kk = kNoKey;
@@ -297,6 +347,14 @@ __global__ void __launch_bounds__(1024, 1) fps_smem_kernel(SmemFpsParams prm) {
     }
   }
 
+  if (kStats) {
+    if (lane == 0) atomicAdd(&g_smem_stats[0], st_active);
+    if (tid == 0) {
+      atomicAdd(&g_smem_stats[1], st_crit);
+      atomicAdd(&g_smem_stats[2], (unsigned long long)(m > 0 ? m - 1 : 0));
+      for (int h = 0; h < 6; ++h) atomicAdd(&g_smem_stats[4 + h], st_hist[h]);
+    }
+  }
   if (prm.temp) {
     float *temp = prm.temp + cloud * (size_t)n;
     sub_barrier(1 + sub, kSub);
@@ -328,14 +386,21 @@ int launch_sort(int b, int n, const float *xyz, float4 *sorted, cudaStream_t str
 // mode (ws3d_set_fps_mode(1)) CTAs are packed full: the sampler is meant to leave the SMs to other work.  Otherwise (a batch
 // too large for the cluster kernels) clouds are packed only as far as the batch exceeds the SM count.
 // WS3D_FPS_SMEM_CLOUDS caps it (1 = one cloud per CTA, which the hardware spreads over as many SMs).
-struct SmemShape { int warps, cloud_smem, clouds_per_cta; };
+struct SmemShape { int warps, bpl, cloud_smem, clouds_per_cta; };
 SmemShape smem_shape(int b, int n) {
   static const int max_clouds = std::max(1, env_int("WS3D_FPS_SMEM_CLOUDS", 8));
+  // 16384 points (512 buckets): 0 = 16 warps x 1 bucket per lane, two clouds per CTA (1024 threads); 1 = 8 warps x 2, three
+  // clouds (768 threads); 2 = 4 warps x 4, three clouds (384 threads).  Shared memory admits three clouds per SM.
+  static const int wide_shape = env_int("WS3D_FPS_SMEM_SHAPE", 0);
   const int nb = (n + 31) / 32;
   SmemShape sh;
+  sh.bpl = 1;
   sh.warps = nb <= 128 ? 4 : nb <= 256 ? 8 : 16;
+  if (sh.warps == 16 && wide_shape == 1) { sh.warps = 8; sh.bpl = 2; }
+  if (sh.warps == 16 && wide_shape == 2) { sh.warps = 4; sh.bpl = 4; }
   sh.cloud_smem = nb * 144 + 3 * sh.warps * (int)sizeof(WarpRec);
-  int cpc = std::min(std::min(32 / sh.warps, (226 * 1024) / sh.cloud_smem), max_clouds);
+  const int by_threads = sh.bpl == 1 ? 32 / sh.warps : 3;
+  int cpc = std::min(std::min(by_threads, (226 * 1024) / sh.cloud_smem), max_clouds);
   if (fps_mode() != 1) cpc = std::min(cpc, (b + num_sms() - 1) / num_sms());
   sh.clouds_per_cta = std::max(1, std::min(cpc, b));
   return sh;
@@ -366,15 +431,30 @@ int fps_smem_launch(const FpsParams &prm, int b, cudaStream_t stream) {
   const size_t smem = (size_t)cpc * q.cloud_smem;
   const int grid = (b + cpc - 1) / cpc;
   cudaError_t e = cudaSuccess;
-#define WS3D_FPS_SMEM_LAUNCH(W)                                                                                      \
+#define WS3D_FPS_SMEM_LAUNCH(W, BPL, MAXT)                                                                           \
   do {                                                                                                                \
-    auto kern = fps_smem_kernel<W>;                                                                                   \
+    auto kern = fps_smem_kernel<W, BPL, MAXT>;                                                                        \
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);                          \
     if (e == cudaSuccess) kern<<<grid, cpc * W * 32, smem, stream>>>(q);                                              \
   } while (0)
-  if (warps == 4) WS3D_FPS_SMEM_LAUNCH(4);
-  else if (warps == 8) WS3D_FPS_SMEM_LAUNCH(8);
-  else WS3D_FPS_SMEM_LAUNCH(16);
+  static const int stats = env_int("WS3D_FPS_STATS", 0);
+  if (stats && warps == 16 && sh.bpl == 1) {   // debug: active buckets and update rounds per iteration (synchronises)
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_smem_stats, z, sizeof(z));
+    auto kern = fps_smem_kernel<16, 1, 1024, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e == cudaSuccess) kern<<<grid, cpc * 16 * 32, smem, stream>>>(q);
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(z, g_smem_stats, sizeof(z));
+    const double it = (double)std::max(1ull, z[2]);
+    fprintf(stderr, "[fps smem stats] b=%d n=%d m=%d clouds/CTA=%d: active buckets per iteration %.2f, update rounds of the slowest warp "
+                    "per iteration %.3f, share of iterations with 0/1/2/3/4/5+ rounds: %.3f %.3f %.3f %.3f %.3f %.3f\n", b, n, prm.m, cpc,
+            z[0] / it, z[1] / it, z[4] / it, z[5] / it, z[6] / it, z[7] / it, z[8] / it, z[9] / it);
+  } else if (sh.bpl == 4) WS3D_FPS_SMEM_LAUNCH(4, 4, 384);
+  else if (sh.bpl == 2) WS3D_FPS_SMEM_LAUNCH(8, 2, 768);
+  else if (warps == 4) WS3D_FPS_SMEM_LAUNCH(4, 1, 1024);
+  else if (warps == 8) WS3D_FPS_SMEM_LAUNCH(8, 1, 1024);
+  else WS3D_FPS_SMEM_LAUNCH(16, 1, 1024);
 #undef WS3D_FPS_SMEM_LAUNCH
   if (e != cudaSuccess) { set_error("fps (shared-memory distances): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   return check_launch("furthest_point_sampling (shared-memory distances)");
