@@ -369,7 +369,7 @@ bool fps_bucket_applicable(int b, int n, int m) {
 
 int fps_bucket_launch(const FpsParams &prm, int b, cudaStream_t stream) {
   const int n = prm.n;
-  // default: the shared-memory-distance kernel (fps_smem.cu: three clouds per SM); WS3D_FPS_SMEM=0 keeps the kernel of this file
+  // default: the shared-memory-distance kernel (fps_smem.cu: several clouds per SM); WS3D_FPS_SMEM=0 keeps the kernel of this file
   static const int use_smem = env_int2("WS3D_FPS_SMEM", 1);
   if (use_smem) return fps_smem_launch(prm, b, stream);
   // buckets per warp: 16 with twice the warps up to 8192 points (measured at b = 16, 4096 -> 1024: 0.70 ms against 0.84:

@@ -5,13 +5,16 @@
 // issuing on a third of the cycles -- a third of the machine's SM-time in the streamed pipeline.  This kernel
 // turns the storage round: the running distances (4 B per point) live in SHARED memory, the Morton-sorted coordinates
 // (16 B per point, with the original index in the fourth word) in a scratch array that stays in L2 and is read only for the
-// buckets a new sample can still lower (~8 of 512 per iteration), and every lane owns whole BUCKETS (box, maximum, tie key and
-// coordinates of the maximum: 11 registers) instead of one point of every bucket.  Consequences:
+// buckets a new sample can still lower (6.7 of 512 per iteration at 16384 -> 4096), and every lane owns whole BUCKETS (box,
+// maximum, tie key: 8 registers; the coordinates of the maximum in shared memory) instead of one point of every bucket.
+// Consequences:
 //   * no register-indexed state: an active bucket is updated by the 32 lanes of its warp (one point each) and its maximum is
 //     recomputed on the spot with two redux.sync -- no select tree, no dirty-lane rescan;
-//   * 64 KB of shared memory and ~40 registers per thread: THREE clouds share an SM and cover each other's stalls, so a cloud
-//     costs a third of an SM for the length of its chain instead of a whole one.
-// Same culling rule, same update arithmetic and same tie key as fps_bucket.cu / fps.cu: bit-identical sample order.
+//   * 72 KB of shared memory and 59 registers per thread for a 16384-point cloud: TWO clouds share an SM (eight at 4096 points)
+//     as independent sub-blocks of one CTA and cover each other's stalls, so a cloud costs half an SM for the length of its
+//     chain instead of a whole one (a third cloud would need the state under 40 registers: measured, spills).
+// Same culling rule (tightened to the bucket's own maximum), same update arithmetic and same tie key as fps_bucket.cu / fps.cu:
+// bit-identical sample order.  DESIGN.md section 3.1c has the measurements.
 //
 // Two launches: fps_sort_kernel (one CTA per cloud: Morton sort in shared memory, writes the sorted float4 array) and
 // fps_smem_kernel (the m - 1 iterations).
