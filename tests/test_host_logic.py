@@ -206,3 +206,31 @@ def test_streamed_runner_rejects_more_buffer_sets_than_scratch_arenas():
     from ws3d_b200 import graphs
     src = inspect.getsource(graphs.StreamedBackboneRunner.__init__)
     assert "num_arenas" in src and "raise ValueError" in src
+
+
+def test_plan_tensors_are_listed_in_one_fixed_order():
+    """The cold-start capture of StreamedBackboneRunner copies its plan into the throughput capture's plan tensor by tensor:
+    both flattenings must pair the same entries whatever the dict insertion order."""
+    from ws3d_b200.graphs import _plan_tensors
+    t = [torch.full((2,), float(k)) for k in range(7)]
+    a = {"xyz": [t[0], t[1]], "idx": [(t[2], t[3])], "nn": [(t[4], t[5])], "xyz0": t[6], "note": "x", "feat0": None}
+    b = {"feat0": None, "xyz0": t[6], "nn": [(t[4], t[5])], "note": "y", "idx": [(t[2], t[3])], "xyz": [t[0], t[1]]}
+    fa, fb = _plan_tensors(a), _plan_tensors(b)
+    assert len(fa) == 7 and all(x is y for x, y in zip(fa, fb))
+    assert [int(x[0]) for x in fa] == [2, 3, 4, 5, 0, 1, 6]          # keys sorted: idx, nn, xyz, xyz0
+
+
+def test_throughput_sampler_packing_rule_is_exposed_without_a_gpu():
+    """ws3d_fps_clouds_per_cta: packed CTAs in throughput mode only (two clouds at 16384 points, four at 8192, eight at 4096),
+    one cloud per CTA otherwise until the batch exceeds the SM count."""
+    from ws3d_b200 import native
+    prev = native.set_fps_mode(1)
+    try:
+        assert native.fps_clouds_per_cta(16, 16384) == 2
+        assert native.fps_clouds_per_cta(16, 8192) == 4
+        assert native.fps_clouds_per_cta(16, 4096) == 8
+        assert native.fps_clouds_per_cta(3, 4096) == 3           # never more than the batch
+        native.set_fps_mode(0)
+        assert native.fps_clouds_per_cta(16, 16384) == 1
+    finally:
+        native.set_fps_mode(prev)
