@@ -110,6 +110,49 @@ def test_fps_throughput_mode_matches_oracle(b, n, m, kind):
     np.testing.assert_array_equal(idx.cpu().numpy(), exp_idx)
     np.testing.assert_array_equal(temp.cpu().numpy(), exp_temp)
     np.testing.assert_array_equal(new_xyz.cpu().numpy(), np.take_along_axis(xyz, exp_idx[..., None].astype(np.int64), 1))
+    ref = require_ref("pointnet2_cuda")
+    if ref is not None and kind != "special":        # (the reference kernel's own treatment of NaN / inf is pinned by the oracle)
+        rtemp = torch.full((b, n), 1e10, device=dev)
+        ridx = torch.empty((b, m), dtype=torch.int32, device=dev)
+        ref.furthest_point_sampling_wrapper(b, n, m, x, rtemp, ridx)
+        assert torch.equal(ridx, idx)
+        assert torch.equal(rtemp, temp)
+
+
+def test_fps_throughput_mode_at_bench_size_equals_latency_mode_and_reference():
+    """The bench's level-1 sampling call (16 clouds x 16384 points -> 4096 samples) in throughput mode (two clouds per CTA),
+    in latency mode and on the reference's own kernel: same indices, same written-back distances; size-independent properties:
+    samples distinct, the selection distances never increase."""
+    from ws3d_b200 import native, synth
+    b, n, m = 16, 16384, 4096
+    x = _t(synth.make_batch(b, n)[..., :3].copy())
+    outs = []
+    for mode in (1, 2):
+        temp = torch.full((b, n), 1e10, device=dev)
+        idx = torch.empty((b, m), dtype=torch.int32, device=dev)
+        nx = torch.empty((b, m, 3), device=dev)
+        prev = native.set_fps_mode(mode)
+        try:
+            native.furthest_point_sampling_gather(b, n, m, x, temp, idx, nx)
+        finally:
+            native.set_fps_mode(prev)
+        outs.append((idx, temp, nx))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    ref = require_ref("pointnet2_cuda")
+    if ref is not None:
+        rtemp = torch.full((b, n), 1e10, device=dev)
+        ridx = torch.empty((b, m), dtype=torch.int32, device=dev)
+        ref.furthest_point_sampling_wrapper(b, n, m, x, rtemp, ridx)
+        assert torch.equal(ridx, outs[0][0]) and torch.equal(rtemp, outs[0][1])
+    idx, _, nx = outs[0]
+    srt = torch.sort(idx.long(), dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                      # distinct samples (the scenes have no duplicate points)
+    # distance of sample k to the nearest earlier sample = its running distance when it was selected: non-increasing in k
+    sel = nx[0].double()
+    d = torch.cdist(sel[:512], sel[:512]).square()
+    tri = torch.tril(torch.ones_like(d, dtype=torch.bool), diagonal=-1)
+    near = torch.where(tri, d, torch.full_like(d, float("inf"))).min(dim=1).values[1:]
+    assert bool((near[1:] <= near[:-1] * (1 + 1e-6)).all())
 
 
 BQ_CASES = [
