@@ -96,6 +96,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -126,6 +134,22 @@ __device__ __forceinline__ float pool_scatter(float (&v)[G], int lane) {
       const float send = upper ? v[i] : v[i + h];
       const float keep = upper ? v[i + h] : v[i];
       v[i] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, send, h));
+    }
+  }
+  return v[0];
+}
+
+// The same over the EIGHT lanes that share lane % 4 (they differ in lane bits 2..4): eight values in, one out; the lane with
+// q = lane / 4 leaves with value index q.
+__device__ __forceinline__ float pool8_q(float (&v)[8], int lane) {
+#pragma unroll
+  for (int h = 4; h >= 1; h >>= 1) {
+    const bool upper = (lane & (h << 2)) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = upper ? v[i] : v[i + h];
+      const float keep = upper ? v[i + h] : v[i];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xFFFFFFFFu, send, h << 2));
     }
   }
   return v[0];
@@ -220,18 +244,23 @@ __global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_ker
   const int n = prm.n, c_feat = prm.c_feat;
   uint32_t phase_d = 0;
   // the neighbour index of this thread's row is fetched one tile ahead (it heads the gather's dependency chain)
-  auto load_idx = [&](int t) -> int {
-    const int cl = t / prm.tiles_per_cloud;
-    const int fl = (t - cl * prm.tiles_per_cloud) * kRows + row;
+  // (cloud, tile inside the cloud) of the current tile and of the one whose index is being prefetched are carried along
+  // instead of divided out per tile: the two integer divisions were 7 % of the SA1 launches' stall samples
+  auto load_idx = [&](int cl, int ti) -> int {
+    const int fl = ti * kRows + row;
     return fl < cols ? __ldg(prm.idx + (size_t)cl * cols + fl) : 0;
   };
-  int p_next = blockIdx.x < prm.n_tiles ? load_idx(blockIdx.x) : 0;
+  const int tpc = prm.tiles_per_cloud;
+  const int step_cl = (int)gridDim.x / tpc, step_ti = (int)gridDim.x - step_cl * tpc;     // one stride of the tile loop
+  int cloud = (int)blockIdx.x / tpc, t_in = (int)blockIdx.x - cloud * tpc;
+  int p_next = blockIdx.x < prm.n_tiles ? load_idx(cloud, t_in) : 0;
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-    const int cloud = tile / prm.tiles_per_cloud, t_in = tile - cloud * prm.tiles_per_cloud;
     const int flat = t_in * kRows + row;
     const bool valid = flat < cols;
     const int p = p_next;
-    if (tile + (int)gridDim.x < prm.n_tiles) p_next = load_idx(tile + (int)gridDim.x);
+    int cloud_n = cloud + step_cl, t_in_n = t_in + step_ti;
+    if (t_in_n >= tpc) { t_in_n -= tpc; ++cloud_n; }
+    if (tile + (int)gridDim.x < prm.n_tiles) p_next = load_idx(cloud_n, t_in_n);
     // ---- gather: [xyz[idx] - centre ; features[:, idx]] along this thread's TMEM lane.  Rows beyond the cloud
     // (last tile only) recompute point 0 against centre 0: finite values that never reach an output.
     if (prm.rows) {
@@ -378,22 +407,53 @@ __global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_ker
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int centre_local = row >> lg_ns;          // centre of this row inside the tile
       int c0 = 0;
-      if (ns >= 32) {
+      // 32 channels at a time through the 16x256b load shape (thread t receives rows {q, q + 8} of a 16-row half, q = t / 4, and
+      // the column pairs 8 g + 2 (t % 4) + {0, 1}, g < 4 -- probed with tools/tmem_ld_probe.cu): after two loads a thread holds
+      // FOUR rows of eight channels, so the first two levels of the max tree are plain FMNMX on its own registers and only the
+      // eight lanes that share t % 4 are left to combine -- 7 exchanges per 32 channels instead of 31 (52 instructions for
+      // 124; the butterfly was a quarter of this kernel's instructions).
+      {
+        const uint32_t warp_acc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)prm.tm_r3;
+        const int q = lane >> 2;
+        const int ch_in_block = 8 * (q >> 1) + 2 * (lane & 3) + (q & 1);     // the channel this lane ends up with
+        const int warp_row0 = (warp & 3) * 32;
         for (; c0 + 32 <= prm.n3; c0 += 32) {
           if (kHalves > 1 && ((c0 >> 5) & (kHalves - 1)) != half) continue;     // warp-uniform: the shares take alternate channel groups
           uint32_t ra[16], rb[16];
-          tmem_ld16(acc + (uint32_t)c0, ra);
-          tmem_ld16(acc + (uint32_t)(c0 + 16), rb);
+          tmem_ld_16x256b_x4(warp_acc + (uint32_t)c0, ra);                       // rows 0..15 of this warp's lane quarter
+          tmem_ld_16x256b_x4(warp_acc + (16u << 16) + (uint32_t)c0, rb);         // rows 16..31
           tmem_ld_wait();
-          float v[32];
+          const int c = c0 + ch_in_block;
+          if (ns >= 32) {
+            float v[8];
 #pragma unroll
-          for (int t = 0; t < 16; ++t) { v[t] = __uint_as_float(ra[t]); v[16 + t] = __uint_as_float(rb[t]); }
-          const float mx = pool_scatter<32>(v, lane);
-          const int c = c0 + lane;
-          if (c < prm.c3) {
-            const unsigned u = __float_as_uint(fmaxf(mx + sh[c], 0.f));
-            if (ns == 32) s_pool[c * cpt + centre_local] = u;
-            else atomicMax(&s_pool[c * cpt + centre_local], u);   // >= 0: unsigned order == float order
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                v[2 * g + j] = fmaxf(fmaxf(__uint_as_float(ra[4 * g + j]), __uint_as_float(ra[4 * g + 2 + j])),
+                                     fmaxf(__uint_as_float(rb[4 * g + j]), __uint_as_float(rb[4 * g + 2 + j])));
+            const float mx = pool8_q(v, lane);
+            if (c < prm.c3) {
+              const int centre = warp_row0 >> lg_ns;
+              const unsigned u = __float_as_uint(fmaxf(mx + sh[c], 0.f));
+              if (ns == 32) s_pool[c * cpt + centre] = u;
+              else atomicMax(&s_pool[c * cpt + centre], u);   // >= 0: unsigned order == float order
+            }
+          } else {   // ns == 16: rows 0..15 and 16..31 are two centres
+            float va[8], vb[8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                va[2 * g + j] = fmaxf(__uint_as_float(ra[4 * g + j]), __uint_as_float(ra[4 * g + 2 + j]));
+                vb[2 * g + j] = fmaxf(__uint_as_float(rb[4 * g + j]), __uint_as_float(rb[4 * g + 2 + j]));
+              }
+            const float ma = pool8_q(va, lane), mb = pool8_q(vb, lane);
+            if (c < prm.c3) {
+              const int centre = warp_row0 >> 4;
+              s_pool[c * cpt + centre] = __float_as_uint(fmaxf(ma + sh[c], 0.f));
+              s_pool[c * cpt + centre + 1] = __float_as_uint(fmaxf(mb + sh[c], 0.f));
+            }
           }
         }
       }
@@ -460,6 +520,7 @@ __global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_ker
       }
       // (the next write to s_pool comes after three more __syncthreads)
     }
+    cloud = cloud_n; t_in = t_in_n;
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
