@@ -121,6 +121,20 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __device__ __forceinline__ uint32_t round_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
 
+// Epilogue of layers 1 and 2 for four accumulator values: + shift, ReLU, round to the nearest TF32 value (the tensor core ignores
+// the low 13 bits, so adding half a TF32 ulp to the bit pattern is the rounding).  Two packed FP32 adds (add.rn.f32x2) and one
+// fused integer add-and-max per value: max(bits + 0x1000, 0x1000) equals bits(max(v, 0)) + 0x1000 for every non-NaN v (negative
+// values have negative bit patterns); a NaN stays a NaN instead of becoming 0, as in the reference's ReLU.  Six instructions for
+// the twelve of FADD + FMNMX + IADD per value: the two epilogues were 20-30 % of this kernel's instructions.
+__device__ __forceinline__ void shift_relu_round4(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d, const float4 s4) {
+  const float2 p = __fadd2_rn(make_float2(__uint_as_float(a), __uint_as_float(b)), make_float2(s4.x, s4.y));
+  const float2 q = __fadd2_rn(make_float2(__uint_as_float(c), __uint_as_float(d)), make_float2(s4.z, s4.w));
+  a = (uint32_t)__viaddmax_s32(__float_as_int(p.x), 0x1000, 0x1000);
+  b = (uint32_t)__viaddmax_s32(__float_as_int(p.y), 0x1000, 0x1000);
+  c = (uint32_t)__viaddmax_s32(__float_as_int(q.x), 0x1000, 0x1000);
+  d = (uint32_t)__viaddmax_s32(__float_as_int(q.y), 0x1000, 0x1000);
+}
+
 // Butterfly max-reduction over the G lanes of a pooling group: every lane enters with G channel values of its own
 // row and leaves with ONE channel (index = lane % G) maximised over the G rows -- a reduce-scatter, G - 1 shuffles
 // for G channels instead of G full-warp reductions.
@@ -357,10 +371,7 @@ __global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_ker
 #pragma unroll
           for (int t = 0; t < 16; t += 4) {
             const float4 s4 = sh[(c0 + t) >> 2];
-            ra[t] = __float_as_uint(fmaxf(__uint_as_float(ra[t]) + s4.x, 0.f)) + 0x1000u;
-            ra[t + 1] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 1]) + s4.y, 0.f)) + 0x1000u;
-            ra[t + 2] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 2]) + s4.z, 0.f)) + 0x1000u;
-            ra[t + 3] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 3]) + s4.w, 0.f)) + 0x1000u;
+            shift_relu_round4(ra[t], ra[t + 1], ra[t + 2], ra[t + 3], s4);
           }
           tmem_st16(acc + (uint32_t)c0, ra);
         }
@@ -372,10 +383,7 @@ __global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_ker
 #pragma unroll
         for (int t = 0; t < 16; t += 4) {
           const float4 s4 = sh[(c0 + t) >> 2];
-          ra[t] = __float_as_uint(fmaxf(__uint_as_float(ra[t]) + s4.x, 0.f)) + 0x1000u;
-          ra[t + 1] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 1]) + s4.y, 0.f)) + 0x1000u;
-          ra[t + 2] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 2]) + s4.z, 0.f)) + 0x1000u;
-          ra[t + 3] = __float_as_uint(fmaxf(__uint_as_float(ra[t + 3]) + s4.w, 0.f)) + 0x1000u;
+          shift_relu_round4(ra[t], ra[t + 1], ra[t + 2], ra[t + 3], s4);
         }
         tmem_st16(acc + (uint32_t)c0, ra);
         if (c0 + 16 < nl) {
@@ -384,10 +392,7 @@ __global__ void __launch_bounds__(kThreads * kHalves, kMinCtas) sa_mlp_fused_ker
 #pragma unroll
           for (int t = 0; t < 16; t += 4) {
             const float4 s4 = sh[(c0 + 16 + t) >> 2];
-            rb[t] = __float_as_uint(fmaxf(__uint_as_float(rb[t]) + s4.x, 0.f)) + 0x1000u;
-            rb[t + 1] = __float_as_uint(fmaxf(__uint_as_float(rb[t + 1]) + s4.y, 0.f)) + 0x1000u;
-            rb[t + 2] = __float_as_uint(fmaxf(__uint_as_float(rb[t + 2]) + s4.z, 0.f)) + 0x1000u;
-            rb[t + 3] = __float_as_uint(fmaxf(__uint_as_float(rb[t + 3]) + s4.w, 0.f)) + 0x1000u;
+            shift_relu_round4(rb[t], rb[t + 1], rb[t + 2], rb[t + 3], s4);
           }
           tmem_st16(acc + (uint32_t)(c0 + 16), rb);
         }
