@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
       float *stage = reinterpret_cast<float *>(s_raw + (stage_base - smem_u32(s_raw)) + kStages * kStageBytes) + quarter * (32 * 36);
       const int co_base = m0 + ((quarter * 32) & (rows_per_copy - 1));
       const int srow = lane >> 3, scol = (lane & 7) * 4;
+      const uint32_t rnd_add = round_out ? 0x1000u : 0u, rnd_mask = round_out ? 0xFFFFE000u : 0xFFFFFFFFu;
+      const int rows_live = prm.c_out - co_base;       // channel rows of this warp that exist (may be <= 0 or > 32)
+      float *out_row0 = prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + co_base + srow) * prm.cols + col0 + scol;
       float st_sum = 0.f, st_sq = 0.f;
       for (int c = cbeg; c < cend && col0 + c < prm.cols; c += 32) {
         uint32_t r[32];
@@ -287,24 +290,37 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) mlp_layer_kernel(const _
             st_sq = fmaf(a, a, st_sq);
           }
         }
+        // + shift (packed FP32 adds), ReLU and rounding to the nearest TF32 (so that the next layer's tensor-core truncation is
+        // exact) as ONE fused integer add-max per value: max(bits + h, h) = bits(max(v, 0)) + h for every non-NaN v, h = half a
+        // TF32 ulp or 0 (negative floats have negative bit patterns); the flags are warp-uniform and tested once per chunk
+        // (ncu: the per-value flag tests and the two-instruction ReLU + add were a third of this kernel's instructions)
+        const float2 sh2 = make_float2(shift, shift);
+        if (relu) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float v = __uint_as_float(r[t]) + shift;
-          if (relu) v = fmaxf(v, 0.f);
-          // round to the nearest TF32 so that the next layer's tensor-core truncation is exact
-          r[t] = round_out ? ((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u) : __float_as_uint(v);
+          for (int t = 0; t < 32; t += 2) {
+            const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[t]), __uint_as_float(r[t + 1])), sh2);
+            r[t] = (uint32_t)__viaddmax_s32(__float_as_int(v.x), (int)rnd_add, (int)rnd_add) & rnd_mask;
+            r[t + 1] = (uint32_t)__viaddmax_s32(__float_as_int(v.y), (int)rnd_add, (int)rnd_add) & rnd_mask;
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[t]), __uint_as_float(r[t + 1])), sh2);
+            r[t] = (__float_as_uint(v.x) + rnd_add) & rnd_mask;
+            r[t + 1] = (__float_as_uint(v.y) + rnd_add) & rnd_mask;
+          }
         }
 #pragma unroll
         for (int t = 0; t < 32; t += 4)
           *reinterpret_cast<uint4 *>(stage + lane * 36 + t) = make_uint4(r[t], r[t + 1], r[t + 2], r[t + 3]);
         __syncwarp();
         if (col0 + c + scol < prm.cols) {
+          float *dst = out_row0 + c;                    // row srow of this warp's 32 channels, this lane's four columns
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int row = k * 4 + srow;
             const uint4 val = *reinterpret_cast<const uint4 *>(stage + row * 36 + scol);
-            if (co_base + row < prm.c_out)
-              __stcs(reinterpret_cast<uint4 *>(prm.out + ((size_t)cloud * prm.out_ctot + prm.out_coff + co_base + row) * prm.cols + col0 + c + scol), val);
+            if (row < rows_live) __stcs(reinterpret_cast<uint4 *>(dst + (size_t)(k * 4) * prm.cols), val);
           }
         }
         __syncwarp();
