@@ -27,7 +27,8 @@ struct Best3 {
 
 // (d, k) is inserted if it precedes a kept pair in (distance, index) order
 __device__ __forceinline__ void insert3(Best3 &b, float d, int k) {
-  if (d < b.d3 || (d == b.d3 && k < b.i3)) {
+  // cheap reject first (one compare for the common case; NaN fails it): half of this kernel's instructions were this cascade
+  if (d <= b.d3 && (d < b.d3 || k < b.i3)) {
     if (d < b.d1 || (d == b.d1 && k < b.i1)) {
       b.d3 = b.d2; b.i3 = b.i2; b.d2 = b.d1; b.i2 = b.i1; b.d1 = d; b.i1 = k;
     } else if (d < b.d2 || (d == b.d2 && k < b.i2)) {
