@@ -305,6 +305,13 @@ def run_gpu(args):
     hosts = [host, host_b]
     resident = host.to(dev)
     residents = [resident, host_b.to(dev)]
+    # --l2 inputs: no flush kernel; the streamed legs rotate over 40 distinct batches (168 MB > the 126 MB L2) instead, so that no
+    # input is L2-resident when its turn comes again (the other way the timing rules allow; an A/B switch, `flush` is the default)
+    if args.l2 == "inputs":
+        for k in range(2, 40):
+            hosts.append(torch.from_numpy(synth.make_batch(BATCH, NPTS, first_scene=(k * world + rank) * BATCH)).pin_memory())
+            residents.append(hosts[-1].to(dev))
+    nb_in = len(hosts)
     steps, warm = args.steps, max(args.warmup, 3)
     look = max(1, args.inflight - 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -402,7 +409,7 @@ def run_gpu(args):
         s.record()
         runner_.fork()
         for j in range(min(look, n)):
-            runner_.submit(src[j % 2])
+            runner_.submit(src[j % nb_in])
 
         def consume(j):
             def fn(out):
@@ -415,11 +422,12 @@ def run_gpu(args):
         for j in range(n):
             fs = runner_.feature_streams
             st = torch.cuda.current_stream(dev) if fs is None else fs[runner_.tail % len(fs)]
-            with torch.cuda.stream(st):
-                flush_small.fill_(0)                              # in-stream L2 flush, inside the timed region
+            if args.l2 == "flush":
+                with torch.cuda.stream(st):
+                    flush_small.fill_(0)                          # in-stream L2 flush, inside the timed region
             runner_.complete(consume(j))
             if j + look < n:
-                runner_.submit(src[(j + look) % 2])
+                runner_.submit(src[(j + look) % nb_in])
         runner_.join()
         e.record()
         e.synchronize()
@@ -428,14 +436,14 @@ def run_gpu(args):
         ok = None
         if check is not None:
             got = pinned.to(dev) if from_host else sums
-            ok = all(bool(torch.equal(got[j], check[j % 2])) for j in range(n))
+            ok = all(bool(torch.equal(got[j], check[j % nb_in])) for j in range(n))
         return ms, ok
 
     timed_streamed(sr, warm + look, False, None)
     timed_streamed(sr, warm + look, True, None)
     ms_total, ok_resident = timed_streamed(sr, steps, False, plain_sums)
     last = sr.outputs[(sr.tail - 1) % sr.nbuf]
-    ok_full = bool(torch.equal(last, plain[(steps - 1) % 2]))
+    ok_full = bool(torch.equal(last, plain[(steps - 1) % nb_in]))
     ms_e2e, ok_host = timed_streamed(sr, steps, True, plain_sums)
     long_steps = max(steps, 200)
     if long_steps != steps:   # converged figure: fill / drain amortised over >= 200 batches (same closed accounting)
@@ -546,7 +554,8 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points_per_cloud": NPTS,
                        "timed_region": "exactly K batches between two device synchronisations; pipeline fill (the first "
                                        f"{look} coordinate phases) and drain are inside it; every stream joined before the end event",
-                       "l2": "flushed before every step, in-stream and inside the timed region (160 MiB write > 126 MB L2)",
+                       "l2": ("flushed before every step, in-stream and inside the timed region (160 MiB write > 126 MB L2)" if args.l2 == "flush"
+                              else "no flush kernel: the streamed legs rotate over 40 distinct input batches (168 MB > 126 MB L2)"),
                        "mlp": "tcgen05 TF32 inputs, FP32 accumulate (the class cuDNN uses for the reference's convolutions by default): "
                               "SA1 / SA2 one fused kernel per scale, other layers one launch per conv1x1+BN+ReLU[+max-pool]; "
                               "`fp32_exact` has the FP32 figure",
@@ -832,6 +841,8 @@ def main():
                     help="batches in flight: the coordinate phase (FPS, ball queries, stencils) runs N-1 batches ahead of the feature phase")
     ap.add_argument("--feature-streams", type=int, default=int(os.environ.get("WS3D_FEATURE_STREAMS", "2")),
                     help="streams the feature phases of consecutive batches alternate between")
+    ap.add_argument("--l2", default="flush", choices=["flush", "inputs"],
+                    help="streamed legs: 160 MiB L2 flush in-stream before every step (default), or 40 distinct input batches (> L2) and no flush")
     ap.add_argument("--cold-start", type=int, default=int(os.environ.get("WS3D_COLD_START", "2")),
                     help="batches submitted into a pipeline with fewer than this many in flight use the latency samplers (0 = never)")
     ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "100")),
