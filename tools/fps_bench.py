@@ -40,15 +40,14 @@ def main():
                       ("cluster", {"WS3D_FPS_BUCKET": "0", "WS3D_FPS_FLAT": "0"}), ("bucket", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "0"}),
                       ("smem", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1"}),
                       ("smem_single", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1", "WS3D_FPS_PAIR": "0"}),
-                      ("smem8x2", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1", "WS3D_FPS_SMEM_SHAPE": "1"}),
-                      ("smem4x4", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1", "WS3D_FPS_SMEM_SHAPE": "2"})]:
+                      ("smem8x2", {"WS3D_FPS_BUCKET": "1", "WS3D_FPS_SMEM": "1", "WS3D_FPS_PAIR": "0", "WS3D_FPS_SMEM_SHAPE": "1"})]:
         e = dict(os.environ); e.update(env)
         p = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True)
         if p.returncode:
             print(name, "FAILED", p.stderr[-2000:])
             continue
         res[name] = json.loads(p.stdout.strip().splitlines()[-1])
-    names = [k for k in ("auto", "flat", "cluster", "bucket", "smem", "smem_single", "smem8x2", "smem4x4") if k in res]
+    names = [k for k in ("auto", "flat", "cluster", "bucket", "smem", "smem_single", "smem8x2") if k in res]
     for i in range(len(res[names[0]])):
         a = res[names[0]][i]
         line = f"b={a['b']:3d} n={a['n']:6d} m={a['m']:5d} "
