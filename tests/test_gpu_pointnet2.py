@@ -39,6 +39,8 @@ FPS_CASES = [
     (80, 2048, 128, "uniform"), (76, 4096, 64, "grid"), (80, 5000, 300, "scene"), (76, 16384, 256, "scene"),
     # clusters of 2 / 4 CTAs with the one-level exchange (fps_flat_kernel): n > 4096
     (40, 5000, 300, "scene"), (3, 8192, 2048, "uniform"), (2, 6000, 700, "grid"), (30, 16384, 128, "scene"),
+    # automatic dispatch to the paired-sample shared-memory kernel: large clouds with fewer than 4 SMs each, small ones beyond the SM count
+    (40, 16384, 96, "scene"), (150, 2048, 64, "uniform"),
 ]
 
 

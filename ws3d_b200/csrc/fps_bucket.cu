@@ -364,7 +364,14 @@ bool fps_bucket_applicable(int b, int n, int m) {
   const int rt = fps_mode();
   const int mode = rt == 1 ? 1 : rt == 2 ? 0 : env_mode;
   if (mode == 0 || n < 2048 || n > 16384 || m < 64 || b < 1 || b > 65535) return false;
-  return mode == 1 || b * 2 > num_sms();
+  if (mode == 1) return true;
+  // automatic: against the cluster kernels of fps.cu measured at 4 / 2 / 1 SMs per cloud (profiles/r2_fps_bench.json, 16384 -> 4096:
+  // 2.11 / 2.23 / 3.09 ms for b = 16 / 32 / 64 against 2.15 ms for the paired-sample kernel on ONE SM per cloud; 4096 -> 1024:
+  // 0.40 ms at b = 16 and 0.50 at b = 96 against 0.54) -- large clouds switch as soon as a cloud gets fewer than 4 SMs, small
+  // ones only when there are more clouds than SMs
+  if (n > 8192) return b * 4 > num_sms();
+  if (n > 4096) return b * 2 > num_sms();
+  return b > num_sms();
 }
 
 int fps_bucket_launch(const FpsParams &prm, int b, cudaStream_t stream) {
