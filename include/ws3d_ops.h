@@ -63,10 +63,11 @@ int ws3d_release_scratch(int all);
  * latency-bound kernel of another batch (FPS) is meant to run beside it.  Returns the previous value. */
 int ws3d_set_sm_budget(int sms);
 /* How the calling thread's subsequent furthest-point-sampling launches trade latency for SMs:
- * 0 = automatic (default: thread-block clusters, 4 SMs per cloud, unless the batch leaves < 2 SMs per
- * cloud), 1 = throughput (for 2048 <= n <= 16384: Morton buckets with exact culling, running distances in
- * shared memory, SEVERAL CLOUDS PER SM -- two at 16384 points, eight at 4096: 1.5x the latency at an eighth
- * of the SM time -- for samplers that run beside other work, see ws3d_b200.graphs.StreamedBackboneRunner),
+ * 0 = automatic (default: thread-block clusters, 4 SMs per cloud, unless the batch leaves a large cloud fewer
+ * than that), 1 = throughput (for 2048 <= n <= 16384: Morton buckets with exact culling, running distances in
+ * shared memory, two samples per traversal of the latency chain when the second is provably the next one,
+ * SEVERAL CLOUDS PER SM -- two at 16384 points, eight at 4096: 1.25x the latency at an eighth of the SM time --
+ * for samplers that run beside other work, see ws3d_b200.graphs.StreamedBackboneRunner),
  * 2 = latency (never that kernel).  Results are bit-identical in every mode.  Returns the previous mode. */
 int ws3d_set_fps_mode(int mode);
 /* Clouds that share one CTA (= one SM) when the throughput sampler runs a batch of b clouds of n points under the calling
