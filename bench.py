@@ -845,7 +845,7 @@ def main():
                     help="streamed legs: 160 MiB L2 flush in-stream before every step (default), or 40 distinct input batches (> L2) and no flush")
     ap.add_argument("--cold-start", type=int, default=int(os.environ.get("WS3D_COLD_START", "2")),
                     help="batches submitted into a pipeline with fewer than this many in flight use the latency samplers (0 = never)")
-    ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "100")),
+    ap.add_argument("--sm-budget", type=int, default=int(os.environ.get("WS3D_SM_BUDGET", "116")),
                     help="SMs a persistent MLP kernel spreads over in the pipelined modes (0 = all)")
     args = ap.parse_args()
     if args.impl == "reference":
