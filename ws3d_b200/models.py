@@ -113,12 +113,42 @@ class Pointnet2MSG(nn.Module):
         that needs few SMs and no bandwidth, so a caller with a stream of batches runs it AHEAD of the feature phase,
         beside the previous batches' feature phases (graphs.StreamedBackboneRunner)."""
         xyz, features = self._break_up_pc(pointcloud)
-        l_xyz, idx = [xyz], []
-        for sa in self.SA_modules:
+        if not xyz.is_cuda or os.environ.get("WS3D_COORD_SIDE", "1") == "0":
+            l_xyz, idx = [xyz], []
+            for sa in self.SA_modules:
+                _, nx = pointnet2_utils.sample_and_gather(l_xyz[-1], sa.npoint)
+                idx.append(sa._neighbour_indices(l_xyz[-1], nx))
+                l_xyz.append(nx)
+            nn_ = [PointnetFPModule.interpolation_weights(l_xyz[i], l_xyz[i + 1]) for i in range(len(self.FP_modules))]
+            return {"xyz": l_xyz[1:], "idx": idx, "nn": nn_, "xyz0": xyz, "feat0": features}
+        # The sampling levels are one dependency chain (level k + 1 samples level k's samples); the ball queries and the
+        # interpolation stencils only hang off it.  They run on a side stream as soon as their level exists, so the phase is as long
+        # as its four FPS launches (what a batch that fills an empty pipeline waits for; in a full pipeline the order is irrelevant).
+        dev = xyz.device
+        main = torch.cuda.current_stream(dev)
+        side = self.__dict__.get("_coord_side_stream")
+        if side is None or side.device != dev:
+            side = self.__dict__["_coord_side_stream"] = torch.cuda.Stream(device=dev)
+        n_fp = len(self.FP_modules)
+        l_xyz, idx, nn_ = [xyz], [], [None] * n_fp
+        xyz.record_stream(side)
+        for k, sa in enumerate(self.SA_modules):
             _, nx = pointnet2_utils.sample_and_gather(l_xyz[-1], sa.npoint)
-            idx.append(sa._neighbour_indices(l_xyz[-1], nx))
+            nx.record_stream(side)
+            level_done = torch.cuda.Event()
+            level_done.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(level_done)
+                ind = sa._neighbour_indices(l_xyz[-1], nx)
+                for t in ind:
+                    t.record_stream(main)
+                idx.append(ind)
+                if k < n_fp:
+                    nn_[k] = PointnetFPModule.interpolation_weights(l_xyz[-1], nx)
+                    for t in nn_[k]:
+                        t.record_stream(main)
             l_xyz.append(nx)
-        nn_ = [PointnetFPModule.interpolation_weights(l_xyz[i], l_xyz[i + 1]) for i in range(len(self.FP_modules))]
+        main.wait_stream(side)
         return {"xyz": l_xyz[1:], "idx": idx, "nn": nn_, "xyz0": xyz, "feat0": features}
 
     def feature_phase(self, pointcloud: torch.Tensor, plan: dict):
