@@ -467,6 +467,11 @@ def run_gpu(args):
                 native.set_fps_mode(prev)
             return model.feature_phase(resident, plan)[1]
 
+    # one launch at a time on ONE stream for this pass (the per-scale streams of a set-abstraction layer and the side stream of the
+    # coordinate phase would overlap launches, and an event pair would then time the overlap, not the kernel)
+    serial_env = {"WS3D_SCALE_STREAMS": "0", "WS3D_COORD_SIDE": "0"}
+    saved_env = {k: os.environ.get(k) for k in serial_env}
+    os.environ.update(serial_env)
     for _ in range(2):
         step_eager_two_phase()
     prof_steps = min(steps, 20)
@@ -481,6 +486,11 @@ def run_gpu(args):
     t1.record()
     t1.synchronize()
     prof.unwrap()
+    for k, v in saved_env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
     ms_prof = t0.elapsed_time(t1)
     kernels = prof.summarize(prof_steps)
 
